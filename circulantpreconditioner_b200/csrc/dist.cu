@@ -1,0 +1,142 @@
+// dist.cu -- NCCL bootstrap and all-to-all (see dist.h).
+#include "dist.h"
+
+#include <dlfcn.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "plan.h"
+
+namespace cpc {
+
+namespace {
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef void *ncclComm_tt;
+typedef int ncclResult_tt;
+enum { NCCL_UINT8 = 1, NCCL_FLOAT32 = 7, NCCL_SUM = 0 };
+
+struct Api {
+    void *handle = nullptr;
+    ncclResult_tt (*GetUniqueId)(ncclUniqueId_t *) = nullptr;
+    ncclResult_tt (*CommInitRank)(ncclComm_tt *, int, ncclUniqueId_t, int) = nullptr;
+    ncclResult_tt (*CommDestroy)(ncclComm_tt) = nullptr;
+    ncclResult_tt (*GroupStart)() = nullptr;
+    ncclResult_tt (*GroupEnd)() = nullptr;
+    ncclResult_tt (*Send)(const void *, size_t, int, int, ncclComm_tt, cudaStream_t) = nullptr;
+    ncclResult_tt (*Recv)(void *, size_t, int, int, ncclComm_tt, cudaStream_t) = nullptr;
+    ncclResult_tt (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_tt, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_tt) = nullptr;
+    bool ok = false;
+};
+
+Api g_api;
+std::once_flag g_once;
+
+void load_api()
+{
+    const char *names[] = { "libnccl.so.2", "libnccl.so" };
+    for (const char *nm : names) {
+        g_api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_api.handle) break;
+    }
+    if (!g_api.handle) return;
+#define LOAD(field, sym)                                                   \
+    *(void **)(&g_api.field) = dlsym(g_api.handle, sym);                   \
+    if (!g_api.field) return;
+    LOAD(GetUniqueId, "ncclGetUniqueId")
+    LOAD(CommInitRank, "ncclCommInitRank")
+    LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(GroupStart, "ncclGroupStart")
+    LOAD(GroupEnd, "ncclGroupEnd")
+    LOAD(Send, "ncclSend")
+    LOAD(Recv, "ncclRecv")
+    LOAD(AllReduce, "ncclAllReduce")
+    LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+    g_api.ok = true;
+}
+
+int need_api()
+{
+    std::call_once(g_once, load_api);
+    if (!g_api.ok) {
+        set_error("NCCL not available: could not dlopen libnccl.so.2 (%s)", dlerror() ? dlerror() : "missing symbol");
+        return CPC_ERR_NCCL;
+    }
+    return CPC_OK;
+}
+
+int nccl_fail(ncclResult_tt r, const char *what)
+{
+    set_error("NCCL error in %s: %s", what, g_api.GetErrorString ? g_api.GetErrorString(r) : "?");
+    return CPC_ERR_NCCL;
+}
+#define CPC_NCCL(call)                                   \
+    do {                                                 \
+        ncclResult_tt _r = (call);                       \
+        if (_r != 0) return nccl_fail(_r, #call);        \
+    } while (0)
+}  // namespace
+
+int dist_unique_id(void *out128)
+{
+    int rc = need_api();
+    if (rc) return rc;
+    ncclUniqueId_t id;
+    CPC_NCCL(g_api.GetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return CPC_OK;
+}
+
+int dist_init(DistState &d, int nranks, int rank, const void *unique_id128, int device)
+{
+    d.nranks = nranks;
+    d.rank = rank;
+    if (nranks == 1) return CPC_OK;
+    if (!unique_id128) { set_error("multi-rank plan needs nccl_unique_id"); return CPC_ERR_ARG; }
+    int rc = need_api();
+    if (rc) return rc;
+    CPC_CUDA(cudaSetDevice(device));
+    ncclUniqueId_t id;
+    memcpy(&id, unique_id128, sizeof(id));
+    ncclComm_tt comm = nullptr;
+    CPC_NCCL(g_api.CommInitRank(&comm, nranks, id, rank));
+    d.comm = comm;
+    return CPC_OK;
+}
+
+void dist_destroy(DistState &d)
+{
+    if (d.comm && g_api.ok) g_api.CommDestroy((ncclComm_tt)d.comm);
+    d.comm = nullptr;
+}
+
+int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes, cudaStream_t stream)
+{
+    if (d.nranks == 1) {
+        CPC_CUDA(cudaMemcpyAsync(recv, send, chunk_bytes, cudaMemcpyDeviceToDevice, stream));
+        return CPC_OK;
+    }
+    CPC_NCCL(g_api.GroupStart());
+    for (int p = 0; p < d.nranks; ++p) {
+        CPC_NCCL(g_api.Send((const char *)send + (size_t)p * chunk_bytes, chunk_bytes, NCCL_UINT8, p,
+                            (ncclComm_tt)d.comm, stream));
+        CPC_NCCL(g_api.Recv((char *)recv + (size_t)p * chunk_bytes, chunk_bytes, NCCL_UINT8, p, (ncclComm_tt)d.comm,
+                            stream));
+    }
+    CPC_NCCL(g_api.GroupEnd());
+    return CPC_OK;
+}
+
+int dist_barrier(DistState &d, cudaStream_t stream)
+{
+    if (d.nranks == 1) return CPC_OK;
+    static thread_local float *buf = nullptr;
+    if (!buf) CPC_CUDA(cudaMalloc(&buf, sizeof(float)));
+    CPC_NCCL(g_api.AllReduce(buf, buf, 1, NCCL_FLOAT32, NCCL_SUM, (ncclComm_tt)d.comm, stream));
+    return CPC_OK;
+}
+
+}  // namespace cpc

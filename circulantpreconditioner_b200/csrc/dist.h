@@ -1,0 +1,26 @@
+// dist.h -- multi-rank plumbing: NCCL (dlopen'ed, so single-GPU use never needs it) all-to-all over NVLink.
+// The reference's counterpart is fftw-mpi's MPI_Alltoall inside PETSc MATFFTW when MatCreateFFT is given
+// PETSC_COMM_WORLD with more than one rank (reference src/PCSHELLFft_3D.cxx:35).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+namespace cpc {
+
+struct DistState {
+    int nranks = 1, rank = 0;
+    void *comm = nullptr;        // ncclComm_t
+};
+
+// Loads libnccl.so.2 on first use.  Returns CPC_OK or CPC_ERR_NCCL (message via cpc_last_error()).
+int dist_unique_id(void *out128);
+int dist_init(DistState &d, int nranks, int rank, const void *unique_id128, int device);
+void dist_destroy(DistState &d);
+// Rank r sends bytes [q*chunk_bytes, (q+1)*chunk_bytes) of `send` to rank q and receives rank s's chunk into
+// recv + s*chunk_bytes (grouped ncclSend/ncclRecv: NCCL 2.27 has no all-to-all entry point).
+int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes, cudaStream_t stream);
+// Stream-ordered barrier across ranks (1-element all-reduce).
+int dist_barrier(DistState &d, cudaStream_t stream);
+
+}  // namespace cpc

@@ -1,0 +1,256 @@
+// fft_pass.cuh -- one HBM pass of the circulant-preconditioner apply: a batch of 1-D Stockham FFTs.
+//
+// A pass transforms every line of one axis of the [nz][ny][nx][ncomp] array.  A CTA owns G "tiles"; a tile is
+// TX neighbouring lines (neighbouring in the direction that is contiguous in HBM, so that each warp-level
+// load/store touches full 32-byte sectors) times the N points of the line.  Thread (l, j) of a tile -- l = lane
+// within the TX lines, j = butterfly column in [0, N/E) -- keeps E = max radix points of its line in registers:
+//
+//   global --(coalesced vector loads)--> registers --radix-R0--> smem --radix-R1--> smem --radix-R2--> registers
+//
+// Stockham autosort (decimation in time): in the stage with radix R and p = product of the previous radices, the
+// butterfly jb reads x[jb + r N/R], multiplies by exp(-/+ 2 pi i r (jb mod p) / (pR)), does an R-point DFT and
+// writes y[(jb - jb mod p) R + (jb mod p) + r p].  With E/R butterflies jb = j + b N/E per thread, every stage
+// reads exactly the indices {j + (N/E) m, m < E}, and the last stage writes exactly those indices, so
+//   * the first stage loads straight from HBM and the last stage stores straight to HBM (no staging copy), and
+//   * in the fused middle pass the forward transform's outputs are, in registers, already the inputs of the
+//     backward transform's first stage: forward-z, the eigenvalue division and backward-z are ONE pass
+//     (reference src/FftLinearSolver_3D.c:170-184 does them as four full-array sweeps).
+//
+// Shared memory holds one [N][TX] tile per group, laid out so that the TX lanes of a line index are contiguous:
+// the 8 (fp64, TX=8) lanes of a quarter warp always hit 128 contiguous bytes -> conflict-free for any index.
+#pragma once
+#include "fft_core.cuh"
+
+namespace cpc {
+
+// Geometry of one pass (all in units of complex elements).
+struct PassGeom {
+    long long SI;         // stride between consecutive points of a line
+    long long SL;         // stride between the TX lines of a tile
+    long long B0, B1;     // tile t starts at (t / tiles_inner) * B1 + (t % tiles_inner) * B0
+    int tiles_inner;
+    int ntiles;
+    int lines_inner;      // number of valid lines along the SL direction per outer index (for partial tiles)
+    // Output side (equal to the input side except in the multi-rank y passes) and split addressing: with D > 0
+    // point i of a line lives at (i / D) * SC + (i % D) * S, i.e. the line is cut into per-destination-rank
+    // chunks (the "zero-pack" slab layout [q][z_loc][y_loc][x]).  sh = log2(D) or -1.
+    long long SIo, B0o, B1o;
+    long long SCi, SCo;
+    int Di, Do, shi, sho;
+    // symbol addressing (fused pass only): line index w = (t % tiles_inner) * TX + l decomposes as
+    //   c = w % ncomp, x = (w / ncomp) % nx, y = w / (ncomp * nx)
+    int ncomp, nx, ny;
+    int y0;               // global y of local y index 0 (multi-rank transposed slab)
+};
+
+enum PassMode { MODE_FWD = 0, MODE_INV = 1, MODE_FUSED_SEP = 2, MODE_FUSED_TABLE = 3, MODE_FUSED_WAVE = 4 };
+
+template <typename T> struct SymbolArgs {
+    // separable: Lambda = ax[x] + ay[y] + az[k]  (ay carries the "+1"), result scaled by `scale` = 1/N
+    const cplx_t<T> *ax, *ay, *az;
+    // table: precomputed scale / Lambda, same layout as the data
+    const cplx_t<T> *inv_table;
+    // wave: 1-D root tables exp(-2 pi i q / n) per axis
+    const cplx_t<T> *rx, *ry, *rz;
+    T c0, mux, muy, muz;
+    T scale;
+};
+
+__device__ __forceinline__ long long point_off(int i, long long S, int D, int sh, long long SC)
+{
+    if (D == 0) return (long long)i * S;
+    if (sh >= 0) return (long long)(i >> sh) * SC + (long long)(i & (D - 1)) * S;
+    return (long long)(i / D) * SC + (long long)(i % D) * S;
+}
+
+template <int A, int B> struct CMax { static constexpr int v = A > B ? A : B; };
+
+// ---------------------------------------------------------------------------------------------------------------
+// One Stockham stage on the register file.  v[] is indexed by m with point index j + TPL*m.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int N, int E, int R, int P, int DIR, bool TO_SMEM, int TX>
+__device__ __forceinline__ void stockham_stage(cplx_t<T> (&v)[E], int j, int l, cplx_t<T> *sm,
+                                               const cplx_t<T> *__restrict__ tw)
+{
+    using C = cplx_t<T>;
+    constexpr int TPL = N / E;
+    constexpr int NB = E / R;          // butterflies per thread in this stage
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int jb = j + b * TPL;
+        C u[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) u[r] = v[b + r * NB];
+        const int k = (P > 1) ? (jb & (P - 1)) : 0;
+        if (P > 1) {
+            constexpr int TWS = N / (P * R);   // table step: exp(-2 pi i r k / (P R)) = tw[r k TWS]
+#pragma unroll
+            for (int r = 1; r < R; ++r) u[r] = twmul<DIR>(u[r], tw[r * k * TWS]);
+        }
+        Butterfly<R, DIR, C>::run(u);
+        if (TO_SMEM) {
+            const int j0 = (jb - k) * R + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) sm[(j0 + r * P) * TX + l] = u[r];
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[b + r * NB] = u[r];
+        }
+    }
+}
+
+template <typename T, int N, int E, int TX>
+__device__ __forceinline__ void smem_gather(cplx_t<T> (&v)[E], int j, int l, const cplx_t<T> *sm)
+{
+    constexpr int TPL = N / E;
+#pragma unroll
+    for (int m = 0; m < E; ++m) v[m] = sm[(j + TPL * m) * TX + l];
+}
+
+// Full 1-D transform of the thread's line: registers -> registers (through shared memory).
+template <typename T, int N, int R0, int R1, int R2, int DIR, int TX>
+__device__ __forceinline__ void line_fft(cplx_t<T> (&v)[CMax<CMax<R0, R1>::v, R2>::v], int j, int l, cplx_t<T> *sm,
+                                         const cplx_t<T> *__restrict__ tw)
+{
+    constexpr int E = CMax<CMax<R0, R1>::v, R2>::v;
+    constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
+    if (NST == 1) {
+        stockham_stage<T, N, E, R0, 1, DIR, false, TX>(v, j, l, sm, tw);
+    } else if (NST == 2) {
+        stockham_stage<T, N, E, R0, 1, DIR, true, TX>(v, j, l, sm, tw);
+        __syncthreads();
+        smem_gather<T, N, E, TX>(v, j, l, sm);
+        stockham_stage<T, N, E, R1, R0, DIR, false, TX>(v, j, l, sm, tw);
+    } else {
+        stockham_stage<T, N, E, R0, 1, DIR, true, TX>(v, j, l, sm, tw);
+        __syncthreads();
+        smem_gather<T, N, E, TX>(v, j, l, sm);
+        __syncthreads();
+        stockham_stage<T, N, E, R1, R0, DIR, true, TX>(v, j, l, sm, tw);
+        __syncthreads();
+        smem_gather<T, N, E, TX>(v, j, l, sm);
+        stockham_stage<T, N, E, R2, R0 * R1, DIR, false, TX>(v, j, l, sm, tw);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Eigenvalue division, applied on the registers between the forward and the backward z transform.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int N, int E, int MODE>
+__device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int j, int w, long long gbase_l, long long SI,
+                                             const PassGeom &g, const SymbolArgs<T> &s)
+{
+    using C = cplx_t<T>;
+    constexpr int TPL = N / E;
+    if (MODE == MODE_FUSED_SEP) {
+        // Lambda[k,j,i] = 1 + lx cx[i] + ly cy[j] + lz cz[k]   (reference FftLinearSolver_3D.c:146-157)
+        const int x = w % g.nx, y = w / g.nx + g.y0;
+        const C a = cadd(s.ax[x], s.ay[y]);
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const C lam = cadd(a, s.az[j + TPL * m]);
+            v[m] = cmul(v[m], crecip_scaled<T>(lam, s.scale));   // b_hat / Diag (:174) and 1/size (:184)
+        }
+    } else if (MODE == MODE_FUSED_TABLE) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = cmul(v[m], s.inv_table[gbase_l + (long long)(j + TPL * m) * SI]);
+    } else if (MODE == MODE_FUSED_WAVE) {
+        // 4 consecutive lanes hold (p, rho0 u, rho0 v, rho0 w) of one cell.  Arrow-matrix Schur solve
+        // (blocks from reference src/WaveSystem.cxx:92-107):
+        //   p  = (r0 - sum_d i c0^2 s_d r_d / D_d) / (M00 + c0^2 sum_d s_d^2 / D_d),  y_d = (r_d - i s_d p) / D_d
+        const int c = w & 3;
+        const int x = (w >> 2) % g.nx, y = (w >> 2) / g.nx + g.y0;
+        const C rx = s.rx[x], ry = s.ry[y];
+        const T sx = -rx.y * s.mux, sy = -ry.y * s.muy;                    // mu_d sin(theta_d)
+        const T ox = ((T)1 - rx.x) * s.mux, oy = ((T)1 - ry.x) * s.muy;    // mu_d (1 - cos(theta_d))
+        const T c0 = s.c0, c02 = s.c0 * s.c0;
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const C rz = s.rz[j + TPL * m];
+            const T sz = -rz.y * s.muz, oz = ((T)1 - rz.x) * s.muz;
+            const T Dx = (T)1 + c0 * ox, Dy = (T)1 + c0 * oy, Dz = (T)1 + c0 * oz;
+            const T m00 = (T)1 + c0 * (ox + oy + oz);
+            const T den = m00 + c02 * (sx * sx / Dx + sy * sy / Dy + sz * sz / Dz);
+            const T sd = (c == 1) ? sx : (c == 2) ? sy : sz;
+            const T Dd = (c == 1) ? Dx : (c == 2) ? Dy : Dz;
+            // contribution of this lane to the numerator: c=0: r0 ; c=d: -i c0^2 s_d r_d / D_d
+            C t;
+            if (c == 0) t = v[m];
+            else {
+                const T f = c02 * sd / Dd;
+                t = mk<T>(v[m].y * f, -v[m].x * f);
+            }
+            t.x += __shfl_xor_sync(0xffffffffu, t.x, 1);
+            t.y += __shfl_xor_sync(0xffffffffu, t.y, 1);
+            t.x += __shfl_xor_sync(0xffffffffu, t.x, 2);
+            t.y += __shfl_xor_sync(0xffffffffu, t.y, 2);
+            const T inv = s.scale / den;
+            const C p = mk<T>(t.x * inv, t.y * inv);                       // already scaled by 1/N
+            if (c == 0) v[m] = p;
+            else {
+                // (r_d / N - i s_d p) / D_d
+                const T q = (T)1 / Dd;
+                v[m] = mk<T>((v[m].x * s.scale + sd * p.y) * q, (v[m].y * s.scale - sd * p.x) * q);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The pass kernel.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int N, int R0, int R1, int R2, int TX, int G, int MODE, int MINB>
+__global__ void __launch_bounds__((N / CMax<CMax<R0, R1>::v, R2>::v) * TX * G, MINB)
+fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
+                const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
+{
+    using C = cplx_t<T>;
+    constexpr int E = CMax<CMax<R0, R1>::v, R2>::v;
+    constexpr int TPL = N / E;
+    constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
+    static_assert(R0 * R1 * R2 == N, "radices must multiply to N");
+    static_assert(E % R0 == 0 && E % R1 == 0 && E % R2 == 0, "each radix must divide the register tile");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int tid = threadIdx.x;
+    const int l = tid % TX;
+    const int j = (tid / TX) % TPL;
+    const int grp = tid / (TX * TPL);
+    C *sm = reinterpret_cast<C *>(smem_raw) + (size_t)grp * (NST > 1 ? N * TX : 0);
+
+    const int t = blockIdx.x * G + grp;
+    const bool tile_ok = t < g.ntiles;
+    const int ti = tile_ok ? t % g.tiles_inner : 0;
+    const int to = tile_ok ? t / g.tiles_inner : 0;
+    const int w = ti * TX + l;                                   // line index along the SL direction
+    const bool active = tile_ok && (w < g.lines_inner);
+    const long long gbase = (long long)to * g.B1 + (long long)ti * g.B0 + (long long)l * g.SL;
+    const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)l * g.SL;
+
+    C v[E];
+    if (active) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = in[gbase + point_off(j + TPL * m, g.SI, g.Di, g.shi, g.SCi)];
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = mk<T>((T)0, (T)0);
+    }
+
+    if (MODE == MODE_FWD) {
+        line_fft<T, N, R0, R1, R2, -1, TX>(v, j, l, sm, tw);
+    } else if (MODE == MODE_INV) {
+        line_fft<T, N, R0, R1, R2, +1, TX>(v, j, l, sm, tw);
+    } else {
+        line_fft<T, N, R0, R1, R2, -1, TX>(v, j, l, sm, tw);
+        apply_symbol<T, N, E, MODE>(v, j, active ? w : 0, gbase, g.SI, g, sym);
+        if (NST > 1) __syncthreads();
+        line_fft<T, N, R0, R1, R2, +1, TX>(v, j, l, sm, tw);
+    }
+
+    if (active) {
+#pragma unroll
+        for (int m = 0; m < E; ++m) out[obase + point_off(j + TPL * m, g.SIo, g.Do, g.sho, g.SCo)] = v[m];
+    }
+}
+
+}  // namespace cpc

@@ -1,0 +1,56 @@
+// plan.h -- host-side plan object behind the C ABI (include/circulantpc.h).  Internal header.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/circulantpc.h"
+
+namespace cpc {
+
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define CPC_CUDA(call)                                                  \
+    do {                                                                \
+        cudaError_t _e = (call);                                        \
+        if (_e != cudaSuccess) return ::cpc::cuda_fail(_e, #call);      \
+    } while (0)
+
+// Slab bookkeeping shared by the multi-rank code and the pure-host ABI helpers.
+struct SlabRange { int start, count; };
+SlabRange slab_range(int n, int nranks, int rank);
+
+struct NcclApi;   // dlopen'ed NCCL entry points (dist.cu)
+
+// Type-erased plan; PlanT<T> (plan_impl.cuh) implements it for double / float.
+struct PlanBase {
+    cpc_plan_desc desc{};
+    cudaStream_t stream = nullptr;
+    int device = 0;
+    int symbol_kind = CPC_SYMBOL_NONE;
+    uint64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
+    virtual ~PlanBase() {}
+    virtual int init() = 0;
+    virtual int set_symbol_separable(const double *cx, const double *cy, const double *cz, double lx, double ly,
+                                     double lz) = 0;
+    virtual int set_symbol_transport(double lx, double ly, double lz) = 0;
+    virtual int set_symbol_diag(const void *diag, int mem_kind) = 0;
+    virtual int set_symbol_first_column(const void *col, int mem_kind) = 0;
+    virtual int set_symbol_wave(double c0, double mx, double my, double mz) = 0;
+    virtual int get_diag(void *diag, int mem_kind) = 0;
+    virtual int apply(const void *b, void *x, int mem_kind, float *pass_ms, int *npasses) = 0;
+    virtual int transform(const void *in, void *out, int mem_kind, int dir) = 0;
+    virtual int get_info(cpc_plan_info *info) = 0;
+};
+
+PlanBase *make_plan_f64();
+PlanBase *make_plan_f32();
+
+}  // namespace cpc
+
+struct cpc_plan_s {
+    cpc::PlanBase *impl;
+};

@@ -1,0 +1,797 @@
+// plan_impl.cuh -- PlanT<T>: set-up, pass scheduling and launches for one dtype (double or float).
+//
+// Reference behaviour being reproduced (all in /root/reference/src):
+//   set-up     FftLinearSolver_3D.c:80-164, 218-249 and PCSHELLFft_3D.cxx:26-84 (once; tables stay in HBM)
+//   apply      FftLinearSolver_3D.c:166-190 (solve_3D): forward DFT, divide by Diag, backward DFT, scale 1/size
+//   tear-down  PCSHELLFft_3D.cxx:86-99
+// Schedule of one apply on one GPU (5 HBM passes):
+//   Fx : b -> x      Fy : x -> x      [Fz . 1/(N Lambda) . Bz] : x -> x      By : x -> x      Bx : x -> x
+// Every pass is tile-disjoint (a tile is read completely before it is written), so all passes run in place on x
+// and b == x aliasing (tests/TransportEquationFFT_SphericalExplosion_impl_mpi.cxx:111) is safe.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <tuple>
+
+#include "dist.h"
+#include "fft_pass.cuh"
+#include "generic_pass.cuh"
+#include "plan.h"
+
+namespace cpc {
+
+// ------------------------------------------------------------------------------------------------
+// Fast-kernel registry
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct FastEntry {
+    void (*kern)(const cplx_t<T> *, cplx_t<T> *, const PassGeom, const cplx_t<T> *, const SymbolArgs<T>);
+    int threads;
+    size_t smem;
+    int g;
+};
+
+template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, tx, mode)
+
+template <typename T, int N, int R0, int R1, int R2, int TX, int G, int MINB, int MINBF = MINB>
+static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
+{
+    constexpr int E = CMax<CMax<R0, R1>::v, R2>::v;
+    constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
+    const int threads = (N / E) * TX * G;
+    const size_t smem = NST > 1 ? (size_t)G * N * TX * sizeof(cplx_t<T>) : 0;
+    m[FastKey<T>(N, TX, MODE_FWD)] = { fft_pass_kernel<T, N, R0, R1, R2, TX, G, MODE_FWD, MINB>, threads, smem, G };
+    m[FastKey<T>(N, TX, MODE_INV)] = { fft_pass_kernel<T, N, R0, R1, R2, TX, G, MODE_INV, MINB>, threads, smem, G };
+    m[FastKey<T>(N, TX, MODE_FUSED_SEP)] =
+        { fft_pass_kernel<T, N, R0, R1, R2, TX, G, MODE_FUSED_SEP, MINBF>, threads, smem, G };
+    m[FastKey<T>(N, TX, MODE_FUSED_TABLE)] =
+        { fft_pass_kernel<T, N, R0, R1, R2, TX, G, MODE_FUSED_TABLE, MINBF>, threads, smem, G };
+    m[FastKey<T>(N, TX, MODE_FUSED_WAVE)] =
+        { fft_pass_kernel<T, N, R0, R1, R2, TX, G, MODE_FUSED_WAVE, MINBF>, threads, smem, G };
+}
+
+template <typename T> struct FastRegistry;
+
+#ifdef CPC_INSTANTIATE_F64
+// fp64: a quarter warp (8 lanes x 16 B) covers one 128-byte row of the [N][8] tile.
+template <> struct FastRegistry<double> {
+    static constexpr int TX_WIDE = 8, TX_NARROW = 4;
+    static void fill(std::map<FastKey<double>, FastEntry<double>> &m)
+    {
+        //                        N   R0  R1  R2 TX   G  MINB [MINB of the fused kernels]
+        register_modes<double,   16, 16,  1,  1, 8, 16, 2>(m);
+        register_modes<double,   32,  8,  4,  1, 8,  8, 2>(m);
+        register_modes<double,   64,  8,  8,  1, 8,  4, 2>(m);
+        register_modes<double,  128, 16,  8,  1, 8,  4, 2>(m);
+        register_modes<double,  256, 16, 16,  1, 8,  2, 2>(m);
+        register_modes<double,  512,  8,  8,  8, 8,  1, 2, 1>(m);
+        register_modes<double, 1024, 16,  8,  8, 8,  1, 1>(m);
+        register_modes<double,   16, 16,  1,  1, 4, 32, 2>(m);
+        register_modes<double,   32,  8,  4,  1, 4, 16, 2>(m);
+        register_modes<double,   64,  8,  8,  1, 4,  8, 2>(m);
+        register_modes<double,  128, 16,  8,  1, 4,  8, 2>(m);
+        register_modes<double,  256, 16, 16,  1, 4,  4, 2>(m);
+        register_modes<double,  512,  8,  8,  8, 4,  2, 2, 1>(m);
+        register_modes<double, 1024, 16,  8,  8, 4,  2, 1>(m);
+        register_modes<double, 2048, 16, 16,  8, 4,  1, 1>(m);
+    }
+};
+
+#endif
+#ifdef CPC_INSTANTIATE_F32
+// fp32: 16 lanes x 8 B = one 128-byte row.
+template <> struct FastRegistry<float> {
+    static constexpr int TX_WIDE = 16, TX_NARROW = 4;
+    static void fill(std::map<FastKey<float>, FastEntry<float>> &m)
+    {
+        register_modes<float,   16, 16,  1,  1, 16,  8, 2>(m);
+        register_modes<float,   32,  8,  4,  1, 16,  4, 2>(m);
+        register_modes<float,   64,  8,  8,  1, 16,  2, 2>(m);
+        register_modes<float,  128, 16,  8,  1, 16,  2, 2>(m);
+        register_modes<float,  256, 16, 16,  1, 16,  1, 2>(m);
+        register_modes<float,  512, 16,  8,  4, 16,  1, 2>(m);
+        register_modes<float, 1024, 16,  8,  8, 16,  1, 1>(m);
+        register_modes<float,   16, 16,  1,  1,  4, 32, 2>(m);
+        register_modes<float,   32,  8,  4,  1,  4, 16, 2>(m);
+        register_modes<float,   64,  8,  8,  1,  4,  8, 2>(m);
+        register_modes<float,  128, 16,  8,  1,  4,  8, 2>(m);
+        register_modes<float,  256, 16, 16,  1,  4,  4, 2>(m);
+        register_modes<float,  512,  8,  8,  8,  4,  2, 2>(m);
+        register_modes<float, 1024, 16,  8,  8,  4,  2, 1>(m);
+        register_modes<float, 2048, 16, 16,  8,  4,  1, 1>(m);
+    }
+};
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Small set-up kernels
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void invert_table_kernel(const double2 *__restrict__ diag, cplx_t<T> *__restrict__ inv, long long n,
+                                    double scale)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double2 d = diag[i];
+        const double q = scale / (d.x * d.x + d.y * d.y);
+        inv[i] = mk<T>((T)(d.x * q), (T)(-d.y * q));
+    }
+}
+
+template <typename T>
+__global__ void invert_inplace_kernel(cplx_t<T> *__restrict__ tab, long long n, double scale)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const cplx_t<T> d = tab[i];
+        const double dx = d.x, dy = d.y;
+        const double q = scale / (dx * dx + dy * dy);
+        tab[i] = mk<T>((T)(dx * q), (T)(-dy * q));
+    }
+}
+
+// Diag[k,j,i] = ax[i] + ay[j] + az[k] from the double-precision 1-D tables (what ctx->Diag holds in the reference).
+__global__ void diag_from_separable_kernel(double2 *__restrict__ diag, const double2 *__restrict__ ax,
+                                           const double2 *__restrict__ ay, const double2 *__restrict__ az, int nx,
+                                           int ny, long long n);
+template <typename T>
+__global__ void diag_from_invtable_kernel(double2 *__restrict__ diag, const cplx_t<T> *__restrict__ inv, long long n,
+                                          double scale)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double dx = inv[i].x, dy = inv[i].y;
+        const double q = scale / (dx * dx + dy * dy);
+        diag[i] = make_double2(dx * q, -dy * q);
+    }
+}
+
+// exp(-2 pi i m / n) rounded from long double
+static inline void exact_root(long long m, long long n, double *re, double *im)
+{
+    m %= n;
+    const long double a = 2.0L * 3.141592653589793238462643383279502884L * (long double)m / (long double)n;
+    // use symmetries so that the classic points are exact
+    if (4 * m == n) { *re = 0.0; *im = -1.0; return; }
+    if (2 * m == n) { *re = -1.0; *im = 0.0; return; }
+    if (4 * m == 3 * n) { *re = 0.0; *im = 1.0; return; }
+    *re = (double)cosl(a);
+    *im = (double)(-sinl(a));
+}
+
+// ------------------------------------------------------------------------------------------------
+// PlanT
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct PlanT : PlanBase {
+    using C = cplx_t<T>;
+
+    struct AxisCfg {
+        bool fast = false;
+        int tx = 1;               // lanes per tile
+        int threads = 0;          // generic kernel block size
+        size_t smem_generic = 0;
+        FactorList fl{};
+    };
+
+    int n[3] = { 1, 1, 1 };
+    int nc = 1;
+    int nzl = 1, z0 = 0;          // local z slab
+    int nyl = 1, y0 = 0;          // local y range in the transposed distribution
+    long long nloc = 0;           // local elements (slab distribution)
+    long long ntot = 0;           // global number of cells * ncomp / ncomp (= nx*ny*nz)
+    std::map<FastKey<T>, FastEntry<T>> reg;
+    AxisCfg cfg[3];
+    C *tw[3] = { nullptr, nullptr, nullptr };
+
+    // symbol state
+    C *sym_tab[3] = { nullptr, nullptr, nullptr };       // ax, ay(+1), az in T
+    double2 *sym_tab64[3] = { nullptr, nullptr, nullptr };
+    C *inv_table = nullptr;
+    double wave_c0 = 0, wave_mu[3] = { 0, 0, 0 };
+
+    // host staging
+    C *dbuf = nullptr;
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
+    cudaEvent_t prof_ev[CPC_MAX_PASSES + 1] = {};
+    bool prof_ev_ok = false;
+
+    // multi-rank
+    DistState dist;
+    C *sendbuf = nullptr, *tbuf = nullptr;
+
+    ~PlanT() override
+    {
+        cudaSetDevice(device);
+        for (int a = 0; a < 3; ++a) {
+            if (tw[a]) cudaFree(tw[a]);
+            if (sym_tab[a]) cudaFree(sym_tab[a]);
+            if (sym_tab64[a]) cudaFree(sym_tab64[a]);
+        }
+        if (inv_table) cudaFree(inv_table);
+        if (dbuf) cudaFree(dbuf);
+        if (sendbuf) cudaFree(sendbuf);
+        if (tbuf) cudaFree(tbuf);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        for (auto e : chunk_ev) cudaEventDestroy(e);
+        if (prof_ev_ok)
+            for (auto e : prof_ev) cudaEventDestroy(e);
+        dist_destroy(dist);
+    }
+
+    // ---------------------------------------------------------------------------------------- init
+    int init() override
+    {
+        n[0] = desc.nx; n[1] = desc.ny; n[2] = desc.nz;
+        nc = desc.ncomp;
+        ntot = (long long)n[0] * n[1] * n[2];
+        const SlabRange zr = slab_range(n[2], desc.nranks, desc.rank);
+        const SlabRange yr = slab_range(n[1], desc.nranks, desc.rank);
+        nzl = zr.count; z0 = zr.start;
+        nyl = yr.count; y0 = yr.start;
+        if (desc.nranks == 1) { nyl = n[1]; y0 = 0; }
+        nloc = (long long)n[0] * n[1] * nzl * nc;
+        if (desc.nranks > 1 && (n[2] % desc.nranks != 0 || n[1] % desc.nranks != 0)) {
+            set_error("multi-rank plans need ny and nz divisible by nranks (ny=%d nz=%d nranks=%d)", n[1], n[2],
+                      desc.nranks);
+            return CPC_ERR_UNSUPPORTED;
+        }
+        FastRegistry<T>::fill(reg);
+
+        int dev_smem = 0;
+        CPC_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+
+        for (int a = 0; a < 3; ++a) {
+            // root table
+            std::vector<C> h(n[a]);
+            for (int m = 0; m < n[a]; ++m) {
+                double re, im;
+                exact_root(m, n[a], &re, &im);
+                h[m] = mk<T>((T)re, (T)im);
+            }
+            CPC_CUDA(cudaMalloc(&tw[a], sizeof(C) * n[a]));
+            CPC_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(C) * n[a], cudaMemcpyHostToDevice));
+
+            // kernel choice
+            AxisCfg &c = cfg[a];
+            // x lines: the TX lanes of a tile are different lines (scalar) or the 4 components of a cell (wave); a
+            // narrow tile leaves 32/TX consecutive points per warp, i.e. longer contiguous HBM segments per line.
+            int tx = (a == 0) ? FastRegistry<T>::TX_NARROW : FastRegistry<T>::TX_WIDE;
+            if (reg.find(FastKey<T>(n[a], tx, MODE_FWD)) == reg.end()) tx = FastRegistry<T>::TX_NARROW;
+            auto it = reg.find(FastKey<T>(n[a], tx, MODE_FWD));
+            if (it != reg.end() && it->second.smem <= (size_t)dev_smem) {
+                c.fast = true;
+                c.tx = tx;
+            } else {
+                c.fast = false;
+                c.fl.n = n[a];
+                c.fl.nfac = 0;
+                int rem = n[a];
+                for (int p = 2; rem > 1;) {
+                    if (rem % p == 0) {
+                        if (c.fl.nfac >= CPC_MAX_FACTORS) { set_error("too many factors"); return CPC_ERR_UNSUPPORTED; }
+                        c.fl.fac[c.fl.nfac++] = p;
+                        rem /= p;
+                    } else {
+                        ++p;
+                        if ((long long)p * p > rem) p = rem;
+                    }
+                }
+                int gtx = (a == 0 && nc == 4) ? 4 : 8;
+                while (gtx > ((nc == 4) ? 4 : 1) && 2ull * n[a] * gtx * sizeof(C) > (size_t)dev_smem) gtx >>= 1;
+                if (2ull * n[a] * gtx * sizeof(C) > (size_t)dev_smem) {
+                    set_error("axis length %d too long for the generic kernel", n[a]);
+                    return CPC_ERR_UNSUPPORTED;
+                }
+                c.tx = gtx;
+                c.smem_generic = 2ull * n[a] * gtx * sizeof(C);
+                long long work = (long long)n[a] * gtx;
+                c.threads = work >= 256 ? 256 : (int)((work + 31) / 32 * 32);
+            }
+        }
+        // opt in to large dynamic shared memory for every kernel we may launch
+        for (auto &kv : reg) {
+            if (kv.second.smem > 48 * 1024 && kv.second.smem <= (size_t)dev_smem)
+                CPC_CUDA(cudaFuncSetAttribute((const void *)kv.second.kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)kv.second.smem));
+        }
+        CPC_CUDA(cudaFuncSetAttribute((const void *)generic_pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      dev_smem));
+        CPC_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        if (desc.nranks > 1) {
+            int rc = dist_init(dist, desc.nranks, desc.rank, desc.nccl_unique_id, device);
+            if (rc) return rc;
+            CPC_CUDA(cudaMalloc(&sendbuf, sizeof(C) * nloc));
+            CPC_CUDA(cudaMalloc(&tbuf, sizeof(C) * nloc));
+        }
+        return CPC_OK;
+    }
+
+    // ------------------------------------------------------------------------------------ geometry
+    // Geometry of the pass along `axis` over z planes [zb, zb+zc) of an array with ny_ rows per plane.
+    // layout: 0 = slab [z][y][x][c] with ny rows; 1 = transposed [z_glob][y_loc][x][c] (axis 2 only).
+    PassGeom make_geom(int axis, int tx, int zb, int zc, int layout, long long *ptr_off) const
+    {
+        PassGeom g{};
+        const long long W = (long long)n[0] * nc;
+        const int rows = (layout == 1) ? nyl : n[1];
+        g.ncomp = nc; g.nx = n[0]; g.ny = rows; g.y0 = (layout == 1) ? y0 : 0;
+        *ptr_off = 0;
+        if (axis == 0) {
+            const long long lines = (long long)rows * zc;
+            *ptr_off = (long long)zb * rows * W;
+            if (nc == 1) {
+                g.SI = 1; g.SL = n[0];
+                g.tiles_inner = (int)((lines + tx - 1) / tx);
+                g.B0 = (long long)tx * n[0]; g.B1 = 0;
+                g.lines_inner = (int)lines;
+                g.ntiles = g.tiles_inner;
+            } else {
+                g.SI = nc; g.SL = 1;
+                g.tiles_inner = 1; g.B0 = 0; g.B1 = W;
+                g.lines_inner = nc;
+                g.ntiles = (int)lines;
+            }
+        } else if (axis == 1) {
+            *ptr_off = (long long)zb * rows * W;
+            g.SI = W; g.SL = 1;
+            g.tiles_inner = (int)((W + tx - 1) / tx);
+            g.B0 = tx; g.B1 = W * rows;
+            g.lines_inner = (int)W;
+            g.ntiles = g.tiles_inner * zc;
+        } else {
+            const long long inner = W * rows;
+            g.SI = inner; g.SL = 1;
+            g.tiles_inner = (int)((inner + tx - 1) / tx);
+            g.B0 = tx; g.B1 = 0;
+            g.lines_inner = (int)inner;
+            g.ntiles = g.tiles_inner;
+        }
+        g.SIo = g.SI; g.B0o = g.B0; g.B1o = g.B1;
+        g.SCi = g.SCo = 0; g.Di = g.Do = 0; g.shi = g.sho = -1;
+        return g;
+    }
+
+    // Multi-rank y pass: one side is the z-slab [z_loc][y][x][c], the other the per-destination chunked layout
+    // [q][z_loc][y_loc][x][c] (q = rank owning global y = q*nyl + y_loc after the transpose).
+    void make_split(PassGeom &g, bool split_out) const
+    {
+        const long long W = (long long)n[0] * nc;
+        int sh = -1;
+        for (int b = 0; b < 31; ++b)
+            if ((1 << b) == nyl) sh = b;
+        if (split_out) {
+            g.SIo = W; g.B0o = g.B0; g.B1o = (long long)nyl * W;
+            g.Do = nyl; g.sho = sh; g.SCo = (long long)nzl * nyl * W;
+        } else {
+            g.B1o = g.B1; g.B0o = g.B0; g.SIo = g.SI;
+            g.B1 = (long long)nyl * W;
+            g.Di = nyl; g.shi = sh; g.SCi = (long long)nzl * nyl * W;
+        }
+    }
+
+    SymbolArgs<T> symbol_args() const
+    {
+        SymbolArgs<T> s{};
+        s.ax = sym_tab[0]; s.ay = sym_tab[1]; s.az = sym_tab[2];
+        s.inv_table = inv_table;
+        s.rx = tw[0]; s.ry = tw[1]; s.rz = tw[2];
+        s.c0 = (T)wave_c0; s.mux = (T)wave_mu[0]; s.muy = (T)wave_mu[1]; s.muz = (T)wave_mu[2];
+        s.scale = (T)(1.0 / (double)ntot);
+        return s;
+    }
+
+    // Launch one pass.  `in`/`out` point at the start of the local array.
+    // split: 0 = none, 1 = store side chunked (forward y of a multi-rank plan), 2 = load side chunked (backward y)
+    int run_pass(int axis, int mode, const C *in, C *out, int zb, int zc, int layout, cudaStream_t st, int split = 0)
+    {
+        const AxisCfg &c = cfg[axis];
+        long long off = 0;
+        PassGeom g = make_geom(axis, c.tx, zb, zc, layout, &off);
+        if (split) make_split(g, split == 1);
+        if (g.ntiles <= 0) return CPC_OK;
+        const SymbolArgs<T> s = symbol_args();
+        if (c.fast) {
+            const FastEntry<T> &e = reg.at(FastKey<T>(n[axis], c.tx, mode));
+            const int grid = (g.ntiles + e.g - 1) / e.g;
+            e.kern<<<grid, e.threads, e.smem, st>>>(in + off, out + off, g, tw[axis], s);
+        } else {
+            generic_pass_kernel<T><<<g.ntiles, c.threads, c.smem_generic, st>>>(in + off, out + off, g, tw[axis], s,
+                                                                               c.fl, c.tx, mode);
+        }
+        ++launches;
+        CPC_CUDA(cudaGetLastError());
+        return CPC_OK;
+    }
+
+    int fused_mode() const
+    {
+        switch (symbol_kind) {
+        case CPC_SYMBOL_SEPARABLE: return MODE_FUSED_SEP;
+        case CPC_SYMBOL_TABLE: return MODE_FUSED_TABLE;
+        case CPC_SYMBOL_WAVE: return MODE_FUSED_WAVE;
+        default: return -1;
+        }
+    }
+
+    // ------------------------------------------------------------------------------------- symbols
+    int upload_tables(const std::vector<double2> (&h)[3])
+    {
+        for (int a = 0; a < 3; ++a) {
+            std::vector<C> ht(n[a]);
+            for (int m = 0; m < n[a]; ++m) ht[m] = mk<T>((T)h[a][m].x, (T)h[a][m].y);
+            if (!sym_tab[a]) CPC_CUDA(cudaMalloc(&sym_tab[a], sizeof(C) * n[a]));
+            if (!sym_tab64[a]) CPC_CUDA(cudaMalloc(&sym_tab64[a], sizeof(double2) * n[a]));
+            CPC_CUDA(cudaMemcpyAsync(sym_tab[a], ht.data(), sizeof(C) * n[a], cudaMemcpyHostToDevice, stream));
+            CPC_CUDA(cudaMemcpyAsync(sym_tab64[a], h[a].data(), sizeof(double2) * n[a], cudaMemcpyHostToDevice, stream));
+            CPC_CUDA(cudaStreamSynchronize(stream));
+        }
+        return CPC_OK;
+    }
+
+    int set_symbol_separable(const double *cx, const double *cy, const double *cz, double lx, double ly,
+                             double lz) override
+    {
+        if (nc != 1) { set_error("separable symbol needs ncomp == 1"); return CPC_ERR_ARG; }
+        const double *c[3] = { cx, cy, cz };
+        const double lam[3] = { lx, ly, lz };
+        std::vector<double2> h[3];
+        for (int a = 0; a < 3; ++a) {
+            if (!c[a]) { set_error("null eigenvalue table"); return CPC_ERR_ARG; }
+            h[a].resize(n[a]);
+            for (int m = 0; m < n[a]; ++m) {
+                h[a][m].x = lam[a] * c[a][2 * m] + (a == 1 ? 1.0 : 0.0);   // the "+1" (VecShift, :155) rides on y
+                h[a][m].y = lam[a] * c[a][2 * m + 1];
+            }
+        }
+        int rc = upload_tables(h);
+        if (rc) return rc;
+        symbol_kind = CPC_SYMBOL_SEPARABLE;
+        return CPC_OK;
+    }
+
+    int set_symbol_transport(double lx, double ly, double lz) override
+    {
+        // c = [1,-1,0..] (FftLinearSolver_3D.c:80-90)  =>  c_hat[q] = 1 - exp(-2 pi i q / n); n == 1 => 0
+        std::vector<double> ch[3];
+        for (int a = 0; a < 3; ++a) {
+            ch[a].assign(2 * (size_t)n[a], 0.0);
+            if (n[a] > 1)
+                for (int q = 0; q < n[a]; ++q) {
+                    double re, im;
+                    exact_root(q, n[a], &re, &im);
+                    ch[a][2 * q] = 1.0 - re;
+                    ch[a][2 * q + 1] = -im;
+                }
+        }
+        return set_symbol_separable(ch[0].data(), ch[1].data(), ch[2].data(), lx, ly, lz);
+    }
+
+    int ensure_inv_table()
+    {
+        if (!inv_table) CPC_CUDA(cudaMalloc(&inv_table, sizeof(C) * nloc));
+        return CPC_OK;
+    }
+
+    int set_symbol_diag(const void *diag, int mem_kind) override
+    {
+        if (desc.nranks != 1) { set_error("cpc_set_symbol_diag: single-rank plans only"); return CPC_ERR_UNSUPPORTED; }
+        if (!diag) { set_error("null diag"); return CPC_ERR_ARG; }
+        int rc = ensure_inv_table();
+        if (rc) return rc;
+        const long long cells = ntot;          // one eigenvalue per cell; replicated over components if ncomp > 1
+        if (nc != 1) { set_error("cpc_set_symbol_diag needs ncomp == 1"); return CPC_ERR_ARG; }
+        const double2 *d = (const double2 *)diag;
+        double2 *tmp = nullptr;
+        if (mem_kind == CPC_MEM_HOST) {
+            CPC_CUDA(cudaMalloc(&tmp, sizeof(double2) * cells));
+            CPC_CUDA(cudaMemcpyAsync(tmp, diag, sizeof(double2) * cells, cudaMemcpyHostToDevice, stream));
+            d = tmp;
+        }
+        invert_table_kernel<T><<<1184, 256, 0, stream>>>(d, inv_table, cells, 1.0 / (double)ntot);
+        ++launches;
+        CPC_CUDA(cudaGetLastError());
+        CPC_CUDA(cudaStreamSynchronize(stream));
+        if (tmp) cudaFree(tmp);
+        symbol_kind = CPC_SYMBOL_TABLE;
+        return CPC_OK;
+    }
+
+    int set_symbol_first_column(const void *col, int mem_kind) override
+    {
+        if (nc != 1) { set_error("first-column symbol needs ncomp == 1"); return CPC_ERR_ARG; }
+        if (!col) { set_error("null column"); return CPC_ERR_ARG; }
+        int rc = ensure_inv_table();
+        if (rc) return rc;
+        // Lambda = FFT3(col) lands in the layout the fused pass runs in (transposed for multi-rank plans).
+        rc = transform_impl((const C *)col, inv_table, mem_kind, -1, /*out_is_device=*/true);
+        if (rc) return rc;
+        invert_inplace_kernel<T><<<1184, 256, 0, stream>>>(inv_table, nloc, 1.0 / (double)ntot);
+        ++launches;
+        CPC_CUDA(cudaGetLastError());
+        CPC_CUDA(cudaStreamSynchronize(stream));
+        symbol_kind = CPC_SYMBOL_TABLE;
+        return CPC_OK;
+    }
+
+    int set_symbol_wave(double c0, double mx, double my, double mz) override
+    {
+        if (nc != 4) { set_error("wave symbol needs ncomp == 4"); return CPC_ERR_ARG; }
+        wave_c0 = c0;
+        // degenerate axes contribute nothing (their root table is [1]: sin = 0, 1 - cos = 0)
+        wave_mu[0] = mx; wave_mu[1] = my; wave_mu[2] = mz;
+        symbol_kind = CPC_SYMBOL_WAVE;
+        return CPC_OK;
+    }
+
+    int get_diag(void *diag, int mem_kind) override
+    {
+        if (desc.nranks != 1) { set_error("cpc_get_diag: single-rank plans only"); return CPC_ERR_UNSUPPORTED; }
+        if (symbol_kind != CPC_SYMBOL_SEPARABLE && symbol_kind != CPC_SYMBOL_TABLE) {
+            set_error("cpc_get_diag: no scalar symbol set");
+            return CPC_ERR_STATE;
+        }
+        double2 *d = (double2 *)diag, *tmp = nullptr;
+        if (mem_kind == CPC_MEM_HOST) {
+            CPC_CUDA(cudaMalloc(&tmp, sizeof(double2) * ntot));
+            d = tmp;
+        }
+        if (symbol_kind == CPC_SYMBOL_SEPARABLE)
+            diag_from_separable_kernel<<<1184, 256, 0, stream>>>(d, sym_tab64[0], sym_tab64[1], sym_tab64[2], n[0], n[1],
+                                                                 ntot);
+        else
+            diag_from_invtable_kernel<T><<<1184, 256, 0, stream>>>(d, inv_table, ntot, 1.0 / (double)ntot);
+        ++launches;
+        CPC_CUDA(cudaGetLastError());
+        if (tmp) {
+            CPC_CUDA(cudaMemcpyAsync(diag, tmp, sizeof(double2) * ntot, cudaMemcpyDeviceToHost, stream));
+            d2h_bytes += sizeof(double2) * ntot;
+        }
+        CPC_CUDA(cudaStreamSynchronize(stream));
+        if (tmp) cudaFree(tmp);
+        return CPC_OK;
+    }
+
+    // ------------------------------------------------------------------------------------ schedules
+    int ensure_dbuf()
+    {
+        if (!dbuf) CPC_CUDA(cudaMalloc(&dbuf, sizeof(C) * nloc));
+        return CPC_OK;
+    }
+
+    int ensure_prof_events()
+    {
+        if (!prof_ev_ok) {
+            for (auto &e : prof_ev) CPC_CUDA(cudaEventCreate(&e));
+            prof_ev_ok = true;
+        }
+        return CPC_OK;
+    }
+
+    // Single-rank apply on device pointers.  pass_ms != nullptr => record events around each pass.
+    int apply_device_single(const C *b, C *x, float *pass_ms, int *npasses)
+    {
+        const int fm = fused_mode();
+        int np = 0;
+        auto mark = [&](int i) -> int {
+            if (pass_ms) CPC_CUDA(cudaEventRecord(prof_ev[i], stream));
+            return CPC_OK;
+        };
+        if (pass_ms) { int rc = ensure_prof_events(); if (rc) return rc; }
+        int rc = mark(0);
+        if (rc) return rc;
+        const C *cur = b;
+        for (int a = 0; a < 2; ++a) {
+            if (n[a] == 1) continue;
+            if ((rc = run_pass(a, MODE_FWD, cur, x, 0, nzl, 0, stream))) return rc;
+            cur = x;
+            if ((rc = mark(++np))) return rc;
+        }
+        if ((rc = run_pass(2, fm, cur, x, 0, nzl, 0, stream))) return rc;
+        if ((rc = mark(++np))) return rc;
+        for (int a = 1; a >= 0; --a) {
+            if (n[a] == 1) continue;
+            if ((rc = run_pass(a, MODE_INV, x, x, 0, nzl, 0, stream))) return rc;
+            if ((rc = mark(++np))) return rc;
+        }
+        if (pass_ms) {
+            CPC_CUDA(cudaEventSynchronize(prof_ev[np]));
+            for (int i = 0; i < np; ++i) CPC_CUDA(cudaEventElapsedTime(&pass_ms[i], prof_ev[i], prof_ev[i + 1]));
+            if (npasses) *npasses = np;
+        }
+        return CPC_OK;
+    }
+
+    // Multi-rank (z-slab) apply: Fx, Fy(split store) | all-to-all | fused z | all-to-all | By(split load), Bx
+    int alltoall(const C *send, C *recv)
+    {
+        const size_t chunk = sizeof(C) * (size_t)(nloc / desc.nranks);
+        return dist_alltoall(dist, send, recv, chunk, stream);
+    }
+
+    int apply_device_dist(const C *b, C *x, float *pass_ms, int *npasses)
+    {
+        const int fm = fused_mode();
+        int np = 0, rc;
+        auto mark = [&](int i) -> int {
+            if (pass_ms) CPC_CUDA(cudaEventRecord(prof_ev[i], stream));
+            return CPC_OK;
+        };
+        if (pass_ms && (rc = ensure_prof_events())) return rc;
+        if ((rc = mark(0))) return rc;
+        const C *cur = b;
+        if (n[0] > 1) {
+            if ((rc = run_pass(0, MODE_FWD, cur, x, 0, nzl, 0, stream))) return rc;
+            cur = x;
+            if ((rc = mark(++np))) return rc;
+        }
+        if ((rc = run_pass(1, MODE_FWD, cur, sendbuf, 0, nzl, 0, stream, 1))) return rc;     // Fy, chunked store
+        if ((rc = mark(++np))) return rc;
+        if ((rc = alltoall(sendbuf, tbuf))) return rc;                                       // z-slab -> y-slab
+        if ((rc = mark(++np))) return rc;
+        if ((rc = run_pass(2, fm, tbuf, tbuf, 0, n[2], 1, stream))) return rc;               // Fz . 1/(N Lambda) . Bz
+        if ((rc = mark(++np))) return rc;
+        if ((rc = alltoall(tbuf, sendbuf))) return rc;                                       // y-slab -> z-slab
+        if ((rc = mark(++np))) return rc;
+        if ((rc = run_pass(1, MODE_INV, sendbuf, x, 0, nzl, 0, stream, 2))) return rc;       // By, chunked load
+        if ((rc = mark(++np))) return rc;
+        if (n[0] > 1) {
+            if ((rc = run_pass(0, MODE_INV, x, x, 0, nzl, 0, stream))) return rc;
+            if ((rc = mark(++np))) return rc;
+        }
+        if (pass_ms) {
+            CPC_CUDA(cudaEventSynchronize(prof_ev[np]));
+            for (int i = 0; i < np; ++i) CPC_CUDA(cudaEventElapsedTime(&pass_ms[i], prof_ev[i], prof_ev[i + 1]));
+            if (npasses) *npasses = np;
+        }
+        return CPC_OK;
+    }
+
+    // forward: in = z-slab, out = transposed (all z, local y range); backward: the reverse
+    int transform_device_dist(const C *in, C *out, int dir)
+    {
+        int rc;
+        if (dir < 0) {
+            const C *cur = in;
+            if (n[0] > 1) {
+                if ((rc = run_pass(0, MODE_FWD, cur, tbuf, 0, nzl, 0, stream))) return rc;
+                cur = tbuf;
+            }
+            if ((rc = run_pass(1, MODE_FWD, cur, sendbuf, 0, nzl, 0, stream, 1))) return rc;
+            if ((rc = alltoall(sendbuf, tbuf))) return rc;
+            if ((rc = run_pass(2, MODE_FWD, tbuf, out, 0, n[2], 1, stream))) return rc;
+        } else {
+            if ((rc = run_pass(2, MODE_INV, in, tbuf, 0, n[2], 1, stream))) return rc;
+            if ((rc = alltoall(tbuf, sendbuf))) return rc;
+            if ((rc = run_pass(1, MODE_INV, sendbuf, out, 0, nzl, 0, stream, 2))) return rc;
+            if (n[0] > 1 && (rc = run_pass(0, MODE_INV, out, out, 0, nzl, 0, stream))) return rc;
+        }
+        return CPC_OK;
+    }
+
+    // Host pointers, single rank: z-chunked pipeline so the PCIe copies overlap the x/y passes.
+    int apply_host_single(const C *b, C *x)
+    {
+        int rc = ensure_dbuf();
+        if (rc) return rc;
+        const int fm = fused_mode();
+        const long long plane = (long long)n[0] * n[1] * nc;
+        int nchunk = nzl < 8 ? nzl : 8;
+        if (plane * nzl * (long long)sizeof(C) < (4ll << 20)) nchunk = 1;
+        while ((int)chunk_ev.size() < 2 * nchunk) {
+            cudaEvent_t e;
+            CPC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            chunk_ev.push_back(e);
+        }
+        // make the copy stream wait for whatever the caller queued on the plan stream before
+        CPC_CUDA(cudaEventRecord(chunk_ev[0], stream));
+        CPC_CUDA(cudaStreamWaitEvent(copy_stream, chunk_ev[0], 0));
+        for (int c = 0; c < nchunk; ++c) {
+            const int zb = (int)((long long)nzl * c / nchunk), ze = (int)((long long)nzl * (c + 1) / nchunk);
+            const long long off = plane * zb, cnt = plane * (ze - zb);
+            CPC_CUDA(cudaMemcpyAsync(dbuf + off, b + off, sizeof(C) * cnt, cudaMemcpyHostToDevice, copy_stream));
+            h2d_bytes += sizeof(C) * cnt;
+            CPC_CUDA(cudaEventRecord(chunk_ev[c], copy_stream));
+            CPC_CUDA(cudaStreamWaitEvent(stream, chunk_ev[c], 0));
+            for (int a = 0; a < 2; ++a)
+                if (n[a] > 1 && (rc = run_pass(a, MODE_FWD, dbuf, dbuf, zb, ze - zb, 0, stream))) return rc;
+        }
+        if ((rc = run_pass(2, fm, dbuf, dbuf, 0, nzl, 0, stream))) return rc;
+        for (int c = 0; c < nchunk; ++c) {
+            const int zb = (int)((long long)nzl * c / nchunk), ze = (int)((long long)nzl * (c + 1) / nchunk);
+            const long long off = plane * zb, cnt = plane * (ze - zb);
+            for (int a = 1; a >= 0; --a)
+                if (n[a] > 1 && (rc = run_pass(a, MODE_INV, dbuf, dbuf, zb, ze - zb, 0, stream))) return rc;
+            CPC_CUDA(cudaEventRecord(chunk_ev[nchunk + c], stream));
+            CPC_CUDA(cudaStreamWaitEvent(copy_stream, chunk_ev[nchunk + c], 0));
+            CPC_CUDA(cudaMemcpyAsync(x + off, dbuf + off, sizeof(C) * cnt, cudaMemcpyDeviceToHost, copy_stream));
+            d2h_bytes += sizeof(C) * cnt;
+        }
+        CPC_CUDA(cudaStreamSynchronize(copy_stream));
+        return CPC_OK;
+    }
+
+    int apply(const void *b, void *x, int mem_kind, float *pass_ms, int *npasses) override
+    {
+        if (fused_mode() < 0) { set_error("cpc_apply: no symbol set (call cpc_set_symbol_* first)"); return CPC_ERR_STATE; }
+        if (!b || !x) { set_error("cpc_apply: null pointer"); return CPC_ERR_ARG; }
+        CPC_CUDA(cudaSetDevice(device));
+        if (mem_kind == CPC_MEM_DEVICE) {
+            if (desc.nranks == 1) return apply_device_single((const C *)b, (C *)x, pass_ms, npasses);
+            return apply_device_dist((const C *)b, (C *)x, pass_ms, npasses);
+        }
+        if (mem_kind != CPC_MEM_HOST) { set_error("bad mem_kind %d", mem_kind); return CPC_ERR_ARG; }
+        if (pass_ms) { set_error("profiled apply needs device pointers"); return CPC_ERR_ARG; }
+        if (desc.nranks == 1) return apply_host_single((const C *)b, (C *)x);
+        // multi-rank host pointers: stage the local slab
+        int rc = ensure_dbuf();
+        if (rc) return rc;
+        CPC_CUDA(cudaMemcpyAsync(dbuf, b, sizeof(C) * nloc, cudaMemcpyHostToDevice, stream));
+        h2d_bytes += sizeof(C) * nloc;
+        if ((rc = apply_device_dist(dbuf, dbuf, nullptr, nullptr))) return rc;
+        CPC_CUDA(cudaMemcpyAsync(x, dbuf, sizeof(C) * nloc, cudaMemcpyDeviceToHost, stream));
+        d2h_bytes += sizeof(C) * nloc;
+        CPC_CUDA(cudaStreamSynchronize(stream));
+        return CPC_OK;
+    }
+
+    // Plain transforms (MatMult / MatMultTranspose of the reference, FftLinearSolver_3D.c:170,180)
+    int transform_impl(const C *in, C *out, int mem_kind, int dir, bool out_is_device)
+    {
+        CPC_CUDA(cudaSetDevice(device));
+        const C *din = in;
+        C *dout = out;
+        int rc;
+        if (mem_kind == CPC_MEM_HOST) {
+            if ((rc = ensure_dbuf())) return rc;
+            CPC_CUDA(cudaMemcpyAsync(dbuf, in, sizeof(C) * nloc, cudaMemcpyHostToDevice, stream));
+            h2d_bytes += sizeof(C) * nloc;
+            din = dbuf;
+            if (!out_is_device) dout = dbuf;
+        }
+        if (desc.nranks > 1) {
+            if ((rc = transform_device_dist(din, dout, dir))) return rc;
+        } else {
+            const int mode = dir < 0 ? MODE_FWD : MODE_INV;
+            const C *cur = din;
+            int done = 0;
+            for (int a = 0; a < 3; ++a) {
+                if (n[a] == 1) continue;
+                if ((rc = run_pass(a, mode, cur, dout, 0, nzl, 0, stream))) return rc;
+                cur = dout;
+                ++done;
+            }
+            if (!done && cur != dout)
+                CPC_CUDA(cudaMemcpyAsync(dout, cur, sizeof(C) * nloc, cudaMemcpyDeviceToDevice, stream));
+        }
+        if (mem_kind == CPC_MEM_HOST && !out_is_device) {
+            CPC_CUDA(cudaMemcpyAsync(out, dbuf, sizeof(C) * nloc, cudaMemcpyDeviceToHost, stream));
+            d2h_bytes += sizeof(C) * nloc;
+            CPC_CUDA(cudaStreamSynchronize(stream));
+        }
+        return CPC_OK;
+    }
+
+    int transform(const void *in, void *out, int mem_kind, int dir) override
+    {
+        if (!in || !out) { set_error("null pointer"); return CPC_ERR_ARG; }
+        if (mem_kind != CPC_MEM_DEVICE && mem_kind != CPC_MEM_HOST) { set_error("bad mem_kind"); return CPC_ERR_ARG; }
+        return transform_impl((const C *)in, (C *)out, mem_kind, dir, false);
+    }
+
+    int get_info(cpc_plan_info *info) override
+    {
+        memset(info, 0, sizeof(*info));
+        info->nx = n[0]; info->ny = n[1]; info->nz = n[2];
+        info->ncomp = nc; info->dtype = desc.dtype;
+        info->nranks = desc.nranks; info->rank = desc.rank;
+        info->symbol_kind = symbol_kind;
+        info->passes_per_apply = 1 + 2 * ((n[0] > 1) + (n[1] > 1));
+        for (int a = 0; a < 3; ++a) info->fast_path[a] = cfg[a].fast ? 1 : 0;
+        info->local_elems = nloc;
+        info->bytes_per_apply_alg = 5ll * 2 * nloc * (long long)sizeof(C);
+        info->kernel_launches = launches;
+        info->h2d_bytes = h2d_bytes;
+        info->d2h_bytes = d2h_bytes;
+        return CPC_OK;
+    }
+};
+
+}  // namespace cpc

@@ -1,0 +1,157 @@
+"""CirculantPlan: thin object wrapper over the cpc_* C ABI (include/circulantpc.h).
+
+Mirrors the life cycle of the reference's ``FFTPrecTransportContext`` (src/PCSHELLFft_3D.hxx:8-21):
+create (== ``setupFFTPrec3D``), set the eigenvalues once, ``apply`` per Krylov iteration
+(== ``applyFFT3DPrecTransport`` -> ``solve_3D``), ``destroy`` (== ``destroyFFTPrec3D``).
+Arrays may be torch tensors (CUDA, or CPU -- ideally pinned) or numpy arrays (host).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import CpcError, MEM_DEVICE, MEM_HOST, check, lib
+
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def nccl_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(_lib.CPC_NCCL_UNIQUE_ID_BYTES)
+    check(lib().cpc_nccl_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+    return buf.raw
+
+
+def slab_range(n, nranks, rank):
+    s, c = ctypes.c_int(), ctypes.c_int()
+    check(lib().cpc_slab_range(n, nranks, rank, ctypes.byref(s), ctypes.byref(c)))
+    return s.value, c.value
+
+
+def _ptr_and_kind(a, writable=False):
+    """(address, mem_kind, keepalive) of a torch tensor or numpy array."""
+    if torch is not None and isinstance(a, torch.Tensor):
+        if not a.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return a.data_ptr(), (MEM_DEVICE if a.is_cuda else MEM_HOST), a
+    if isinstance(a, np.ndarray):
+        if not a.flags.c_contiguous:
+            raise ValueError("array must be C-contiguous")
+        if writable and not a.flags.writeable:
+            raise ValueError("output array is read-only")
+        return a.ctypes.data, MEM_HOST, a
+    raise TypeError(f"unsupported array type {type(a)}")
+
+
+class CirculantPlan:
+    def __init__(self, nx, ny=1, nz=1, ncomp=1, dtype="c128", stream=None, device=-1, nranks=1, rank=0,
+                 nccl_id: bytes | None = None):
+        self._h = ctypes.c_void_p()
+        self.nx, self.ny, self.nz, self.ncomp = int(nx), int(ny), int(nz), int(ncomp)
+        self.dtype = dtype
+        self.np_dtype = np.complex128 if dtype == "c128" else np.complex64
+        self._id_buf = ctypes.create_string_buffer(nccl_id, len(nccl_id)) if nccl_id else None
+        if stream is None and torch is not None and torch.cuda.is_available():
+            stream = torch.cuda.current_stream().cuda_stream
+        d = _lib.PlanDesc(self.nx, self.ny, self.nz, self.ncomp, _lib.DTYPES[dtype], int(nranks), int(rank),
+                          ctypes.cast(self._id_buf, ctypes.c_void_p) if self._id_buf else None,
+                          ctypes.c_void_p(stream or 0), int(device))
+        check(lib().cpc_plan_create(ctypes.byref(self._h), ctypes.byref(d)))
+
+    # -- life cycle ----------------------------------------------------------------------------
+    def destroy(self):
+        if self._h:
+            lib().cpc_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.destroy()
+
+    def set_stream(self, stream):
+        check(lib().cpc_set_stream(self._h, ctypes.c_void_p(stream or 0)))
+
+    def sync(self):
+        check(lib().cpc_sync(self._h))
+
+    # -- eigenvalue set-up ----------------------------------------------------------------------
+    def set_symbol_transport(self, lambda_x, lambda_y=0.0, lambda_z=0.0):
+        check(lib().cpc_set_symbol_transport(self._h, lambda_x, lambda_y, lambda_z))
+
+    def set_symbol_separable(self, cx_hat, cy_hat, cz_hat, lambda_x, lambda_y, lambda_z):
+        tabs = [np.ascontiguousarray(t, dtype=np.complex128) for t in (cx_hat, cy_hat, cz_hat)]
+        for t, n in zip(tabs, (self.nx, self.ny, self.nz)):
+            if t.size != n:
+                raise ValueError("eigenvalue table has the wrong length")
+        p = [t.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) for t in tabs]
+        check(lib().cpc_set_symbol_separable(self._h, p[0], p[1], p[2], lambda_x, lambda_y, lambda_z))
+
+    def set_symbol_diag(self, diag):
+        ptr, kind, keep = _ptr_and_kind(diag)
+        check(lib().cpc_set_symbol_diag(self._h, ctypes.c_void_p(ptr), kind))
+
+    def set_symbol_first_column(self, col):
+        ptr, kind, keep = _ptr_and_kind(col)
+        check(lib().cpc_set_symbol_first_column(self._h, ctypes.c_void_p(ptr), kind))
+
+    def set_symbol_wave(self, c0, mu_x, mu_y, mu_z):
+        check(lib().cpc_set_symbol_wave(self._h, c0, mu_x, mu_y, mu_z))
+
+    def get_diag(self):
+        out = np.empty(self.nx * self.ny * self.nz, dtype=np.complex128)
+        check(lib().cpc_get_diag(self._h, ctypes.c_void_p(out.ctypes.data), MEM_HOST))
+        return out
+
+    # -- hot path -----------------------------------------------------------------------------------
+    def _call(self, fn, src, dst):
+        ps, ks, _k1 = _ptr_and_kind(src)
+        pd, kd, _k2 = _ptr_and_kind(dst, writable=True)
+        if ks != kd:
+            raise ValueError("input and output must live in the same memory kind")
+        check(fn(self._h, ctypes.c_void_p(ps), ctypes.c_void_p(pd), ks))
+        return dst
+
+    def apply(self, b, x=None):
+        """x = (1/N) F^H( F(b) / Lambda )  (reference solve_3D, FftLinearSolver_3D.c:166-190)."""
+        if x is None:
+            x = b.clone() if (torch is not None and isinstance(b, torch.Tensor)) else np.empty_like(b)
+        return self._call(lib().cpc_apply, b, x)
+
+    def forward(self, v, out=None):
+        if out is None:
+            out = torch.empty_like(v) if (torch is not None and isinstance(v, torch.Tensor)) else np.empty_like(v)
+        return self._call(lib().cpc_forward, v, out)
+
+    def inverse(self, v, out=None):
+        if out is None:
+            out = torch.empty_like(v) if (torch is not None and isinstance(v, torch.Tensor)) else np.empty_like(v)
+        return self._call(lib().cpc_inverse, v, out)
+
+    def apply_profiled(self, b, x):
+        """Device-pointer apply that also returns the per-pass durations in ms (CUDA events on the plan stream)."""
+        pb, kb, _ = _ptr_and_kind(b)
+        px, kx, _ = _ptr_and_kind(x, writable=True)
+        if kb != MEM_DEVICE or kx != MEM_DEVICE:
+            raise ValueError("apply_profiled needs CUDA tensors")
+        ms = (ctypes.c_float * _lib.CPC_MAX_PASSES)()
+        n = ctypes.c_int()
+        check(lib().cpc_apply_profiled(self._h, ctypes.c_void_p(pb), ctypes.c_void_p(px), ms, ctypes.byref(n)))
+        return [ms[i] for i in range(n.value)]
+
+    def info(self):
+        inf = _lib.PlanInfo()
+        check(lib().cpc_get_info(self._h, ctypes.byref(inf)))
+        return {f[0]: (list(getattr(inf, f[0])) if f[0] == "fast_path" else getattr(inf, f[0])) for f in inf._fields_}
+
+
+__all__ = ["CirculantPlan", "CpcError", "nccl_unique_id", "slab_range"]

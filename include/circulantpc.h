@@ -1,0 +1,157 @@
+/* circulantpc.h -- C ABI of libcirculantpc.so (B200 / sm_100a circulant preconditioner apply).
+ *
+ * This is the drop-in boundary for the one hot path of ndjinga/CirculantPreconditioner:
+ *     x = IFFT3( FFT3(b) ./ Lambda )        (reference: src/FftLinearSolver_3D.c:166-190, solve_3D)
+ * plus its eigenvalue set-up (src/FftLinearSolver_3D.c:80-164) and the PCShell context life cycle
+ * (src/PCSHELLFft_3D.cxx:10-99).  Plain pointers and sizes only; no PETSc, torch or C++ types.
+ * All arrays use the reference's layout: index m = i + nx*(j + ny*k), x fastest
+ * (dims = {nz, ny, nx}, src/PCSHELLFft_3D.cxx:34); complex numbers are interleaved (re, im).
+ * For ncomp = 4 (wave system) unknown c of cell m is element 4*m + c
+ * (tests/WaveSystem_SphericalExplosion_impl_mpi.cxx:104-115).
+ *
+ * Every function returns 0 (CPC_OK) on success, a cpc_status code otherwise; cpc_last_error()
+ * returns a thread-local message.  There is no CPU fallback: without a CUDA device every compute
+ * entry point fails with CPC_ERR_CUDA.
+ *
+ * Which reference interface each entry point replaces is noted per function; the reference-named
+ * wrappers (solve_3D, build_diag_mat_vec_3D, setupFFTPrec3D, ...) that sit on top of this ABI are in
+ * circulantpreconditioner_b200/glue/ and the binding a maintainer would add is in INTEGRATION.md.
+ */
+#ifndef CIRCULANTPC_H
+#define CIRCULANTPC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPC_VERSION_MAJOR 0
+#define CPC_VERSION_MINOR 1
+
+typedef struct cpc_plan_s *cpc_plan;
+
+enum cpc_status {
+    CPC_OK = 0,
+    CPC_ERR_ARG = 1,          /* bad argument (PETSC_ERR_ARG_WRONG in the glue) */
+    CPC_ERR_CUDA = 2,         /* CUDA runtime error / no device */
+    CPC_ERR_UNSUPPORTED = 3,  /* valid request the library does not implement */
+    CPC_ERR_STATE = 4,        /* call order error (e.g. apply before a symbol was set) */
+    CPC_ERR_NCCL = 5,         /* NCCL missing or failing (multi-rank plans only) */
+    CPC_ERR_NOMEM = 6
+};
+
+enum cpc_dtype {
+    CPC_C128 = 0,             /* PetscScalar of a complex PETSc build: complex128 in, complex128 out */
+    CPC_C64 = 1               /* fp32 option: complex64 in/out */
+};
+
+enum cpc_mem {
+    CPC_MEM_DEVICE = 0,       /* pointers as returned by VecCUDAGetArrayRead/Write */
+    CPC_MEM_HOST = 1          /* pointers as returned by VecGetArrayRead/Write (staged through pinned memory) */
+};
+
+enum cpc_symbol_kind {
+    CPC_SYMBOL_NONE = 0,
+    CPC_SYMBOL_SEPARABLE = 1, /* Lambda[k,j,i] = 1 + lx*cx[i] + ly*cy[j] + lz*cz[k] from three 1-D tables */
+    CPC_SYMBOL_TABLE = 2,     /* full table of N eigenvalues held in HBM */
+    CPC_SYMBOL_WAVE = 3       /* 4x4 arrow matrix per frequency (ncomp = 4) */
+};
+
+typedef struct {
+    int nx, ny, nz;           /* grid extents, x fastest; use 1 for unused axes (FftLinearSolver_3D.c:283-301) */
+    int ncomp;                /* 1 = scalar circulant, 4 = wave block-circulant (p, rho0*u, rho0*v, rho0*w) */
+    int dtype;                /* enum cpc_dtype */
+    int nranks, rank;         /* slab decomposition over z (1, 0 for a single GPU) */
+    const void *nccl_unique_id; /* CPC_NCCL_UNIQUE_ID_BYTES bytes made by cpc_nccl_unique_id on rank 0 and
+                                   broadcast by the caller; NULL when nranks == 1 */
+    void *stream;             /* cudaStream_t to run on; NULL = the legacy default stream */
+    int device;               /* CUDA device ordinal; -1 = current device */
+} cpc_plan_desc;
+
+#define CPC_NCCL_UNIQUE_ID_BYTES 128
+
+/* ---- life cycle ------------------------------------------------------------------------------
+ * cpc_plan_create  <- setupFFTPrec3D: MatCreateFFT + MatCreateVecsFFTW (PCSHELLFft_3D.cxx:33-37)
+ * cpc_destroy      <- destroyFFTPrec3D (PCSHELLFft_3D.cxx:86-99)
+ * The plan owns twiddle tables, symbol tables, staging buffers and (multi-rank) the NCCL communicator. */
+int cpc_plan_create(cpc_plan *plan, const cpc_plan_desc *desc);
+int cpc_destroy(cpc_plan plan);
+int cpc_set_stream(cpc_plan plan, void *stream);
+int cpc_sync(cpc_plan plan);
+
+/* ---- eigenvalue set-up (done once, held in HBM) ------------------------------------------------
+ * cpc_set_symbol_transport   <- build_transport_col x3 + 1-D MatMult x3 + build_diag_mat_vec_3D
+ *                               (FftLinearSolver_3D.c:80-90,136-164,218-249; PCSHELLFft_3D.cxx:51-69)
+ * cpc_set_symbol_separable   <- build_diag_mat_vec_3D with caller-supplied c_x_hat, c_y_hat, c_z_hat
+ *                               (FftLinearSolver_3D.c:136-164); tables are HOST complex128 arrays of nx, ny, nz
+ * cpc_set_symbol_diag        <- the Diag argument of solve_3D (FftLinearSolver_3D.c:166,174): N eigenvalues,
+ *                               complex128 (always, whatever the plan dtype), host or device, local slab for
+ *                               multi-rank plans is NOT supported (single rank only)
+ * cpc_set_symbol_first_column<- general circulant: Lambda = FFT3(first column), the 1-D form of which is
+ *                               tests/FFTDirectSolver/testFftSolver_1D.c:144-177; column in the plan dtype
+ * cpc_set_symbol_wave        <- (absent in the reference) arrow-matrix symbol derived from
+ *                               jacobianMatrices (WaveSystem.cxx:92-107); mu_d = dt/delta_d                    */
+int cpc_set_symbol_transport(cpc_plan plan, double lambda_x, double lambda_y, double lambda_z);
+int cpc_set_symbol_separable(cpc_plan plan, const double *cx_hat, const double *cy_hat, const double *cz_hat,
+                             double lambda_x, double lambda_y, double lambda_z);
+int cpc_set_symbol_diag(cpc_plan plan, const void *diag_c128, int mem_kind);
+int cpc_set_symbol_first_column(cpc_plan plan, const void *column, int mem_kind);
+int cpc_set_symbol_wave(cpc_plan plan, double c0, double mu_x, double mu_y, double mu_z);
+/* Writes the N eigenvalues currently in force (complex128) -- what the reference keeps in ctx->Diag. */
+int cpc_get_diag(cpc_plan plan, void *diag_c128, int mem_kind);
+
+/* ---- the hot path -----------------------------------------------------------------------------
+ * cpc_apply   <- solve_3D (FftLinearSolver_3D.c:166-190): x = (1/N) F^H( F(b) ./ Lambda ).
+ *                b is read-only, x fully overwritten, b == x allowed
+ *                (tests/TransportEquationFFT_SphericalExplosion_impl_mpi.cxx:111 passes Un, Un).
+ *                Asynchronous on the plan's stream for device pointers; host pointers return after the
+ *                result has landed in x.
+ * cpc_forward <- MatMult(FFT_MAT, in, out)          (unnormalised, exp(-2 pi i ..), :170)
+ * cpc_inverse <- MatMultTranspose(FFT_MAT, in, out) (unnormalised, exp(+2 pi i ..), :180)
+ * For multi-rank plans b/x/in are the rank's z-slab [cpc_slab_range over nz]; out of cpc_forward and in of
+ * cpc_inverse are in the transposed distribution (all z, the rank's y-range; index i + nx*(jloc + nyloc*k)). */
+int cpc_apply(cpc_plan plan, const void *b, void *x, int mem_kind);
+int cpc_forward(cpc_plan plan, const void *in, void *out, int mem_kind);
+int cpc_inverse(cpc_plan plan, const void *in, void *out, int mem_kind);
+/* Same as cpc_apply on device pointers, but records CUDA events around each of the passes on the plan's
+ * stream and returns their durations (ms).  pass_ms must hold CPC_MAX_PASSES floats; *npasses gets the count. */
+#define CPC_MAX_PASSES 16
+int cpc_apply_profiled(cpc_plan plan, const void *b, void *x, float *pass_ms, int *npasses);
+
+/* ---- introspection -----------------------------------------------------------------------------*/
+typedef struct {
+    int nx, ny, nz, ncomp, dtype, nranks, rank;
+    int symbol_kind;
+    int passes_per_apply;          /* HBM passes (kernel launches) of one cpc_apply */
+    int fast_path[3];              /* 1 if axis x/y/z runs the templated Stockham kernel, 0 = generic kernel */
+    int64_t local_elems;           /* elements (of ncomp * cells) held by this rank */
+    int64_t bytes_per_apply_alg;   /* 5 passes x 2 x local_elems x sizeof(elem): SURVEY.md 8(d) */
+    uint64_t kernel_launches;      /* running count of kernels launched by this plan */
+    uint64_t h2d_bytes, d2h_bytes; /* running totals of staged copies (host-pointer calls) */
+} cpc_plan_info;
+int cpc_get_info(cpc_plan plan, cpc_plan_info *info);
+
+const char *cpc_last_error(void);
+int cpc_version(void);             /* major * 1000 + minor */
+int cpc_device_count(void);        /* number of CUDA devices visible, 0 if none / no driver */
+
+/* ---- pure host helpers (no GPU needed; shared by the multi-rank code and its CPU tests) ----------
+ * Slab decomposition: rank r of P owns indices [start, start+count) of an axis of length n,
+ * count = n/P (+1 for the first n%P ranks).                                                        */
+int cpc_slab_range(int n, int nranks, int rank, int *start, int *count);
+/* Element offset (within the rank-local send buffer, laid out [dest q][z_loc][y_loc(q)][x]) and element count of
+ * the chunk that rank `rank` sends to rank `q` in the forward transpose of an nx x ny x nz x ncomp grid. */
+int cpc_slab_send_chunk(int nx, int ny, int nz, int ncomp, int nranks, int rank, int q,
+                        int64_t *offset, int64_t *count);
+/* Same for the chunk received from rank `s` into the transposed buffer [z_glob][y_loc][x]. */
+int cpc_slab_recv_chunk(int nx, int ny, int nz, int ncomp, int nranks, int rank, int s,
+                        int64_t *offset, int64_t *count);
+/* NCCL bootstrap: fills CPC_NCCL_UNIQUE_ID_BYTES bytes (call on rank 0, broadcast out of band). */
+int cpc_nccl_unique_id(void *out_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CIRCULANTPC_H */

@@ -1,0 +1,265 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerance (BASELINE.json north_star): relative L2 error <= 1e-12 in fp64, <= 1e-5 in fp32.
+Nothing here reads /root/reference; golden inputs/outputs come from tests/golden/*.npz.
+"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+import circulantpreconditioner_b200 as cpc
+from oracle import circulant_oracle as O
+from tests.conftest import GOLDEN, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+TOL32 = 1e-5
+
+
+def dev(a, dtype=torch.complex128):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def g(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def rand_c(rng, n):
+    return rng.standard_normal(n) + 1j * rng.standard_normal(n)
+
+
+# ----------------------------------------------------------------------------------------------------
+# golden vectors of the reference (generic any-n kernel path: 4, 8, 3x2, 4x3x2, 50x200, 10x25x40)
+# ----------------------------------------------------------------------------------------------------
+def test_kat1_first_column_n4():
+    f = g("ref_c_kat1_n4.npz")
+    with cpc.CirculantPlan(4, 1, 1) as p:
+        p.set_symbol_first_column(dev(f["col"]))
+        x = host(p.apply(dev(f["b"])))
+    np.testing.assert_allclose(x.real, [6.7, 2.9, 6.3, 20.1], rtol=1e-13)
+    np.testing.assert_allclose(x.imag, 0, atol=1e-13)
+    assert rel_l2(x, f["x"]) < TOL64
+
+
+@pytest.mark.parametrize("name", ["ref_c_kat2_3x2.npz", "ref_c_kat3_4x3x2.npz", "ref_py_2d_50x200.npz",
+                                  "ref_py_3d_10x25x40.npz"])
+def test_reference_fixtures_transport(name):
+    f = g(name)
+    nx, ny, nz = (int(v) for v in f["n"])
+    lam = [float(v) for v in f["lam"]]
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        p.set_symbol_transport(*lam)
+        assert np.abs(p.get_diag() - f["Diag"]).max() < 1e-13
+        b = dev(f["b"])
+        x = host(p.apply(b))
+        assert rel_l2(x, f["X"]) < TOL64
+        assert rel_l2(x, f["X_ref"]) < TOL64
+        # same answer when the caller hands over Diag itself (solve_3D's signature) ...
+        p.set_symbol_diag(dev(f["Diag"]))
+        assert rel_l2(host(p.apply(b)), f["X"]) < TOL64
+        # ... or the three 1-D eigenvalue tables (build_diag_mat_vec_3D's signature)
+        p.set_symbol_separable(O.column_hat(nx), O.column_hat(ny), O.column_hat(nz), *lam)
+        assert rel_l2(host(p.apply(b)), f["X"]) < TOL64
+
+
+def test_reference_fixture_1d_n8():
+    f = g("ref_py_1d_n8.npz")
+    with cpc.CirculantPlan(8) as p:
+        p.set_symbol_first_column(dev(f["col"]))
+        assert rel_l2(host(p.apply(dev(f["b"]))), f["x"]) < TOL64
+        p.set_symbol_transport(float(f["lam"]))
+        assert rel_l2(host(p.apply(dev(f["b"]))), f["x"]) < TOL64
+
+
+@pytest.mark.parametrize("tag", ["phys", "unit"])
+def test_config0_32cube_fast_path(tag):
+    f = g(f"ref_py_3d_32cube_{tag}.npz")
+    lam = [float(v) for v in f["lam"]]
+    with cpc.CirculantPlan(32, 32, 32) as p:
+        assert p.info()["fast_path"] == [1, 1, 1]
+        p.set_symbol_transport(*lam)
+        assert np.abs(p.get_diag()[:64] - f["Diag_head"]).max() < 1e-13
+        x = host(p.apply(dev(f["b"])))
+    assert rel_l2(x.real, f["X_real"]) < TOL64
+    assert np.abs(x.imag).max() < 1e-11
+    assert rel_l2(x, f["X_ref"]) < TOL64
+
+
+# ----------------------------------------------------------------------------------------------------
+# seeded comparisons with the oracle
+# ----------------------------------------------------------------------------------------------------
+SHAPES = [(16, 16, 16), (32, 64, 16), (64, 16, 128), (128, 32, 16), (256, 16, 32), (16, 256, 16), (512, 16, 8),
+          (16, 8, 512), (1024, 4, 4), (8, 1024, 2), (2048, 2, 2), (2, 4, 2048), (48, 20, 36), (7, 11, 13),
+          (64, 64, 1), (128, 1, 1), (1, 1, 64), (1, 1, 1), (30, 1, 17)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_forward_inverse_match_oracle(shape):
+    nx, ny, nz = shape
+    rng = np.random.default_rng(nx * 7919 + ny * 31 + nz)
+    v = rand_c(rng, nx * ny * nz)
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        d = dev(v)
+        f = host(p.forward(d))
+        ref = O.fft3_forward(v.reshape(nz, ny, nx)).ravel()
+        assert rel_l2(f, ref) < TOL64
+        bk = host(p.inverse(dev(ref)))
+        assert rel_l2(bk, v * v.size) < TOL64
+        assert np.array_equal(host(d), v)           # input untouched
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_apply_transport_matches_oracle(shape):
+    nx, ny, nz = shape
+    rng = np.random.default_rng(nx + 13 * ny + 101 * nz)
+    lam = (55.5556, 0.3, 2.5)
+    x_ref = rand_c(rng, nx * ny * nz)
+    b = O.apply_transport_matrix(x_ref, nx, ny, nz, *lam)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b)
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        p.set_symbol_transport(*lam)
+        d = dev(b)
+        out = torch.empty_like(d)
+        p.apply(d, out)
+        assert rel_l2(host(out), want) < TOL64
+        assert rel_l2(host(out), x_ref) < 1e-11
+        assert np.array_equal(host(d), b)           # b is read-only
+        p.apply(d, d)                               # b == x aliasing (TransportEquationFFT...:111 passes Un, Un)
+        assert rel_l2(host(d), want) < TOL64
+
+
+def test_general_first_column_and_diag_table():
+    nx, ny, nz = 32, 16, 64
+    rng = np.random.default_rng(3)
+    col = np.zeros((nz, ny, nx), dtype=np.complex128)
+    col[0, 0, 0] = 7.0
+    col[0, 0, 1] = -1.0; col[0, 1, 0] = -1.5; col[1, 0, 0] = -0.5
+    col[0, 0, -1] = -0.25; col[-1, 0, 0] = -0.75; col[0, -1, 0] = 0.3j
+    b = rand_c(rng, nx * ny * nz)
+    want = O.solve_first_column(col.ravel(), b, nx, ny, nz)
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        p.set_symbol_first_column(dev(col.ravel()))
+        assert rel_l2(host(p.apply(dev(b))), want) < TOL64
+        lam = O.fft3_forward(col).ravel()
+        assert rel_l2(p.get_diag(), lam) < TOL64
+        p.set_symbol_diag(lam)                       # host pointer
+        assert rel_l2(host(p.apply(dev(b))), want) < TOL64
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 16, 64), (64, 32, 16), (6, 5, 4), (16, 16, 1), (128, 16, 32)])
+def test_wave_block_matches_oracle(shape):
+    nx, ny, nz = shape
+    rng = np.random.default_rng(17)
+    c0, mu = 700.0, (0.0793651, 0.0793651, 0.0793651)
+    y = rng.standard_normal(nx * ny * nz * 4)
+    b = O.apply_wave_matrix(y, nx, ny, nz, c0, *mu).astype(np.complex128)
+    want = O.solve_wave_block(b, nx, ny, nz, c0, *mu)
+    with cpc.CirculantPlan(nx, ny, nz, ncomp=4) as p:
+        p.set_symbol_wave(c0, *mu)
+        got = host(p.apply(dev(b)))
+    # the two evaluations of the same closed form agree to rounding times the block conditioning (~c0^2 mu)
+    assert rel_l2(got, want) < 1e-10
+    c0 = 3.0
+    b = O.apply_wave_matrix(y, nx, ny, nz, c0, *mu).astype(np.complex128)
+    with cpc.CirculantPlan(nx, ny, nz, ncomp=4) as p:
+        p.set_symbol_wave(c0, *mu)
+        got = host(p.apply(dev(b)))
+    assert rel_l2(got, O.solve_wave_block(b, nx, ny, nz, c0, *mu)) < TOL64
+    assert rel_l2(got.real, y) < 1e-11
+
+
+@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 128, 16), (512, 8, 16), (20, 12, 9)])
+def test_fp32_option(shape):
+    nx, ny, nz = shape
+    rng = np.random.default_rng(23)
+    lam = (5.0, 0.3, 2.5)
+    x_ref = rand_c(rng, nx * ny * nz)
+    b = O.apply_transport_matrix(x_ref, nx, ny, nz, *lam)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b)
+    with cpc.CirculantPlan(nx, ny, nz, dtype="c64") as p:
+        p.set_symbol_transport(*lam)
+        got = host(p.apply(dev(b, torch.complex64)))
+        assert rel_l2(got, want) < TOL32
+        f = host(p.forward(dev(b, torch.complex64)))
+        assert rel_l2(f, O.fft3_forward(b.reshape(nz, ny, nx)).ravel()) < TOL32
+
+
+def test_host_pointer_path_and_counters():
+    nx, ny, nz = 64, 32, 48
+    rng = np.random.default_rng(29)
+    lam = (1.0, 2.0, 3.0)
+    b = rand_c(rng, nx * ny * nz)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b)
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        p.set_symbol_transport(*lam)
+        x = np.empty_like(b)
+        p.apply(b, x)                                # numpy (pageable host) pointers
+        assert rel_l2(x, want) < TOL64
+        bt = torch.from_numpy(b).pin_memory()
+        xt = torch.empty_like(bt).pin_memory()
+        p.apply(bt, xt)                              # pinned host pointers
+        assert rel_l2(xt.numpy(), want) < TOL64
+        inf = p.info()
+        assert inf["h2d_bytes"] == 2 * b.nbytes and inf["d2h_bytes"] == 2 * b.nbytes
+        assert inf["kernel_launches"] >= 10 and inf["passes_per_apply"] == 5
+        assert inf["bytes_per_apply_alg"] == 160 * b.size
+        f = np.empty_like(b)
+        p.forward(b, f)
+        assert rel_l2(f, O.fft3_forward(b.reshape(nz, ny, nx)).ravel()) < TOL64
+
+
+def test_error_behaviour_on_device():
+    with cpc.CirculantPlan(16, 16, 16) as p:
+        b = torch.zeros(16 ** 3, dtype=torch.complex128, device="cuda")
+        with pytest.raises(cpc.CpcError) as e:
+            p.apply(b)                               # no symbol yet
+        assert e.value.status == 4
+        with pytest.raises(cpc.CpcError):
+            p.set_symbol_wave(700.0, 1, 1, 1)        # ncomp == 1
+    with cpc.CirculantPlan(16, 16, 16, ncomp=4) as p:
+        with pytest.raises(cpc.CpcError):
+            p.set_symbol_transport(1, 1, 1)
+
+
+# ----------------------------------------------------------------------------------------------------
+# size-independent properties at the BASELINE sizes (the oracle would take too long here)
+# ----------------------------------------------------------------------------------------------------
+def _transport_matrix_torch(u, lam):
+    out = u.clone()
+    for ax, l in zip((2, 1, 0), lam):
+        if u.shape[ax] > 1:
+            out += l * (u - torch.roll(u, 1, dims=ax))
+    return out
+
+
+@pytest.mark.parametrize("n", [128, 256, 512])
+def test_roundtrip_and_linearity_at_baseline_sizes(n):
+    lam = (55.5556, 55.5556, 55.5556)
+    gen = torch.Generator(device="cuda").manual_seed(n)
+    xr = torch.randn(n, n, n, dtype=torch.float64, device="cuda", generator=gen).to(torch.complex128)
+    b = _transport_matrix_torch(xr, lam).reshape(-1)
+    with cpc.CirculantPlan(n, n, n) as p:
+        assert p.info()["fast_path"] == [1, 1, 1]
+        p.set_symbol_transport(*lam)
+        x = p.apply(b)
+        err = (torch.linalg.vector_norm(x - xr.reshape(-1)) / torch.linalg.vector_norm(xr)).item()
+        assert err < TOL64, err                      # b := C x_ref  =>  apply(b) == x_ref
+        # forward / inverse round trip and Parseval
+        f = p.forward(b)
+        bb = p.inverse(f)
+        N = float(n) ** 3
+        assert (torch.linalg.vector_norm(bb / N - b) / torch.linalg.vector_norm(b)).item() < TOL64
+        pars = (torch.linalg.vector_norm(f) ** 2 / N / torch.linalg.vector_norm(b) ** 2).item()
+        assert abs(pars - 1.0) < 1e-12
+        del f, bb
+        # linearity: apply(2 b + i b) == (2 + i) apply(b)
+        y = p.apply((2.0 + 1.0j) * b)
+        assert (torch.linalg.vector_norm(y - (2.0 + 1.0j) * x) / torch.linalg.vector_norm(x)).item() < TOL64
