@@ -16,7 +16,7 @@ template <> struct cplx_of<double> { using type = double2; };
 template <> struct cplx_of<float> { using type = float2; };
 template <typename T> using cplx_t = typename cplx_of<T>::type;
 
-template <typename T> __device__ __forceinline__ cplx_t<T> mk(T a, T b) { cplx_t<T> r; r.x = a; r.y = b; return r; }
+template <typename T> __host__ __device__ __forceinline__ cplx_t<T> mk(T a, T b) { cplx_t<T> r; r.x = a; r.y = b; return r; }
 template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
 template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
 // a * b

@@ -10,6 +10,8 @@
 // and b == x aliasing (tests/TransportEquationFFT_SphericalExplosion_impl_mpi.cxx:111) is safe.
 #pragma once
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <tuple>
@@ -219,6 +221,9 @@ template <typename T> struct PlanT : PlanBase {
     // ---------------------------------------------------------------------------------------- init
     int init() override
     {
+        const bool dbg = getenv("CPC_DEBUG") != nullptr;
+#define CPC_TRACE(msg) do { if (dbg) { fprintf(stderr, "[cpc] %s\n", msg); fflush(stderr); } } while (0)
+        CPC_TRACE("init begin");
         n[0] = desc.nx; n[1] = desc.ny; n[2] = desc.nz;
         nc = desc.ncomp;
         ntot = (long long)n[0] * n[1] * n[2];
@@ -234,9 +239,11 @@ template <typename T> struct PlanT : PlanBase {
             return CPC_ERR_UNSUPPORTED;
         }
         FastRegistry<T>::fill(reg);
+        CPC_TRACE("registry filled");
 
         int dev_smem = 0;
         CPC_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        CPC_TRACE("got smem attribute");
 
         for (int a = 0; a < 3; ++a) {
             // root table
@@ -246,8 +253,11 @@ template <typename T> struct PlanT : PlanBase {
                 exact_root(m, n[a], &re, &im);
                 h[m] = mk<T>((T)re, (T)im);
             }
+            CPC_TRACE("roots computed");
             CPC_CUDA(cudaMalloc(&tw[a], sizeof(C) * n[a]));
+            CPC_TRACE("malloc done");
             CPC_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(C) * n[a], cudaMemcpyHostToDevice));
+            CPC_TRACE("memcpy done");
 
             // kernel choice
             AxisCfg &c = cfg[a];
@@ -286,6 +296,7 @@ template <typename T> struct PlanT : PlanBase {
                 c.threads = work >= 256 ? 256 : (int)((work + 31) / 32 * 32);
             }
         }
+        CPC_TRACE("axes configured");
         // opt in to large dynamic shared memory for every kernel we may launch
         for (auto &kv : reg) {
             if (kv.second.smem > 48 * 1024 && kv.second.smem <= (size_t)dev_smem)
@@ -294,6 +305,7 @@ template <typename T> struct PlanT : PlanBase {
         }
         CPC_CUDA(cudaFuncSetAttribute((const void *)generic_pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       dev_smem));
+        CPC_TRACE("func attributes set");
         CPC_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
         if (desc.nranks > 1) {
             int rc = dist_init(dist, desc.nranks, desc.rank, desc.nccl_unique_id, device);
