@@ -16,8 +16,16 @@
 //     backward transform's first stage: forward-z, the eigenvalue division and backward-z are ONE pass
 //     (reference src/FftLinearSolver_3D.c:170-184 does them as four full-array sweeps).
 //
-// Shared memory holds one [N][TX] tile per group, laid out so that the TX lanes of a line index are contiguous:
-// the 8 (fp64, TX=8) lanes of a quarter warp always hit 128 contiguous bytes -> conflict-free for any index.
+// Thread/shared-memory mappings (template flag XMAP):
+//   XMAP = false (lines strided in HBM: y, z passes, and the wave x pass whose 4 components are the lanes):
+//       l = tid % TX fastest, shared memory [N][TX]: the 8 (fp64, TX=8) lanes of a quarter warp always hit 128
+//       contiguous bytes of HBM and of shared memory -> coalesced and bank-conflict-free for any point index.
+//   XMAP = true (lines contiguous in HBM: the scalar x pass):
+//       j = tid % (N/E) fastest, so a warp reads 32 consecutive points (512 contiguous bytes) of ONE line; shared
+//       memory is [TX][N + N/R0] with one pad element every R0 points, which makes the stride-R0 stores of the first
+//       stage and every later (consecutive) access conflict-free.
+// Twiddles come from per-stage tables laid out [r-1][k] (k = butterfly index mod p), so the lanes of a warp read
+// consecutive entries: one LSU wavefront per load instead of one per distinct cache line.
 #pragma once
 #include "fft_core.cuh"
 
@@ -41,6 +49,7 @@ struct PassGeom {
     //   c = w % ncomp, x = (w / ncomp) % nx, y = w / (ncomp * nx)
     int ncomp, nx, ny;
     int y0;               // global y of local y index 0 (multi-rank transposed slab)
+    int pf_tiles;         // > 0: prefetch into L2 the tile `pf_tiles` after this one (about one wave of CTAs ahead)
 };
 
 enum PassMode { MODE_FWD = 0, MODE_INV = 1, MODE_FUSED_SEP = 2, MODE_FUSED_TABLE = 3, MODE_FUSED_WAVE = 4 };
@@ -66,9 +75,24 @@ __device__ __forceinline__ long long point_off(int i, long long S, int D, int sh
 template <int A, int B> struct CMax { static constexpr int v = A > B ? A : B; };
 
 // ---------------------------------------------------------------------------------------------------------------
-// One Stockham stage on the register file.  v[] is indexed by m with point index j + TPL*m.
+// Shared-memory index of point i of lane-line l.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int N, int E, int R, int P, int DIR, bool TO_SMEM, int TX>
+template <int N, int TX, int PADSH, bool XMAP> __device__ __forceinline__ int sm_index(int i, int l)
+{
+    if (XMAP) return l * (N + (N >> PADSH)) + i + (i >> PADSH);
+    return i * TX + l;
+}
+template <int N, int TX, int PADSH, bool XMAP> struct SmemTile {
+    static constexpr int elems = XMAP ? TX * (N + (N >> PADSH)) : N * TX;
+};
+template <int R> struct Log2 { static constexpr int v = 1 + Log2<R / 2>::v; };
+template <> struct Log2<1> { static constexpr int v = 0; };
+
+// ---------------------------------------------------------------------------------------------------------------
+// One Stockham stage on the register file.  v[] is indexed by m with point index j + TPL*m.
+// tw points at this stage's table: tw[(r-1)*P + k] = exp(-2 pi i r k / (P R)).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int N, int E, int R, int P, int DIR, bool TO_SMEM, int TX, int PADSH, bool XMAP>
 __device__ __forceinline__ void stockham_stage(cplx_t<T> (&v)[E], int j, int l, cplx_t<T> *sm,
                                                const cplx_t<T> *__restrict__ tw)
 {
@@ -83,15 +107,14 @@ __device__ __forceinline__ void stockham_stage(cplx_t<T> (&v)[E], int j, int l, 
         for (int r = 0; r < R; ++r) u[r] = v[b + r * NB];
         const int k = (P > 1) ? (jb & (P - 1)) : 0;
         if (P > 1) {
-            constexpr int TWS = N / (P * R);   // table step: exp(-2 pi i r k / (P R)) = tw[r k TWS]
 #pragma unroll
-            for (int r = 1; r < R; ++r) u[r] = twmul<DIR>(u[r], tw[r * k * TWS]);
+            for (int r = 1; r < R; ++r) u[r] = twmul<DIR>(u[r], __ldg(&tw[(r - 1) * P + k]));
         }
         Butterfly<R, DIR, C>::run(u);
         if (TO_SMEM) {
             const int j0 = (jb - k) * R + k;
 #pragma unroll
-            for (int r = 0; r < R; ++r) sm[(j0 + r * P) * TX + l] = u[r];
+            for (int r = 0; r < R; ++r) sm[sm_index<N, TX, PADSH, XMAP>(j0 + r * P, l)] = u[r];
         } else {
 #pragma unroll
             for (int r = 0; r < R; ++r) v[b + r * NB] = u[r];
@@ -99,37 +122,39 @@ __device__ __forceinline__ void stockham_stage(cplx_t<T> (&v)[E], int j, int l, 
     }
 }
 
-template <typename T, int N, int E, int TX>
+template <typename T, int N, int E, int TX, int PADSH, bool XMAP>
 __device__ __forceinline__ void smem_gather(cplx_t<T> (&v)[E], int j, int l, const cplx_t<T> *sm)
 {
     constexpr int TPL = N / E;
 #pragma unroll
-    for (int m = 0; m < E; ++m) v[m] = sm[(j + TPL * m) * TX + l];
+    for (int m = 0; m < E; ++m) v[m] = sm[sm_index<N, TX, PADSH, XMAP>(j + TPL * m, l)];
 }
 
 // Full 1-D transform of the thread's line: registers -> registers (through shared memory).
-template <typename T, int N, int R0, int R1, int R2, int DIR, int TX>
-__device__ __forceinline__ void line_fft(cplx_t<T> (&v)[CMax<CMax<R0, R1>::v, R2>::v], int j, int l, cplx_t<T> *sm,
+// Stage tables are concatenated: stage 1 at tw, stage 2 at tw + (R1-1)*R0.
+template <typename T, int N, int R0, int R1, int R2, int E, int DIR, int TX, bool XMAP>
+__device__ __forceinline__ void line_fft(cplx_t<T> (&v)[E], int j, int l, cplx_t<T> *sm,
                                          const cplx_t<T> *__restrict__ tw)
 {
-    constexpr int E = CMax<CMax<R0, R1>::v, R2>::v;
     constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
+    constexpr int PS = Log2<R0>::v;
+    const cplx_t<T> *tw2 = tw + (R1 - 1) * R0;
     if (NST == 1) {
-        stockham_stage<T, N, E, R0, 1, DIR, false, TX>(v, j, l, sm, tw);
+        stockham_stage<T, N, E, R0, 1, DIR, false, TX, PS, XMAP>(v, j, l, sm, tw);
     } else if (NST == 2) {
-        stockham_stage<T, N, E, R0, 1, DIR, true, TX>(v, j, l, sm, tw);
+        stockham_stage<T, N, E, R0, 1, DIR, true, TX, PS, XMAP>(v, j, l, sm, tw);
         __syncthreads();
-        smem_gather<T, N, E, TX>(v, j, l, sm);
-        stockham_stage<T, N, E, R1, R0, DIR, false, TX>(v, j, l, sm, tw);
+        smem_gather<T, N, E, TX, PS, XMAP>(v, j, l, sm);
+        stockham_stage<T, N, E, R1, R0, DIR, false, TX, PS, XMAP>(v, j, l, sm, tw);
     } else {
-        stockham_stage<T, N, E, R0, 1, DIR, true, TX>(v, j, l, sm, tw);
+        stockham_stage<T, N, E, R0, 1, DIR, true, TX, PS, XMAP>(v, j, l, sm, tw);
         __syncthreads();
-        smem_gather<T, N, E, TX>(v, j, l, sm);
+        smem_gather<T, N, E, TX, PS, XMAP>(v, j, l, sm);
         __syncthreads();
-        stockham_stage<T, N, E, R1, R0, DIR, true, TX>(v, j, l, sm, tw);
+        stockham_stage<T, N, E, R1, R0, DIR, true, TX, PS, XMAP>(v, j, l, sm, tw);
         __syncthreads();
-        smem_gather<T, N, E, TX>(v, j, l, sm);
-        stockham_stage<T, N, E, R2, R0 * R1, DIR, false, TX>(v, j, l, sm, tw);
+        smem_gather<T, N, E, TX, PS, XMAP>(v, j, l, sm);
+        stockham_stage<T, N, E, R2, R0 * R1, DIR, false, TX, PS, XMAP>(v, j, l, sm, tw2);
     }
 }
 
@@ -164,48 +189,46 @@ __device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int j, int w, lo
         const T sx = -rx.y * s.mux, sy = -ry.y * s.muy;                    // mu_d sin(theta_d)
         const T ox = ((T)1 - rx.x) * s.mux, oy = ((T)1 - ry.x) * s.muy;    // mu_d (1 - cos(theta_d))
         const T c0 = s.c0, c02 = s.c0 * s.c0;
+        const T iDx = fast_rcp((T)1 + c0 * ox), iDy = fast_rcp((T)1 + c0 * oy);
+        const T sxx = sx * sx * iDx, syy = sy * sy * iDy;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const C rz = s.rz[j + TPL * m];
             const T sz = -rz.y * s.muz, oz = ((T)1 - rz.x) * s.muz;
-            const T Dx = (T)1 + c0 * ox, Dy = (T)1 + c0 * oy, Dz = (T)1 + c0 * oz;
+            const T Dz = (T)1 + c0 * oz, iDz = fast_rcp(Dz);
             const T m00 = (T)1 + c0 * (ox + oy + oz);
-            const T den = m00 + c02 * (sx * sx / Dx + sy * sy / Dy + sz * sz / Dz);
+            const T den = m00 + c02 * (sxx + syy + sz * sz * iDz);
             const T sd = (c == 1) ? sx : (c == 2) ? sy : sz;
-            const T Dd = (c == 1) ? Dx : (c == 2) ? Dy : Dz;
+            const T iDd = (c == 1) ? iDx : (c == 2) ? iDy : iDz;
             // contribution of this lane to the numerator: c=0: r0 ; c=d: -i c0^2 s_d r_d / D_d
             C t;
             if (c == 0) t = v[m];
             else {
-                const T f = c02 * sd / Dd;
+                const T f = c02 * sd * iDd;
                 t = mk<T>(v[m].y * f, -v[m].x * f);
             }
             t.x += __shfl_xor_sync(0xffffffffu, t.x, 1);
             t.y += __shfl_xor_sync(0xffffffffu, t.y, 1);
             t.x += __shfl_xor_sync(0xffffffffu, t.x, 2);
             t.y += __shfl_xor_sync(0xffffffffu, t.y, 2);
-            const T inv = s.scale / den;
+            const T inv = s.scale * fast_rcp(den);
             const C p = mk<T>(t.x * inv, t.y * inv);                       // already scaled by 1/N
             if (c == 0) v[m] = p;
-            else {
-                // (r_d / N - i s_d p) / D_d
-                const T q = (T)1 / Dd;
-                v[m] = mk<T>((v[m].x * s.scale + sd * p.y) * q, (v[m].y * s.scale - sd * p.x) * q);
-            }
+            else                                                           // (r_d / N - i s_d p) / D_d
+                v[m] = mk<T>((v[m].x * s.scale + sd * p.y) * iDd, (v[m].y * s.scale - sd * p.x) * iDd);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// The pass kernel.
+// The pass kernel.  E = points per thread (a multiple of every radix), TX = lines per tile, G = tiles per CTA.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int N, int R0, int R1, int R2, int TX, int G, int MODE, int MINB>
-__global__ void __launch_bounds__((N / CMax<CMax<R0, R1>::v, R2>::v) * TX * G, MINB)
+template <typename T, int N, int R0, int R1, int R2, int E, int TX, int G, int MODE, int MINB, bool XMAP>
+__global__ void __launch_bounds__((N / E) * TX * G, MINB)
 fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
                 const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
 {
     using C = cplx_t<T>;
-    constexpr int E = CMax<CMax<R0, R1>::v, R2>::v;
     constexpr int TPL = N / E;
     constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
     static_assert(R0 * R1 * R2 == N, "radices must multiply to N");
@@ -213,10 +236,10 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
     const int tid = threadIdx.x;
-    const int l = tid % TX;
-    const int j = (tid / TX) % TPL;
+    const int l = XMAP ? (tid / TPL) % TX : tid % TX;
+    const int j = XMAP ? tid % TPL : (tid / TX) % TPL;
     const int grp = tid / (TX * TPL);
-    C *sm = reinterpret_cast<C *>(smem_raw) + (size_t)grp * (NST > 1 ? N * TX : 0);
+    C *sm = reinterpret_cast<C *>(smem_raw) + (size_t)grp * (NST > 1 ? SmemTile<N, TX, Log2<R0>::v, XMAP>::elems : 0);
 
     const int t = blockIdx.x * G + grp;
     const bool tile_ok = t < g.ntiles;
@@ -226,6 +249,24 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
     const bool active = tile_ok && (w < g.lines_inner);
     const long long gbase = (long long)to * g.B1 + (long long)ti * g.B0 + (long long)l * g.SL;
     const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)l * g.SL;
+
+    // Pull the tile that a later wave of CTAs will read towards L2 while this one computes: HBM stays busy during
+    // the butterfly phases although only a few CTAs fit on an SM.  One 128-byte row per prefetch instruction.
+    if (g.pf_tiles > 0) {
+        const int tp = t + g.pf_tiles;
+        if (tp < g.ntiles) {
+            const long long pbase = (long long)(tp / g.tiles_inner) * g.B1 + (long long)(tp % g.tiles_inner) * g.B0;
+            if (XMAP) {
+                // lines are contiguous: thread (l, j) covers 128 bytes = 128/sizeof(C) points at a time
+                constexpr int PER = 128 / (int)sizeof(C);
+                for (int i = j * PER; i < N; i += TPL * PER)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(in + pbase + (long long)l * g.SL + i));
+            } else {
+                for (int m = l; m < E; m += TX)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(in + pbase + point_off(j + TPL * m, g.SI, g.Di, g.shi, g.SCi)));
+            }
+        }
+    }
 
     C v[E];
     if (active) {
@@ -237,14 +278,14 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
     }
 
     if (MODE == MODE_FWD) {
-        line_fft<T, N, R0, R1, R2, -1, TX>(v, j, l, sm, tw);
+        line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
     } else if (MODE == MODE_INV) {
-        line_fft<T, N, R0, R1, R2, +1, TX>(v, j, l, sm, tw);
+        line_fft<T, N, R0, R1, R2, E, +1, TX, XMAP>(v, j, l, sm, tw);
     } else {
-        line_fft<T, N, R0, R1, R2, -1, TX>(v, j, l, sm, tw);
+        line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
         apply_symbol<T, N, E, MODE>(v, j, active ? w : 0, gbase, g.SI, g, sym);
         if (NST > 1) __syncthreads();
-        line_fft<T, N, R0, R1, R2, +1, TX>(v, j, l, sm, tw);
+        line_fft<T, N, R0, R1, R2, E, +1, TX, XMAP>(v, j, l, sm, tw);
     }
 
     if (active) {

@@ -30,26 +30,43 @@ template <typename T> struct FastEntry {
     void (*kern)(const cplx_t<T> *, cplx_t<T> *, const PassGeom, const cplx_t<T> *, const SymbolArgs<T>);
     int threads;
     size_t smem;
-    int g;
+    int g;          // tiles per CTA
+    int tx;         // lines per tile
+    int radix[3];
 };
 
-template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, tx, mode)
+// Kernel variants of one axis length.
+enum Variant {
+    VAR_WIDE = 0,     // strided lines, TX lanes = one 128-byte row (y, z passes)
+    VAR_NARROW = 1,   // strided lines, TX = 4 (wave x pass: the 4 components of a cell; long lines)
+    VAR_XMAP = 2,     // contiguous lines (scalar x pass)
+    VAR_WIDE2 = 3,    // as VAR_WIDE with twice the points per thread (fewer, fatter threads)
+    VAR_EXP4 = 4, VAR_EXP5 = 5, VAR_EXP6 = 6, VAR_EXP7 = 7,   // tuning experiments (tools/sweep)
+    VAR_COUNT = 8
+};
 
-template <typename T, int N, int R0, int R1, int R2, int TX, int G, int MINB, int MINBF = MINB>
+template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, variant, mode)
+
+template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF = MINB>
 static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
 {
-    constexpr int E = CMax<CMax<R0, R1>::v, R2>::v;
     constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
-    const int threads = (N / E) * TX * G;
-    const size_t smem = NST > 1 ? (size_t)G * N * TX * sizeof(cplx_t<T>) : 0;
-    m[FastKey<T>(N, TX, MODE_FWD)] = { fft_pass_kernel<T, N, R0, R1, R2, TX, G, MODE_FWD, MINB>, threads, smem, G };
-    m[FastKey<T>(N, TX, MODE_INV)] = { fft_pass_kernel<T, N, R0, R1, R2, TX, G, MODE_INV, MINB>, threads, smem, G };
-    m[FastKey<T>(N, TX, MODE_FUSED_SEP)] =
-        { fft_pass_kernel<T, N, R0, R1, R2, TX, G, MODE_FUSED_SEP, MINBF>, threads, smem, G };
-    m[FastKey<T>(N, TX, MODE_FUSED_TABLE)] =
-        { fft_pass_kernel<T, N, R0, R1, R2, TX, G, MODE_FUSED_TABLE, MINBF>, threads, smem, G };
-    m[FastKey<T>(N, TX, MODE_FUSED_WAVE)] =
-        { fft_pass_kernel<T, N, R0, R1, R2, TX, G, MODE_FUSED_WAVE, MINBF>, threads, smem, G };
+    constexpr bool XM = (VAR == VAR_XMAP);
+    constexpr int threads = (N / E) * TX * G;
+    constexpr size_t smem = NST > 1 ? (size_t)G * SmemTile<N, TX, Log2<R0>::v, XM>::elems * sizeof(cplx_t<T>) : 0;
+    FastEntry<T> e{ nullptr, threads, smem, G, TX, { R0, R1, R2 } };
+    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FWD, MINB, XM>;
+    m[FastKey<T>(N, VAR, MODE_FWD)] = e;
+    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_INV, MINB, XM>;
+    m[FastKey<T>(N, VAR, MODE_INV)] = e;
+    if constexpr (!XM) {
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_SEP, MINBF, XM>;
+        m[FastKey<T>(N, VAR, MODE_FUSED_SEP)] = e;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_TABLE, MINBF, XM>;
+        m[FastKey<T>(N, VAR, MODE_FUSED_TABLE)] = e;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_WAVE, MINBF, XM>;
+        m[FastKey<T>(N, VAR, MODE_FUSED_WAVE)] = e;
+    }
 }
 
 template <typename T> struct FastRegistry;
@@ -57,50 +74,68 @@ template <typename T> struct FastRegistry;
 #ifdef CPC_INSTANTIATE_F64
 // fp64: a quarter warp (8 lanes x 16 B) covers one 128-byte row of the [N][8] tile.
 template <> struct FastRegistry<double> {
-    static constexpr int TX_WIDE = 8, TX_NARROW = 4;
     static void fill(std::map<FastKey<double>, FastEntry<double>> &m)
     {
-        //                        N   R0  R1  R2 TX   G  MINB [MINB of the fused kernels]
-        register_modes<double,   16, 16,  1,  1, 8, 16, 2>(m);
-        register_modes<double,   32,  8,  4,  1, 8,  8, 2>(m);
-        register_modes<double,   64,  8,  8,  1, 8,  4, 2>(m);
-        register_modes<double,  128, 16,  8,  1, 8,  4, 2>(m);
-        register_modes<double,  256, 16, 16,  1, 8,  2, 2>(m);
-        register_modes<double,  512,  8,  8,  8, 8,  1, 2, 1>(m);
-        register_modes<double, 1024, 16,  8,  8, 8,  1, 1>(m);
-        register_modes<double,   16, 16,  1,  1, 4, 32, 2>(m);
-        register_modes<double,   32,  8,  4,  1, 4, 16, 2>(m);
-        register_modes<double,   64,  8,  8,  1, 4,  8, 2>(m);
-        register_modes<double,  128, 16,  8,  1, 4,  8, 2>(m);
-        register_modes<double,  256, 16, 16,  1, 4,  4, 2>(m);
-        register_modes<double,  512,  8,  8,  8, 4,  2, 2, 1>(m);
-        register_modes<double, 1024, 16,  8,  8, 4,  2, 1>(m);
-        register_modes<double, 2048, 16, 16,  8, 4,  1, 1>(m);
+        //                     variant        N   R0  R1  R2   E  TX   G MINB [MINB fused]
+        register_modes<double, VAR_WIDE,     16, 16,  1,  1, 16,  8, 16, 2>(m);
+        register_modes<double, VAR_WIDE,     32,  8,  4,  1,  8,  8,  8, 2>(m);
+        register_modes<double, VAR_WIDE,     64,  8,  8,  1,  8,  8,  4, 2>(m);
+        register_modes<double, VAR_WIDE,    128, 16,  8,  1, 16,  8,  4, 2>(m);
+        register_modes<double, VAR_WIDE,    256, 16, 16,  1, 16,  8,  2, 2>(m);
+        register_modes<double, VAR_WIDE,    512,  8,  8,  8,  8,  8,  1, 2, 1>(m);
+        register_modes<double, VAR_WIDE,   1024, 16,  8,  8, 16,  8,  1, 1>(m);
+        register_modes<double, VAR_WIDE2,   512,  8,  8,  8, 16,  8,  1, 2>(m);
+        register_modes<double, VAR_EXP4,    512,  8,  8,  8,  8,  4,  1, 3>(m);      // 256 thr, <=80 regs, 3 CTA/SM
+        register_modes<double, VAR_EXP5,    512,  8,  8,  8,  8,  4,  1, 2>(m);      // 256 thr, <=128 regs, 2 CTA/SM
+        register_modes<double, VAR_EXP6,    512,  8,  8,  8,  8,  8,  1, 2, 2>(m);   // 512 thr, 64 regs fused, 2 CTA/SM
+        register_modes<double, VAR_EXP7,    512,  8,  8,  8, 16,  4,  1, 4>(m);      // 128 thr, E=16, <=128 regs, 4 CTA/SM
+        register_modes<double, VAR_NARROW,   16, 16,  1,  1, 16,  4, 32, 2>(m);
+        register_modes<double, VAR_NARROW,   32,  8,  4,  1,  8,  4, 16, 2>(m);
+        register_modes<double, VAR_NARROW,   64,  8,  8,  1,  8,  4,  8, 2>(m);
+        register_modes<double, VAR_NARROW,  128, 16,  8,  1, 16,  4,  8, 2>(m);
+        register_modes<double, VAR_NARROW,  256, 16, 16,  1, 16,  4,  4, 2>(m);
+        register_modes<double, VAR_NARROW,  512,  8,  8,  8,  8,  4,  2, 2, 1>(m);
+        register_modes<double, VAR_NARROW, 1024, 16,  8,  8, 16,  4,  2, 1>(m);
+        register_modes<double, VAR_NARROW, 2048, 16, 16,  8, 16,  4,  1, 1>(m);
+        register_modes<double, VAR_XMAP,     16, 16,  1,  1, 16, 64,  1, 2>(m);
+        register_modes<double, VAR_XMAP,     32,  8,  4,  1,  8, 64,  1, 2>(m);
+        register_modes<double, VAR_XMAP,     64,  8,  8,  1,  8, 32,  1, 2>(m);
+        register_modes<double, VAR_XMAP,    128, 16,  8,  1, 16, 32,  1, 2>(m);
+        register_modes<double, VAR_XMAP,    256, 16, 16,  1, 16, 16,  1, 2>(m);
+        register_modes<double, VAR_XMAP,    512,  8,  8,  8,  8,  8,  1, 2>(m);
+        register_modes<double, VAR_XMAP,   1024, 16,  8,  8, 16,  4,  1, 2>(m);
+        register_modes<double, VAR_XMAP,   2048, 16, 16,  8, 16,  2,  1, 2>(m);
     }
 };
-
 #endif
 #ifdef CPC_INSTANTIATE_F32
 // fp32: 16 lanes x 8 B = one 128-byte row.
 template <> struct FastRegistry<float> {
-    static constexpr int TX_WIDE = 16, TX_NARROW = 4;
     static void fill(std::map<FastKey<float>, FastEntry<float>> &m)
     {
-        register_modes<float,   16, 16,  1,  1, 16,  8, 2>(m);
-        register_modes<float,   32,  8,  4,  1, 16,  4, 2>(m);
-        register_modes<float,   64,  8,  8,  1, 16,  2, 2>(m);
-        register_modes<float,  128, 16,  8,  1, 16,  2, 2>(m);
-        register_modes<float,  256, 16, 16,  1, 16,  1, 2>(m);
-        register_modes<float,  512, 16,  8,  4, 16,  1, 2>(m);
-        register_modes<float, 1024, 16,  8,  8, 16,  1, 1>(m);
-        register_modes<float,   16, 16,  1,  1,  4, 32, 2>(m);
-        register_modes<float,   32,  8,  4,  1,  4, 16, 2>(m);
-        register_modes<float,   64,  8,  8,  1,  4,  8, 2>(m);
-        register_modes<float,  128, 16,  8,  1,  4,  8, 2>(m);
-        register_modes<float,  256, 16, 16,  1,  4,  4, 2>(m);
-        register_modes<float,  512,  8,  8,  8,  4,  2, 2>(m);
-        register_modes<float, 1024, 16,  8,  8,  4,  2, 1>(m);
-        register_modes<float, 2048, 16, 16,  8,  4,  1, 1>(m);
+        register_modes<float, VAR_WIDE,     16, 16,  1,  1, 16, 16,  8, 2>(m);
+        register_modes<float, VAR_WIDE,     32,  8,  4,  1,  8, 16,  4, 2>(m);
+        register_modes<float, VAR_WIDE,     64,  8,  8,  1,  8, 16,  2, 2>(m);
+        register_modes<float, VAR_WIDE,    128, 16,  8,  1, 16, 16,  2, 2>(m);
+        register_modes<float, VAR_WIDE,    256, 16, 16,  1, 16, 16,  1, 2>(m);
+        register_modes<float, VAR_WIDE,    512, 16,  8,  4, 16, 16,  1, 2>(m);
+        register_modes<float, VAR_WIDE,   1024, 16,  8,  8, 16, 16,  1, 1>(m);
+        register_modes<float, VAR_NARROW,   16, 16,  1,  1, 16,  4, 32, 2>(m);
+        register_modes<float, VAR_NARROW,   32,  8,  4,  1,  8,  4, 16, 2>(m);
+        register_modes<float, VAR_NARROW,   64,  8,  8,  1,  8,  4,  8, 2>(m);
+        register_modes<float, VAR_NARROW,  128, 16,  8,  1, 16,  4,  8, 2>(m);
+        register_modes<float, VAR_NARROW,  256, 16, 16,  1, 16,  4,  4, 2>(m);
+        register_modes<float, VAR_NARROW,  512,  8,  8,  8,  8,  4,  2, 2>(m);
+        register_modes<float, VAR_NARROW, 1024, 16,  8,  8, 16,  4,  2, 1>(m);
+        register_modes<float, VAR_NARROW, 2048, 16, 16,  8, 16,  4,  1, 1>(m);
+        register_modes<float, VAR_XMAP,     16, 16,  1,  1, 16, 64,  1, 2>(m);
+        register_modes<float, VAR_XMAP,     32,  8,  4,  1,  8, 64,  1, 2>(m);
+        register_modes<float, VAR_XMAP,     64,  8,  8,  1,  8, 32,  1, 2>(m);
+        register_modes<float, VAR_XMAP,    128, 16,  8,  1, 16, 32,  1, 2>(m);
+        register_modes<float, VAR_XMAP,    256, 16, 16,  1, 16, 16,  1, 2>(m);
+        register_modes<float, VAR_XMAP,    512,  8,  8,  8,  8,  8,  1, 2>(m);
+        register_modes<float, VAR_XMAP,   1024, 16,  8,  8, 16,  8,  1, 2>(m);
+        register_modes<float, VAR_XMAP,   2048, 16, 16,  8, 16,  4,  1, 2>(m);
     }
 };
 #endif
@@ -166,6 +201,7 @@ template <typename T> struct PlanT : PlanBase {
 
     struct AxisCfg {
         bool fast = false;
+        int variant = 0;          // enum Variant of the fast kernel
         int tx = 1;               // lanes per tile
         int threads = 0;          // generic kernel block size
         size_t smem_generic = 0;
@@ -174,13 +210,16 @@ template <typename T> struct PlanT : PlanBase {
 
     int n[3] = { 1, 1, 1 };
     int nc = 1;
+    int num_sms = 148;
+    int pf_waves = 0;             // L2 prefetch distance in units of (SM count) CTAs; 0 = off
     int nzl = 1, z0 = 0;          // local z slab
     int nyl = 1, y0 = 0;          // local y range in the transposed distribution
     long long nloc = 0;           // local elements (slab distribution)
     long long ntot = 0;           // global number of cells * ncomp / ncomp (= nx*ny*nz)
     std::map<FastKey<T>, FastEntry<T>> reg;
     AxisCfg cfg[3];
-    C *tw[3] = { nullptr, nullptr, nullptr };
+    C *tw[3] = { nullptr, nullptr, nullptr };    // roots exp(-2 pi i m / n)
+    C *stw[3] = { nullptr, nullptr, nullptr };   // per-stage twiddle tables of the fast kernel chosen for the axis
 
     // symbol state
     C *sym_tab[3] = { nullptr, nullptr, nullptr };       // ax, ay(+1), az in T
@@ -204,6 +243,7 @@ template <typename T> struct PlanT : PlanBase {
         cudaSetDevice(device);
         for (int a = 0; a < 3; ++a) {
             if (tw[a]) cudaFree(tw[a]);
+            if (stw[a]) cudaFree(stw[a]);
             if (sym_tab[a]) cudaFree(sym_tab[a]);
             if (sym_tab64[a]) cudaFree(sym_tab64[a]);
         }
@@ -243,6 +283,8 @@ template <typename T> struct PlanT : PlanBase {
 
         int dev_smem = 0;
         CPC_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        CPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+        if (const char *pf = getenv("CPC_PREFETCH_WAVES")) pf_waves = atoi(pf);   // tuning hook
         CPC_TRACE("got smem attribute");
 
         for (int a = 0; a < 3; ++a) {
@@ -253,22 +295,46 @@ template <typename T> struct PlanT : PlanBase {
                 exact_root(m, n[a], &re, &im);
                 h[m] = mk<T>((T)re, (T)im);
             }
-            CPC_TRACE("roots computed");
             CPC_CUDA(cudaMalloc(&tw[a], sizeof(C) * n[a]));
-            CPC_TRACE("malloc done");
             CPC_CUDA(cudaMemcpy(tw[a], h.data(), sizeof(C) * n[a], cudaMemcpyHostToDevice));
-            CPC_TRACE("memcpy done");
 
-            // kernel choice
+            // kernel choice.  Scalar x lines are contiguous in HBM -> XMAP; the wave x pass uses the 4 components of
+            // a cell as lanes (narrow strided); y and z lines are strided with >= 128 contiguous bytes across lanes.
             AxisCfg &c = cfg[a];
-            // x lines: the TX lanes of a tile are different lines (scalar) or the 4 components of a cell (wave); a
-            // narrow tile leaves 32/TX consecutive points per warp, i.e. longer contiguous HBM segments per line.
-            int tx = (a == 0) ? FastRegistry<T>::TX_NARROW : FastRegistry<T>::TX_WIDE;
-            if (reg.find(FastKey<T>(n[a], tx, MODE_FWD)) == reg.end()) tx = FastRegistry<T>::TX_NARROW;
-            auto it = reg.find(FastKey<T>(n[a], tx, MODE_FWD));
+            int var = (a == 0) ? (nc == 4 ? VAR_NARROW : VAR_XMAP) : VAR_WIDE;
+            // the fused pass does two transforms per tile: fewer, fatter threads (2 butterflies each, 2 CTAs/SM)
+            // measured 1.18 ms vs 1.98 ms at 512^3 (profiles/r01_notes.md)
+            if (a == 2 && reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
+            {
+                const char *names[3] = { "CPC_VARIANT_X", "CPC_VARIANT_Y", "CPC_VARIANT_Z" };
+                const char *ov = getenv(names[a]);
+                if (ov && *ov) var = atoi(ov);      // tuning hook (tools/), not part of the ABI
+            }
+            if (reg.find(FastKey<T>(n[a], var, MODE_FWD)) == reg.end() && var != VAR_XMAP) var = VAR_NARROW;
+            auto it = reg.find(FastKey<T>(n[a], var, MODE_FWD));
+            if (it != reg.end() && a == 2 && reg.find(FastKey<T>(n[a], var, MODE_FUSED_SEP)) == reg.end()) it = reg.end();
             if (it != reg.end() && it->second.smem <= (size_t)dev_smem) {
                 c.fast = true;
-                c.tx = tx;
+                c.variant = var;
+                c.tx = it->second.tx;
+                // per-stage twiddle tables [r-1][k]: exp(-2 pi i r k / (P R)) for the 2nd and 3rd radix
+                const int *R = it->second.radix;
+                std::vector<C> st;
+                int P = R[0];
+                for (int sidx = 1; sidx < 3; ++sidx) {
+                    if (R[sidx] <= 1) break;
+                    for (int r = 1; r < R[sidx]; ++r)
+                        for (int k = 0; k < P; ++k) {
+                            double re, im;
+                            exact_root((long long)r * k, (long long)P * R[sidx], &re, &im);
+                            st.push_back(mk<T>((T)re, (T)im));
+                        }
+                    P *= R[sidx];
+                }
+                if (!st.empty()) {
+                    CPC_CUDA(cudaMalloc(&stw[a], sizeof(C) * st.size()));
+                    CPC_CUDA(cudaMemcpy(stw[a], st.data(), sizeof(C) * st.size(), cudaMemcpyHostToDevice));
+                }
             } else {
                 c.fast = false;
                 c.fl.n = n[a];
@@ -358,6 +424,7 @@ template <typename T> struct PlanT : PlanBase {
         }
         g.SIo = g.SI; g.B0o = g.B0; g.B1o = g.B1;
         g.SCi = g.SCo = 0; g.Di = g.Do = 0; g.shi = g.sho = -1;
+        g.pf_tiles = 0;
         return g;
     }
 
@@ -401,9 +468,10 @@ template <typename T> struct PlanT : PlanBase {
         if (g.ntiles <= 0) return CPC_OK;
         const SymbolArgs<T> s = symbol_args();
         if (c.fast) {
-            const FastEntry<T> &e = reg.at(FastKey<T>(n[axis], c.tx, mode));
+            const FastEntry<T> &e = reg.at(FastKey<T>(n[axis], c.variant, mode));
             const int grid = (g.ntiles + e.g - 1) / e.g;
-            e.kern<<<grid, e.threads, e.smem, st>>>(in + off, out + off, g, tw[axis], s);
+            g.pf_tiles = pf_waves > 0 ? pf_waves * num_sms * e.g : 0;
+            e.kern<<<grid, e.threads, e.smem, st>>>(in + off, out + off, g, stw[axis], s);
         } else {
             generic_pass_kernel<T><<<g.ntiles, c.threads, c.smem_generic, st>>>(in + off, out + off, g, tw[axis], s,
                                                                                c.fl, c.tx, mode);

@@ -29,9 +29,9 @@ for line in out.splitlines():
 def pretty(name):
     m = re.search(r"fft_pass_kernelI([df])((?:Li\d+E)+)", name)
     if m:
-        nums = re.findall(r"Li(\d+)E", m.group(2))
-        keys = ["N", "R0", "R1", "R2", "TX", "G", "MODE", "MINB"]
-        return ("f64 " if m.group(1) == "d" else "f32 ") + " ".join(f"{k}={v}" for k, v in zip(keys, nums))
+        nums = re.findall(r"Li(\d+)E", m.group(2)); xm = "X" if re.search(r"Lb1E", name) else "-"
+        keys = ["N", "R0", "R1", "R2", "E", "TX", "G", "MODE", "MINB"]
+        return ("f64 " if m.group(1) == "d" else "f32 ") + " ".join(f"{k}={v}" for k, v in zip(keys, nums)) + " xmap=" + xm
     return name[:70]
 
 
