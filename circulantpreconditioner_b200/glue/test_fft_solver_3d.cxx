@@ -1,0 +1,169 @@
+// test_fft_solver_3d.cxx -- the reference's direct-solver tests (tests/FFTDirectSolver/testFftSolver_{1D,2D,3D}.c)
+// restated against the B200 glue, with the assertions the reference lacks (its asserts are `< 1` / non-zero).
+//   b := C X_ref with X_ref[m] = m^3 (testFftSolver_3D.c:133-138), C = I + sum_d lambda_d (I - S_d) applied
+//   matrix-free; Fft{1,2,3}DTransportSolver must return X_ref; residual and error <= 1e-12.
+// Also drives the PCShell life cycle the way KSP would (PCSetUp once, PCApply many times, PCDestroy).
+// Needs a GPU (there is no CPU fallback); run by tests/test_glue.py under -m gpu.
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "circulantpc_petsc.h"
+
+static int g_fail = 0;
+#define EXPECT(cond, ...)                                   \
+    do {                                                    \
+        if (!(cond)) { ++g_fail; printf("FAIL: " __VA_ARGS__); printf("\n"); } \
+    } while (0)
+#define CHK(call)                                                                       \
+    do {                                                                                \
+        PetscErrorCode _e = (call);                                                     \
+        if (_e) { printf("error %d in %s: %s\n", _e, #call, ShimLastError()); return 1; } \
+    } while (0)
+
+static void apply_C(const std::vector<PetscScalar> &u, std::vector<PetscScalar> &out, int nx, int ny, int nz,
+                    double lx, double ly, double lz)
+{
+    out = u;
+    auto at = [&](int i, int j, int k) { return u[(size_t)i + (size_t)nx * (j + (size_t)ny * k)]; };
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                PetscScalar c = at(i, j, k), s = 0;
+                if (nx > 1) s += lx * (c - at((i + nx - 1) % nx, j, k));
+                if (ny > 1) s += ly * (c - at(i, (j + ny - 1) % ny, k));
+                if (nz > 1) s += lz * (c - at(i, j, (k + nz - 1) % nz));
+                out[(size_t)i + (size_t)nx * (j + (size_t)ny * k)] += s;
+            }
+}
+
+static double rel_err(const PetscScalar *a, const std::vector<PetscScalar> &ref)
+{
+    long double num = 0, den = 0;
+    for (size_t m = 0; m < ref.size(); ++m) { num += std::norm(a[m] - ref[m]); den += std::norm(ref[m]); }
+    return (double)std::sqrt(num / den);
+}
+
+static int direct_solver_case(int nx, int ny, int nz, double ax, double ay, double az, double dt, double dx, double dy,
+                              double dz, const char *name)
+{
+    const int N = nx * ny * nz;
+    std::vector<PetscScalar> xref(N), b;
+    for (int m = 0; m < N; ++m) xref[m] = (double)m * m * m;
+    apply_C(xref, b, nx, ny, nz, ax * dt / dx, ay * dt / dy, az * dt / dz);
+    Mat FFT_MAT;
+    PetscInt dims[3] = { nz, ny, nx };
+    CHK(MatCreateFFT(PETSC_COMM_WORLD, 3, dims, MATFFTW, &FFT_MAT));
+    Vec X, B;
+    CHK(MatCreateVecsFFTW(FFT_MAT, &B, NULL, &X));
+    for (int m = 0; m < N; ++m) CHK(VecSetValue(B, m, b[m], INSERT_VALUES));
+    if (nz > 1) CHK(Fft3DTransportSolver(nx, ny, nz, ax, ay, az, dt, dx, dy, dz, X, B, FFT_MAT));
+    else if (ny > 1) CHK(Fft2DTransportSolver(nx, ny, ax, ay, dt, dx, dy, X, B, FFT_MAT));
+    else CHK(Fft1DTransportSolver(nx, ax, dt, dx, X, B, FFT_MAT));
+    const double e1 = rel_err(X->array, xref);
+    std::vector<PetscScalar> xs(X->array, X->array + N), r;
+    apply_C(xs, r, nx, ny, nz, ax * dt / dx, ay * dt / dy, az * dt / dz);
+    const double res = rel_err(r.data(), b);
+    // second call on the same Mat, in place (the time loop of TransportEquationFFT_..._impl_mpi.cxx:107-112)
+    StructuredTransportContext sc = { nx, ny, nz, ax, ay, az, dt, dx, dy, dz, FFT_MAT };
+    CHK(PetscFft3DTransportSolver(sc, B, B));
+    const double e2 = rel_err(B->array, xref);
+    printf("%-28s %4d x %3d x %3d : rel error %.2e, rel residual %.2e, in-place 2nd call %.2e\n", name, nx, ny, nz, e1,
+           res, e2);
+    EXPECT(e1 < 1e-12 && res < 1e-12 && e2 < 1e-12, "%s above tolerance", name);
+    CHK(VecDestroy(&X));
+    CHK(VecDestroy(&B));
+    CHK(MatDestroy(&FFT_MAT));
+    return 0;
+}
+
+static int explicit_diag_case()
+{
+    // the long way round, as setupFFTPrec3D does it: columns, 1-D DFTs, build_diag_mat_vec_3D, solve_3D
+    const int nx = 4, ny = 3, nz = 2, N = nx * ny * nz;
+    const int n[3] = { nx, ny, nz };
+    Vec c[3], ch[3];
+    for (int a = 0; a < 3; ++a) {
+        Mat F1;
+        PetscInt d1[1] = { n[a] };
+        CHK(MatCreateFFT(PETSC_COMM_WORLD, 1, d1, MATFFTW, &F1));
+        CHK(MatCreateVecsFFTW(F1, &c[a], &ch[a], NULL));
+        CHK(build_transport_col(c[a], n[a]));
+        CHK(MatMult(F1, c[a], ch[a]));
+        CHK(MatDestroy(&F1));
+    }
+    Mat FFT_MAT;
+    PetscInt dims[3] = { nz, ny, nx };
+    CHK(MatCreateFFT(PETSC_COMM_WORLD, 3, dims, MATFFTW, &FFT_MAT));
+    Vec Diag, B, Bh, X;
+    CHK(MatCreateVecsFFTW(FFT_MAT, &B, &Bh, &X));
+    CHK(MatCreateVecsFFTW(FFT_MAT, NULL, &Diag, NULL));
+    CHK(build_diag_mat_vec_3D(Diag, ch[0], ch[1], ch[2], nx, ny, nz, 1.0, 1.0, 1.0));
+    // Lambda[0..5]
+    const PetscScalar want[6] = { { 1, 0 }, { 2, 1 }, { 3, 0 }, { 2, -1 }, { 2.5, 0.8660254037844386 }, { 3.5, 1.8660254037844386 } };
+    for (int m = 0; m < 6; ++m) EXPECT(std::abs(Diag->array[m] - want[m]) < 1e-14, "Diag[%d] = (%g,%g)", m, Diag->array[m].real(), Diag->array[m].imag());
+    std::vector<PetscScalar> xref(N), b;
+    for (int m = 0; m < N; ++m) xref[m] = (double)m * m * m;
+    apply_C(xref, b, nx, ny, nz, 1, 1, 1);
+    const double bwant[6] = { -2267, -2922, -3713, -4606, -4183, -4478 };
+    for (int m = 0; m < 6; ++m) EXPECT(std::abs(b[m] - bwant[m]) < 1e-9, "b[%d]", m);
+    for (int m = 0; m < N; ++m) CHK(VecSetValue(B, m, b[m], INSERT_VALUES));
+    CHK(solve_3D(FFT_MAT, X, Diag, B, Bh, N));
+    const double e = rel_err(X->array, xref);
+    printf("%-28s %4d x %3d x %3d : rel error %.2e (solve_3D with explicit Diag)\n", "KAT-3 explicit Diag", nx, ny, nz, e);
+    EXPECT(e < 1e-12, "solve_3D explicit Diag");
+    // wrong size is an argument error, not a crash
+    EXPECT(solve_3D(FFT_MAT, X, Diag, B, Bh, N + 1) == PETSC_ERR_ARG_WRONG, "size check");
+    for (int a = 0; a < 3; ++a) { CHK(VecDestroy(&c[a])); CHK(VecDestroy(&ch[a])); }
+    CHK(VecDestroy(&Diag)); CHK(VecDestroy(&B)); CHK(VecDestroy(&Bh)); CHK(VecDestroy(&X));
+    CHK(MatDestroy(&FFT_MAT));
+    return 0;
+}
+
+static int pcshell_case()
+{
+    // what KSP does with a PCSHELL: set up once, apply per iteration, destroy
+    const int n = 16, N = n * n * n;
+    const double a[3] = { 1.0, 0.5, 0.25 }, dt = 0.4;
+    FFTPrecTransportContext *ctx = nullptr;
+    CHK(getFFTPrec3DContextCreate(3, dt, N, a[0], a[1], a[2], -0.5, -0.5, -0.5, 0.5, 0.5, 0.5, &ctx));
+    EXPECT(ctx->n_x == n && ctx->n_y == n && ctx->n_z == n, "cube root of nbCells");
+    EXPECT(std::abs(ctx->lambda_x - a[0] * dt * n) < 1e-12, "lambda_x = a dt n / L");
+    PC pc;
+    CHK(PCCreate(PETSC_COMM_WORLD, &pc));
+    CHK(PCShellFFT3DAttach(pc, ctx));
+    CHK(PCSetUp(pc));
+    std::vector<PetscScalar> xref(N), b;
+    for (int m = 0; m < N; ++m) xref[m] = std::sin(0.37 * m) + 2.0;
+    apply_C(xref, b, n, n, n, a[0] * dt * n, a[1] * dt * n, a[2] * dt * n);
+    Vec B, X;
+    CHK(VecCreateSeq(PETSC_COMM_WORLD, N, &B));
+    CHK(VecDuplicate(B, &X));
+    for (int m = 0; m < N; ++m) CHK(VecSetValue(B, m, b[m], INSERT_VALUES));
+    double worst = 0;
+    for (int it = 0; it < 3; ++it) {
+        CHK(PCApply(pc, B, X));
+        worst = std::fmax(worst, rel_err(X->array, xref));
+    }
+    printf("%-28s %4d x %3d x %3d : worst rel error over 3 PCApply %.2e\n", "PCSHELL life cycle", n, n, n, worst);
+    EXPECT(worst < 1e-12, "PCApply");
+    CHK(PCDestroy(&pc));
+    EXPECT(ctx->FFT_MAT == nullptr && ctx->Diag == nullptr, "destroyFFTPrec3D released the context's objects");
+    CHK(FFTPrec3DContextFree(&ctx));
+    CHK(VecDestroy(&B));
+    CHK(VecDestroy(&X));
+    return 0;
+}
+
+int main()
+{
+    if (direct_solver_case(4, 1, 1, 1, 0, 0, 0.5, 1, 1, 1, "1-D (testFftSolver_1D.c)")) return 1;
+    if (direct_solver_case(3, 2, 1, 1, 1, 0, 1, 1, 1, 1, "2-D KAT-2 (testFftSolver_2D.c)")) return 1;
+    if (direct_solver_case(4, 3, 2, 1, 1, 1, 1, 1, 1, 1, "3-D KAT-3 (testFftSolver_3D.c)")) return 1;
+    if (direct_solver_case(10, 25, 40, 6, 3, 1, 0.01, 0.1, 0.2, 0.5, "3-D (testFftSolver_3D.py)")) return 1;
+    if (direct_solver_case(32, 32, 32, 6, 3, 1, 0.01, 0.1, 0.2, 0.5, "32^3 (BASELINE config 0)")) return 1;
+    if (explicit_diag_case()) return 1;
+    if (pcshell_case()) return 1;
+    printf(g_fail ? "FAILED (%d)\n" : "ALL PASSED\n", g_fail);
+    return g_fail ? 1 : 0;
+}

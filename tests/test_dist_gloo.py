@@ -1,0 +1,87 @@
+"""CPU test of the multi-rank (z-slab) schedule: world_size-2 gloo processes replay the distributed apply with numpy
+1-D FFTs, using the library's own layout helpers (cpc_slab_range / cpc_slab_send_chunk / cpc_slab_recv_chunk) for the
+"zero-pack" chunk layout that the CUDA y-pass writes and NCCL ships.  Result must equal the single-process oracle."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from tests.conftest import rel_l2
+
+
+def _chunk(fn, nx, ny, nz, nc, P, r, q):
+    o, c = ctypes.c_int64(), ctypes.c_int64()
+    assert fn(nx, ny, nz, nc, P, r, q, ctypes.byref(o), ctypes.byref(c)) == 0
+    return o.value, c.value
+
+
+def _exchange(send, send_chunks, recv_chunks, rank, P):
+    """all-to-all built from all_gather (gloo has no all_to_all): chunk q of every rank's send buffer goes to rank q."""
+    bufs = [torch.empty_like(send) for _ in range(P)]
+    dist.all_gather(bufs, send)
+    out = torch.empty_like(send)
+    for s in range(P):
+        so, sc = send_chunks[s][rank]          # what rank s sends to me
+        ro, rc = recv_chunks[s]                # where it lands here
+        assert sc == rc
+        out[ro:ro + rc] = bufs[s][so:so + sc]
+    return out
+
+
+def _worker(rank, P, port, shape, lam, b_full, ret):
+    import circulantpreconditioner_b200 as cpc
+    from oracle import circulant_oracle as O
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=P)
+    L = cpc.lib()
+    nx, ny, nz = shape
+    z0, nzl = cpc.slab_range(nz, P, rank)
+    y0, nyl = cpc.slab_range(ny, P, rank)
+    send_chunks = [[_chunk(L.cpc_slab_send_chunk, nx, ny, nz, 1, P, s, q) for q in range(P)] for s in range(P)]
+    recv_chunks = [_chunk(L.cpc_slab_recv_chunk, nx, ny, nz, 1, P, rank, s) for s in range(P)]
+    back_recv = [send_chunks[rank][q] for q in range(P)]
+
+    slab = b_full.reshape(nz, ny, nx)[z0:z0 + nzl].copy()
+    slab = np.fft.fft(np.fft.fft(slab, axis=2), axis=1)                      # Fx, Fy on the z-slab
+    send = np.empty(slab.size, dtype=np.complex128)
+    for q in range(P):                                                        # [q][z_loc][y_loc][x]
+        yq0, nyq = cpc.slab_range(ny, P, q)
+        o, c = send_chunks[rank][q]
+        send[o:o + c] = slab[:, yq0:yq0 + nyq, :].ravel()
+    tr = _exchange(torch.from_numpy(send), send_chunks, recv_chunks, rank, P).numpy().reshape(nz, nyl, nx)
+    Diag = O.transport_diag(nx, ny, nz, *lam).reshape(nz, ny, nx)[:, y0:y0 + nyl, :]
+    tr = np.fft.ifft(np.fft.fft(tr, axis=0) / Diag, axis=0) * nz             # Fz . 1/Lambda . Bz (unnormalised Bz)
+    # reverse exchange: chunk s of the transposed buffer goes back to rank s
+    rsend_chunks = [[_chunk(L.cpc_slab_recv_chunk, nx, ny, nz, 1, P, s, q) for q in range(P)] for s in range(P)]
+    back = _exchange(torch.from_numpy(tr.ravel().copy()), rsend_chunks, back_recv, rank, P).numpy()
+    slab2 = np.empty((nzl, ny, nx), dtype=np.complex128)
+    for q in range(P):
+        yq0, nyq = cpc.slab_range(ny, P, q)
+        o, c = send_chunks[rank][q]
+        slab2[:, yq0:yq0 + nyq, :] = back[o:o + c].reshape(nzl, nyq, nx)
+    slab2 = np.fft.ifft(np.fft.ifft(slab2, axis=1), axis=2) * (ny * nx) / (nx * ny * nz)
+    parts = [None] * P
+    dist.all_gather_object(parts, (z0, slab2))
+    if rank == 0:
+        full = np.concatenate([p[1] for p in sorted(parts, key=lambda t: t[0])], axis=0).ravel()
+        ret["x"] = full
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,P", [((8, 6, 4), 2), ((5, 10, 6), 2)])   # ny, nz divisible by P, as the CUDA path requires
+def test_slab_schedule_world_size_2(shape, P):
+    from oracle import circulant_oracle as O
+    nx, ny, nz = shape
+    rng = np.random.default_rng(1)
+    lam = (0.6, 0.15, 2.0)
+    b = rng.standard_normal(nx * ny * nz) + 1j * rng.standard_normal(nx * ny * nz)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(P, port, shape, lam, b, ret), nprocs=P, join=True)
+    assert rel_l2(ret["x"], want) < 1e-13

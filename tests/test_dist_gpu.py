@@ -1,0 +1,80 @@
+"""Multi-GPU parity (-m gpu, needs >= 2 GPUs: run with `gpurun --gpus 2 -- python -m pytest tests/test_dist_gpu.py -m gpu`).
+One process per GPU, NCCL all-to-all inside libcirculantpc; every rank's slab must match the single-process oracle."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, P, port, shape, lam, b_full, want, ncomp, wave, errs):
+    import circulantpreconditioner_b200 as cpc
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=P, device_id=torch.device("cuda", rank))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(cpc.nccl_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    nx, ny, nz = shape
+    z0, nzl = cpc.slab_range(nz, P, rank)
+    plane = nx * ny * ncomp
+    loc = torch.from_numpy(b_full[z0 * plane:(z0 + nzl) * plane].copy()).cuda()
+    with cpc.CirculantPlan(nx, ny, nz, ncomp=ncomp, nranks=P, rank=rank, nccl_id=idt.cpu().numpy().tobytes()) as p:
+        if wave:
+            p.set_symbol_wave(*lam)
+        else:
+            p.set_symbol_transport(*lam)
+        out = torch.empty_like(loc)
+        p.apply(loc, out)
+        e1 = np.linalg.norm(out.cpu().numpy() - want[z0 * plane:(z0 + nzl) * plane]) / np.linalg.norm(want)
+        p.apply(loc, loc)                      # in place
+        e2 = np.linalg.norm(loc.cpu().numpy() - want[z0 * plane:(z0 + nzl) * plane]) / np.linalg.norm(want)
+        # forward then inverse returns N * input
+        src = torch.from_numpy(b_full[z0 * plane:(z0 + nzl) * plane].copy()).cuda()
+        f = p.forward(src)
+        bk = p.inverse(f)
+        e3 = (torch.linalg.vector_norm(bk / (nx * ny * nz) - src) / torch.linalg.vector_norm(src)).item()
+    errs[rank] = (float(e1), float(e2), float(e3))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run(shape, lam, ncomp=1, wave=False, P=2):
+    from oracle import circulant_oracle as O
+    if torch.cuda.device_count() < P:
+        pytest.skip(f"needs {P} GPUs")
+    nx, ny, nz = shape
+    rng = np.random.default_rng(5)
+    n = nx * ny * nz * ncomp
+    b = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex128)
+    want = O.solve_wave_block(b, nx, ny, nz, *lam) if wave else O.FftTransportSolver(nx, ny, nz, *lam, b)
+    mgr = mp.Manager()
+    errs = mgr.dict()
+    port = 29600 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(P, port, shape, lam, b, want, ncomp, wave, errs), nprocs=P, join=True)
+    return dict(errs)
+
+
+@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 32, 16), (32, 16, 256), (20, 12, 10)])
+def test_two_rank_transport(shape):
+    errs = _run(shape, (55.5556, 0.3, 2.5))
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
+
+
+def test_two_rank_wave_block():
+    errs = _run((32, 32, 32), (3.0, 0.0793651, 0.0793651, 0.0793651), ncomp=4, wave=True)
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
+
+
+def test_four_rank_transport():
+    errs = _run((64, 64, 64), (1.0, 2.0, 3.0), P=4)
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
