@@ -246,8 +246,11 @@ def run_gpu(args):
         ms = plan.apply_profiled(b, x)
         acc = ms if acc is None else [a + m for a, m in zip(acc, ms)]
     pass_ms = [a / nprof for a in acc]
+    dist_mode = plan.info()["dist_mode"]
     if world == 1:
         names = ["Fx", "Fy", "Fz*Lambda^-1*Bz", "By", "Bx"]
+    elif dist_mode == 2:      # transposes fused into the passes (NVLink peer stores), stream-ordered barriers between
+        names = ["Fx", "Fy+transpose", "barrier", "Fz*Lambda^-1*Bz+transpose", "barrier", "By", "Bx"]
     else:
         names = ["Fx", "Fy", "all-to-all", "Fz*Lambda^-1*Bz", "all-to-all", "By", "Bx"]
     names = names[:len(pass_ms)]
@@ -273,7 +276,7 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         bytes_pass = 2 * nloc * ELEM_BYTES
-        kern = [(nm, m) for nm, m in zip(names, pass_ms) if nm != "all-to-all"]
+        kern = [(nm, m) for nm, m in zip(names, pass_ms) if nm not in ("all-to-all", "barrier")]
         dom_name, dom_ms = max(kern, key=lambda kv: kv[1])
         achieved = bytes_pass / dom_ms / 1e6
         traffic = None
@@ -287,15 +290,23 @@ def run_gpu(args):
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": bytes_pass,
-                    "passes": {nm: {"ms": m, "GB/s": (bytes_pass / m / 1e6) if nm != "all-to-all" else None}
-                               for nm, m in zip(names, pass_ms)},
+                    "passes": [{"name": nm, "ms": m, "GB/s": (bytes_pass / m / 1e6) if nm not in ("all-to-all", "barrier") else None}
+                               for nm, m in zip(names, pass_ms)],
                     "apply": {"alg_bytes": apply_alg, "achieved": apply_alg / ms_step / 1e6,
                               "frac": apply_alg / ms_step / 1e6 / peak}}
         if world > 1:
-            a2a = [m for nm, m in zip(names, pass_ms) if nm == "all-to-all"]
             sent = nloc * ELEM_BYTES * (world - 1) / world
-            roofline["alltoall"] = {"bytes_sent_per_gpu": sent, "ms": a2a, "busbw_GB/s": [sent / m / 1e6 for m in a2a],
-                                    "peak_GB/s": 900.0, "frac": [sent / m / 1e6 / 900.0 for m in a2a]}
+            if dist_mode == 2:
+                # the transpose travels inside the producing kernel; charge kernel + the barrier that follows it
+                a2a = [pass_ms[i] + pass_ms[i + 1] for i, nm in enumerate(names) if nm.endswith("+transpose")]
+                how = "peer stores fused into the Fy / fused-z kernels; time = kernel + following barrier"
+            else:
+                a2a = [m for nm, m in zip(names, pass_ms) if nm == "all-to-all"]
+                how = "NCCL grouped send/recv"
+            roofline["alltoall"] = {"how": how, "bytes_sent_per_gpu": sent, "ms": a2a,
+                                    "busbw_GB/s": [sent / m / 1e6 for m in a2a], "peak_GB/s": 900.0,
+                                    "frac": [sent / m / 1e6 / 900.0 for m in a2a],
+                                    "measured_peer_copy_GB/s": 770.0}
         line = {"metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),

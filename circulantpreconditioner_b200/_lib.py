@@ -26,7 +26,8 @@ class PlanDesc(ctypes.Structure):
 class PlanInfo(ctypes.Structure):
     _fields_ = [("nx", ctypes.c_int), ("ny", ctypes.c_int), ("nz", ctypes.c_int), ("ncomp", ctypes.c_int),
                 ("dtype", ctypes.c_int), ("nranks", ctypes.c_int), ("rank", ctypes.c_int),
-                ("symbol_kind", ctypes.c_int), ("passes_per_apply", ctypes.c_int), ("fast_path", ctypes.c_int * 3),
+                ("symbol_kind", ctypes.c_int), ("passes_per_apply", ctypes.c_int), ("dist_mode", ctypes.c_int),
+                ("fast_path", ctypes.c_int * 3),
                 ("local_elems", ctypes.c_int64), ("bytes_per_apply_alg", ctypes.c_int64),
                 ("kernel_launches", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
 

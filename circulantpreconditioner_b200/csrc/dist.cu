@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "plan.h"
 
@@ -27,6 +28,7 @@ struct Api {
     ncclResult_tt (*Send)(const void *, size_t, int, int, ncclComm_tt, cudaStream_t) = nullptr;
     ncclResult_tt (*Recv)(void *, size_t, int, int, ncclComm_tt, cudaStream_t) = nullptr;
     ncclResult_tt (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_tt, cudaStream_t) = nullptr;
+    ncclResult_tt (*AllGather)(const void *, void *, size_t, int, ncclComm_tt, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_tt) = nullptr;
     bool ok = false;
 };
@@ -53,6 +55,7 @@ void load_api()
     LOAD(Send, "ncclSend")
     LOAD(Recv, "ncclRecv")
     LOAD(AllReduce, "ncclAllReduce")
+    LOAD(AllGather, "ncclAllGather")
     LOAD(GetErrorString, "ncclGetErrorString")
 #undef LOAD
     g_api.ok = true;
@@ -109,8 +112,62 @@ int dist_init(DistState &d, int nranks, int rank, const void *unique_id128, int 
 
 void dist_destroy(DistState &d)
 {
+    if (d.barrier_buf) cudaFree(d.barrier_buf);
+    d.barrier_buf = nullptr;
     if (d.comm && g_api.ok) g_api.CommDestroy((ncclComm_tt)d.comm);
     d.comm = nullptr;
+}
+
+int dist_map_peers(DistState &d, void *local, void **peers, int device, cudaStream_t stream)
+{
+    for (int q = 0; q < d.nranks; ++q) peers[q] = nullptr;
+    peers[d.rank] = local;
+    if (d.nranks == 1) return CPC_OK;
+    CPC_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t mine;
+    CPC_CUDA(cudaIpcGetMemHandle(&mine, local));
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    char *dev = nullptr;
+    CPC_CUDA(cudaMalloc(&dev, hs * (size_t)(d.nranks + 1)));
+    CPC_CUDA(cudaMemcpyAsync(dev + hs * d.nranks, &mine, hs, cudaMemcpyHostToDevice, stream));
+    CPC_NCCL(g_api.AllGather(dev + hs * d.nranks, dev, hs, NCCL_UINT8, (ncclComm_tt)d.comm, stream));
+    std::vector<cudaIpcMemHandle_t> all(d.nranks);
+    CPC_CUDA(cudaMemcpyAsync(all.data(), dev, hs * d.nranks, cudaMemcpyDeviceToHost, stream));
+    CPC_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(dev);
+    int rc = CPC_OK;
+    for (int q = 0; q < d.nranks && rc == CPC_OK; ++q) {
+        if (q == d.rank) continue;
+        cudaError_t e = cudaIpcOpenMemHandle(&peers[q], all[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaIpcOpenMemHandle(rank %d) failed: %s", q, cudaGetErrorString(e));
+            peers[q] = nullptr;
+            rc = CPC_ERR_UNSUPPORTED;
+        }
+    }
+    // every rank must agree on the outcome, otherwise one would push while another waits for NCCL
+    float flag = rc == CPC_OK ? 0.f : 1.f, *dflag = nullptr;
+    CPC_CUDA(cudaMalloc(&dflag, sizeof(float)));
+    CPC_CUDA(cudaMemcpyAsync(dflag, &flag, sizeof(float), cudaMemcpyHostToDevice, stream));
+    CPC_NCCL(g_api.AllReduce(dflag, dflag, 1, NCCL_FLOAT32, NCCL_SUM, (ncclComm_tt)d.comm, stream));
+    CPC_CUDA(cudaMemcpyAsync(&flag, dflag, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CPC_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(dflag);
+    if (flag != 0.f) {
+        dist_unmap_peers(d, peers);
+        if (rc == CPC_OK) set_error("a peer rank could not map IPC memory");
+        return CPC_ERR_UNSUPPORTED;
+    }
+    return CPC_OK;
+}
+
+void dist_unmap_peers(DistState &d, void **peers)
+{
+    for (int q = 0; q < d.nranks; ++q) {
+        if (q != d.rank && peers[q]) cudaIpcCloseMemHandle(peers[q]);
+        peers[q] = nullptr;
+    }
 }
 
 int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes, cudaStream_t stream)
@@ -133,9 +190,11 @@ int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes
 int dist_barrier(DistState &d, cudaStream_t stream)
 {
     if (d.nranks == 1) return CPC_OK;
-    static thread_local float *buf = nullptr;
-    if (!buf) CPC_CUDA(cudaMalloc(&buf, sizeof(float)));
-    CPC_NCCL(g_api.AllReduce(buf, buf, 1, NCCL_FLOAT32, NCCL_SUM, (ncclComm_tt)d.comm, stream));
+    if (!d.barrier_buf) {
+        CPC_CUDA(cudaMalloc(&d.barrier_buf, sizeof(float)));
+        CPC_CUDA(cudaMemsetAsync(d.barrier_buf, 0, sizeof(float), stream));
+    }
+    CPC_NCCL(g_api.AllReduce(d.barrier_buf, d.barrier_buf, 1, NCCL_FLOAT32, NCCL_SUM, (ncclComm_tt)d.comm, stream));
     return CPC_OK;
 }
 

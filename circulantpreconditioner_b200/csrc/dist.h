@@ -11,6 +11,7 @@ namespace cpc {
 struct DistState {
     int nranks = 1, rank = 0;
     void *comm = nullptr;        // ncclComm_t
+    float *barrier_buf = nullptr;
 };
 
 // Loads libnccl.so.2 on first use.  Returns CPC_OK or CPC_ERR_NCCL (message via cpc_last_error()).
@@ -22,5 +23,10 @@ void dist_destroy(DistState &d);
 int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes, cudaStream_t stream);
 // Stream-ordered barrier across ranks (1-element all-reduce).
 int dist_barrier(DistState &d, cudaStream_t stream);
+// Exchange CUDA IPC handles of `local` (a cudaMalloc'ed buffer) through an NCCL all-gather and map every peer's
+// buffer: peers[q] = address of rank q's buffer in this process (peers[rank] = local).  CPC_ERR_UNSUPPORTED when a
+// peer cannot be mapped (the caller then keeps the NCCL all-to-all path).
+int dist_map_peers(DistState &d, void *local, void **peers, int device, cudaStream_t stream);
+void dist_unmap_peers(DistState &d, void **peers);
 
 }  // namespace cpc

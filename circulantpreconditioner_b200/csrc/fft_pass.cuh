@@ -31,6 +31,8 @@
 
 namespace cpc {
 
+#define CPC_MAX_PEERS 8
+
 // Geometry of one pass (all in units of complex elements).
 struct PassGeom {
     long long SI;         // stride between consecutive points of a line
@@ -50,6 +52,11 @@ struct PassGeom {
     int ncomp, nx, ny;
     int y0;               // global y of local y index 0 (multi-rank transposed slab)
     int pf_tiles;         // > 0: prefetch into L2 the tile `pf_tiles` after this one (about one wave of CTAs ahead)
+    // Fused transpose (multi-rank plans with peer access): with npeer > 0 the chunk index i / Do selects the rank
+    // whose buffer receives the point, and the store goes straight to that rank's HBM over NVLink
+    // (peer[q] is the IPC-mapped base of rank q's buffer, already offset to this rank's slot).
+    int npeer;
+    void *peer[CPC_MAX_PEERS];
 };
 
 enum PassMode { MODE_FWD = 0, MODE_INV = 1, MODE_FUSED_SEP = 2, MODE_FUSED_TABLE = 3, MODE_FUSED_WAVE = 4 };
@@ -64,6 +71,20 @@ template <typename T> struct SymbolArgs {
     T c0, mux, muy, muz;
     T scale;
 };
+
+// Output address of point i of a line: local (split or plain) or a peer's buffer.
+template <typename C>
+__device__ __forceinline__ C *out_ptr(C *out, const PassGeom &g, long long obase, int i)
+{
+    if (g.npeer > 0) {
+        const int q = g.sho >= 0 ? (i >> g.sho) : (i / g.Do);
+        const int r = g.sho >= 0 ? (i & (g.Do - 1)) : (i % g.Do);
+        return reinterpret_cast<C *>(g.peer[q]) + obase + (long long)r * g.SIo;
+    }
+    if (g.Do == 0) return out + obase + (long long)i * g.SIo;
+    if (g.sho >= 0) return out + obase + (long long)(i >> g.sho) * g.SCo + (long long)(i & (g.Do - 1)) * g.SIo;
+    return out + obase + (long long)(i / g.Do) * g.SCo + (long long)(i % g.Do) * g.SIo;
+}
 
 __device__ __forceinline__ long long point_off(int i, long long S, int D, int sh, long long SC)
 {
@@ -290,7 +311,7 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
 
     if (active) {
 #pragma unroll
-        for (int m = 0; m < E; ++m) out[obase + point_off(j + TPL * m, g.SIo, g.Do, g.sho, g.SCo)] = v[m];
+        for (int m = 0; m < E; ++m) *out_ptr<C>(out, g, obase, j + TPL * m) = v[m];
     }
 }
 

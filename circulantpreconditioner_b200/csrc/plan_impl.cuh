@@ -237,6 +237,8 @@ template <typename T> struct PlanT : PlanBase {
     // multi-rank
     DistState dist;
     C *sendbuf = nullptr, *tbuf = nullptr;
+    bool p2p = false;                         // peers' buffers are IPC-mapped: transposes are fused into the passes
+    void *peer_t[CPC_MAX_PEERS] = {}, *peer_s[CPC_MAX_PEERS] = {};
 
     ~PlanT() override
     {
@@ -249,6 +251,14 @@ template <typename T> struct PlanT : PlanBase {
         }
         if (inv_table) cudaFree(inv_table);
         if (dbuf) cudaFree(dbuf);
+        if (p2p) {
+            dist_barrier(dist, stream);
+            cudaStreamSynchronize(stream);
+            dist_unmap_peers(dist, peer_t);
+            dist_unmap_peers(dist, peer_s);
+            dist_barrier(dist, stream);          // nobody frees a buffer a peer still has mapped
+            cudaStreamSynchronize(stream);
+        }
         if (sendbuf) cudaFree(sendbuf);
         if (tbuf) cudaFree(tbuf);
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -378,6 +388,16 @@ template <typename T> struct PlanT : PlanBase {
             if (rc) return rc;
             CPC_CUDA(cudaMalloc(&sendbuf, sizeof(C) * nloc));
             CPC_CUDA(cudaMalloc(&tbuf, sizeof(C) * nloc));
+            // Fused transposes need every peer's buffers mapped (CUDA IPC over NVLink); otherwise NCCL all-to-all.
+            const char *mode = getenv("CPC_DIST_MODE");
+            const bool want_p2p = !(mode && strcmp(mode, "nccl") == 0) && desc.nranks <= CPC_MAX_PEERS;
+            if (want_p2p) {
+                int r1 = dist_map_peers(dist, tbuf, peer_t, device, stream);
+                int r2 = r1 == CPC_OK ? dist_map_peers(dist, sendbuf, peer_s, device, stream) : r1;
+                if (r1 == CPC_OK && r2 != CPC_OK) dist_unmap_peers(dist, peer_t);
+                p2p = (r1 == CPC_OK && r2 == CPC_OK);
+                if (!p2p && r1 != CPC_ERR_UNSUPPORTED && r2 != CPC_ERR_UNSUPPORTED) return r1 ? r1 : r2;
+            }
         }
         return CPC_OK;
     }
@@ -425,6 +445,8 @@ template <typename T> struct PlanT : PlanBase {
         g.SIo = g.SI; g.B0o = g.B0; g.B1o = g.B1;
         g.SCi = g.SCo = 0; g.Di = g.Do = 0; g.shi = g.sho = -1;
         g.pf_tiles = 0;
+        g.npeer = 0;
+        for (int q = 0; q < CPC_MAX_PEERS; ++q) g.peer[q] = nullptr;
         return g;
     }
 
@@ -459,12 +481,32 @@ template <typename T> struct PlanT : PlanBase {
 
     // Launch one pass.  `in`/`out` point at the start of the local array.
     // split: 0 = none, 1 = store side chunked (forward y of a multi-rank plan), 2 = load side chunked (backward y)
+    // split: 0 = none, 1 = store side chunked, 2 = load side chunked, 3 = stores pushed to the peers' transposed
+    // buffers (forward y), 4 = stores pushed to the peers' chunked buffers (fused z)
     int run_pass(int axis, int mode, const C *in, C *out, int zb, int zc, int layout, cudaStream_t st, int split = 0)
     {
         const AxisCfg &c = cfg[axis];
         long long off = 0;
         PassGeom g = make_geom(axis, c.tx, zb, zc, layout, &off);
-        if (split) make_split(g, split == 1);
+        if (split == 1 || split == 2) make_split(g, split == 1);
+        if (split == 3 || split == 4) {
+            const long long W = (long long)n[0] * nc;
+            int sh = -1;
+            const int D = split == 3 ? nyl : nzl;
+            for (int b = 0; b < 31; ++b)
+                if ((1 << b) == D) sh = b;
+            g.npeer = desc.nranks;
+            g.Do = D; g.sho = sh; g.SCo = 0;
+            if (split == 3) {
+                // point ky of the y line at (z_loc, x) -> rank q = ky / nyl, element [(z0 + z_loc)][ky % nyl][x]
+                g.SIo = W; g.B0o = g.B0; g.B1o = (long long)nyl * W;
+                for (int q = 0; q < desc.nranks; ++q) g.peer[q] = (C *)peer_t[q] + (long long)z0 * nyl * W;
+            } else {
+                // point k of the z line at (y_loc, x) -> rank s = k / nzl, element [me][k % nzl][y_loc][x]
+                g.SIo = (long long)nyl * W; g.B0o = g.B0; g.B1o = 0;
+                for (int q = 0; q < desc.nranks; ++q) g.peer[q] = (C *)peer_s[q] + (long long)desc.rank * (nloc / desc.nranks);
+            }
+        }
         if (g.ntiles <= 0) return CPC_OK;
         const SymbolArgs<T> s = symbol_args();
         if (c.fast) {
@@ -702,14 +744,28 @@ template <typename T> struct PlanT : PlanBase {
             cur = x;
             if ((rc = mark(++np))) return rc;
         }
-        if ((rc = run_pass(1, MODE_FWD, cur, sendbuf, 0, nzl, 0, stream, 1))) return rc;     // Fy, chunked store
-        if ((rc = mark(++np))) return rc;
-        if ((rc = alltoall(sendbuf, tbuf))) return rc;                                       // z-slab -> y-slab
-        if ((rc = mark(++np))) return rc;
-        if ((rc = run_pass(2, fm, tbuf, tbuf, 0, n[2], 1, stream))) return rc;               // Fz . 1/(N Lambda) . Bz
-        if ((rc = mark(++np))) return rc;
-        if ((rc = alltoall(tbuf, sendbuf))) return rc;                                       // y-slab -> z-slab
-        if ((rc = mark(++np))) return rc;
+        if (p2p) {
+            // transposes fused into the producing kernels: stores go straight to the owning rank over NVLink.
+            // Leading barrier: no peer may still be reading its buffers from an earlier call when pushes start.
+            if ((rc = dist_barrier(dist, stream))) return rc;
+            if ((rc = run_pass(1, MODE_FWD, cur, tbuf, 0, nzl, 0, stream, 3))) return rc;    // Fy -> peers' y-slabs
+            if ((rc = mark(++np))) return rc;
+            if ((rc = dist_barrier(dist, stream))) return rc;                                // all pushes have landed
+            if ((rc = mark(++np))) return rc;
+            if ((rc = run_pass(2, fm, tbuf, sendbuf, 0, n[2], 1, stream, 4))) return rc;     // fused z -> peers' z-slabs
+            if ((rc = mark(++np))) return rc;
+            if ((rc = dist_barrier(dist, stream))) return rc;
+            if ((rc = mark(++np))) return rc;
+        } else {
+            if ((rc = run_pass(1, MODE_FWD, cur, sendbuf, 0, nzl, 0, stream, 1))) return rc; // Fy, chunked store
+            if ((rc = mark(++np))) return rc;
+            if ((rc = alltoall(sendbuf, tbuf))) return rc;                                   // z-slab -> y-slab
+            if ((rc = mark(++np))) return rc;
+            if ((rc = run_pass(2, fm, tbuf, tbuf, 0, n[2], 1, stream))) return rc;           // Fz . 1/(N Lambda) . Bz
+            if ((rc = mark(++np))) return rc;
+            if ((rc = alltoall(tbuf, sendbuf))) return rc;                                   // y-slab -> z-slab
+            if ((rc = mark(++np))) return rc;
+        }
         if ((rc = run_pass(1, MODE_INV, sendbuf, x, 0, nzl, 0, stream, 2))) return rc;       // By, chunked load
         if ((rc = mark(++np))) return rc;
         if (n[0] > 1) {
@@ -864,6 +920,7 @@ template <typename T> struct PlanT : PlanBase {
         info->nranks = desc.nranks; info->rank = desc.rank;
         info->symbol_kind = symbol_kind;
         info->passes_per_apply = 1 + 2 * ((n[0] > 1) + (n[1] > 1));
+        info->dist_mode = desc.nranks == 1 ? 0 : (p2p ? 2 : 1);
         for (int a = 0; a < 3; ++a) info->fast_path[a] = cfg[a].fast ? 1 : 0;
         info->local_elems = nloc;
         info->bytes_per_apply_alg = 5ll * 2 * nloc * (long long)sizeof(C);

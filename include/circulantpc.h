@@ -125,6 +125,8 @@ typedef struct {
     int nx, ny, nz, ncomp, dtype, nranks, rank;
     int symbol_kind;
     int passes_per_apply;          /* HBM passes (kernel launches) of one cpc_apply */
+    int dist_mode;                 /* 0 single rank, 1 NCCL all-to-all transposes, 2 transposes fused into the passes
+                                      (stores pushed to IPC-mapped peer buffers over NVLink) */
     int fast_path[3];              /* 1 if axis x/y/z runs the templated Stockham kernel, 0 = generic kernel */
     int64_t local_elems;           /* elements (of ncomp * cells) held by this rank */
     int64_t bytes_per_apply_alg;   /* 5 passes x 2 x local_elems x sizeof(elem): SURVEY.md 8(d) */
