@@ -244,7 +244,10 @@ __device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int j, int w, lo
 // ---------------------------------------------------------------------------------------------------------------
 // The pass kernel.  E = points per thread (a multiple of every radix), TX = lines per tile, G = tiles per CTA.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int N, int R0, int R1, int R2, int E, int TX, int G, int MODE, int MINB, bool XMAP>
+// CL (fused modes only): run the backward transform as conj(FFT(conj(.))) inside a 2-trip loop, so the kernel holds
+// ONE copy of the transform code instead of a forward and a backward copy (the fused kernel is instruction-cache
+// bound otherwise: ~28 KB of straight-line SASS, 11 % "no instruction" stalls in ncu).
+template <typename T, int N, int R0, int R1, int R2, int E, int TX, int G, int MODE, int MINB, bool XMAP, bool CL = false>
 __global__ void __launch_bounds__((N / E) * TX * G, MINB)
 fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
                 const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
@@ -302,11 +305,22 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
         line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
     } else if (MODE == MODE_INV) {
         line_fft<T, N, R0, R1, R2, E, +1, TX, XMAP>(v, j, l, sm, tw);
-    } else {
+    } else if (!CL) {
         line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
         apply_symbol<T, N, E, MODE>(v, j, active ? w : 0, gbase, g.SI, g, sym);
         if (NST > 1) __syncthreads();
         line_fft<T, N, R0, R1, R2, E, +1, TX, XMAP>(v, j, l, sm, tw);
+    } else {
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
+            if (pass == 0) {
+                apply_symbol<T, N, E, MODE>(v, j, active ? w : 0, gbase, g.SI, g, sym);
+                if (NST > 1) __syncthreads();
+            }
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m].y = -v[m].y;
+        }
     }
 
     if (active) {

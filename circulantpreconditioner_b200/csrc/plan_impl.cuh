@@ -47,7 +47,8 @@ enum Variant {
 
 template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, variant, mode)
 
-template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF = MINB>
+template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF = MINB,
+          bool CL = false>
 static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
 {
     constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
@@ -60,11 +61,11 @@ static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
     e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_INV, MINB, XM>;
     m[FastKey<T>(N, VAR, MODE_INV)] = e;
     if constexpr (!XM) {
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_SEP, MINBF, XM>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_SEP, MINBF, XM, CL>;
         m[FastKey<T>(N, VAR, MODE_FUSED_SEP)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_TABLE, MINBF, XM>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_TABLE, MINBF, XM, CL>;
         m[FastKey<T>(N, VAR, MODE_FUSED_TABLE)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_WAVE, MINBF, XM>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_WAVE, MINBF, XM, CL>;
         m[FastKey<T>(N, VAR, MODE_FUSED_WAVE)] = e;
     }
 }
@@ -85,10 +86,6 @@ template <> struct FastRegistry<double> {
         register_modes<double, VAR_WIDE,    512,  8,  8,  8,  8,  8,  1, 2, 1>(m);
         register_modes<double, VAR_WIDE,   1024, 16,  8,  8, 16,  8,  1, 1>(m);
         register_modes<double, VAR_WIDE2,   512,  8,  8,  8, 16,  8,  1, 2>(m);
-        register_modes<double, VAR_EXP4,    512,  8,  8,  8,  8,  4,  1, 3>(m);      // 256 thr, <=80 regs, 3 CTA/SM
-        register_modes<double, VAR_EXP5,    512,  8,  8,  8,  8,  4,  1, 2>(m);      // 256 thr, <=128 regs, 2 CTA/SM
-        register_modes<double, VAR_EXP6,    512,  8,  8,  8,  8,  8,  1, 2, 2>(m);   // 512 thr, 64 regs fused, 2 CTA/SM
-        register_modes<double, VAR_EXP7,    512,  8,  8,  8, 16,  4,  1, 4>(m);      // 128 thr, E=16, <=128 regs, 4 CTA/SM
         register_modes<double, VAR_NARROW,   16, 16,  1,  1, 16,  4, 32, 2>(m);
         register_modes<double, VAR_NARROW,   32,  8,  4,  1,  8,  4, 16, 2>(m);
         register_modes<double, VAR_NARROW,   64,  8,  8,  1,  8,  4,  8, 2>(m);
