@@ -63,7 +63,7 @@ ABI = {
 
 CPC_MAX_PASSES = 16
 CPC_NCCL_UNIQUE_ID_BYTES = 128
-DTYPES = {"c128": 0, "c64": 1}
+DTYPES = {"c128": 0, "c64": 1, "f64": 2, "f32": 3}
 MEM_DEVICE, MEM_HOST = 0, 1
 
 

@@ -64,7 +64,7 @@ int cpc_plan_create(cpc_plan *plan, const cpc_plan_desc *d)
         return CPC_ERR_ARG;
     }
     if (d->ncomp != 1 && d->ncomp != 4) { set_error("cpc_plan_create: ncomp must be 1 or 4 (got %d)", d->ncomp); return CPC_ERR_ARG; }
-    if (d->dtype != CPC_C128 && d->dtype != CPC_C64) { set_error("cpc_plan_create: unknown dtype %d", d->dtype); return CPC_ERR_ARG; }
+    if (d->dtype < CPC_C128 || d->dtype > CPC_F32) { set_error("cpc_plan_create: unknown dtype %d", d->dtype); return CPC_ERR_ARG; }
     if (d->nranks < 1 || d->rank < 0 || d->rank >= d->nranks) {
         set_error("cpc_plan_create: bad rank %d of %d", d->rank, d->nranks);
         return CPC_ERR_ARG;
@@ -79,7 +79,7 @@ int cpc_plan_create(cpc_plan *plan, const cpc_plan_desc *d)
     if (dev < 0) CPC_CUDA(cudaGetDevice(&dev));
     if (dev >= ndev) { set_error("cpc_plan_create: device %d out of range (%d visible)", dev, ndev); return CPC_ERR_ARG; }
     CPC_CUDA(cudaSetDevice(dev));
-    PlanBase *impl = d->dtype == CPC_C128 ? make_plan_f64() : make_plan_f32();
+    PlanBase *impl = (d->dtype == CPC_C128 || d->dtype == CPC_F64) ? make_plan_f64() : make_plan_f32();
     if (!impl) { set_error("out of host memory"); return CPC_ERR_NOMEM; }
     impl->desc = *d;
     impl->device = dev;

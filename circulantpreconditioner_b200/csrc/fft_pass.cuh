@@ -36,7 +36,8 @@ namespace cpc {
 // Geometry of one pass (all in units of complex elements).
 struct PassGeom {
     long long SI;         // stride between consecutive points of a line
-    long long SL;         // stride between the TX lines of a tile
+    long long SL;         // stride between the TX lines of a tile (input side)
+    long long SLo;        // same on the output side (differs only in the r2c / c2r passes)
     long long B0, B1;     // tile t starts at (t / tiles_inner) * B1 + (t % tiles_inner) * B0
     int tiles_inner;
     int ntiles;
@@ -59,7 +60,12 @@ struct PassGeom {
     void *peer[CPC_MAX_PEERS];
 };
 
-enum PassMode { MODE_FWD = 0, MODE_INV = 1, MODE_FUSED_SEP = 2, MODE_FUSED_TABLE = 3, MODE_FUSED_WAVE = 4 };
+enum PassMode {
+    MODE_FWD = 0, MODE_INV = 1, MODE_FUSED_SEP = 2, MODE_FUSED_TABLE = 3, MODE_FUSED_WAVE = 4,
+    // real-scalar plans (XMAP x pass only): a real line of 2N points is transformed as N complex points
+    MODE_R2C = 5,     // forward: N-point FFT of z[m] = x[2m] + i x[2m+1], then untangle to X[0..N] (N+1 outputs)
+    MODE_C2R = 6      // backward: tangle X[0..N] into N complex points, N-point backward FFT, store as 2N reals
+};
 
 template <typename T> struct SymbolArgs {
     // separable: Lambda = ax[x] + ay[y] + az[k]  (ay carries the "+1"), result scaled by `scale` = 1/N
@@ -244,10 +250,7 @@ __device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int j, int w, lo
 // ---------------------------------------------------------------------------------------------------------------
 // The pass kernel.  E = points per thread (a multiple of every radix), TX = lines per tile, G = tiles per CTA.
 // ---------------------------------------------------------------------------------------------------------------
-// CL (fused modes only): run the backward transform as conj(FFT(conj(.))) inside a 2-trip loop, so the kernel holds
-// ONE copy of the transform code instead of a forward and a backward copy (the fused kernel is instruction-cache
-// bound otherwise: ~28 KB of straight-line SASS, 11 % "no instruction" stalls in ncu).
-template <typename T, int N, int R0, int R1, int R2, int E, int TX, int G, int MODE, int MINB, bool XMAP, bool CL = false>
+template <typename T, int N, int R0, int R1, int R2, int E, int TX, int G, int MODE, int MINB, bool XMAP>
 __global__ void __launch_bounds__((N / E) * TX * G, MINB)
 fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
                 const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
@@ -272,7 +275,7 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
     const int w = ti * TX + l;                                   // line index along the SL direction
     const bool active = tile_ok && (w < g.lines_inner);
     const long long gbase = (long long)to * g.B1 + (long long)ti * g.B0 + (long long)l * g.SL;
-    const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)l * g.SL;
+    const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)l * g.SLo;
 
     // Pull the tile that a later wave of CTAs will read towards L2 while this one computes: HBM stays busy during
     // the butterfly phases although only a few CTAs fit on an SM.  One 128-byte row per prefetch instruction.
@@ -305,22 +308,46 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
         line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
     } else if (MODE == MODE_INV) {
         line_fft<T, N, R0, R1, R2, E, +1, TX, XMAP>(v, j, l, sm, tw);
-    } else if (!CL) {
+    } else if (MODE == MODE_R2C) {
+        // Untangle (reference a2/a4 rows of SURVEY.md 8a: the real-scalar build's r2c transform):
+        //   X[k] = E[k] + w^k O[k],  E[k] = (Z[k] + conj Z[N-k]) / 2,  O[k] = -i (Z[k] - conj Z[N-k]) / 2,  w = exp(-i pi / N)
+        line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
+        constexpr int PS = Log2<R0>::v;
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < E; ++m) sm[sm_index<N, TX, PS, XMAP>(j + TPL * m, l)] = v[m];
+        __syncthreads();
+        C nyq = mk<T>((T)0, (T)0);
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int k = j + TPL * m;
+            const C a = v[m];
+            const C bq = sm[sm_index<N, TX, PS, XMAP>((N - k) & (N - 1), l)];
+            const C ev = mk<T>((T)0.5 * (a.x + bq.x), (T)0.5 * (a.y - bq.y));
+            const C od = mk<T>((T)0.5 * (a.y + bq.y), (T)-0.5 * (a.x - bq.x));       // -i (a - conj b) / 2
+            const C wk = sym.rx[k];                                                   // exp(-2 pi i k / (2N))
+            v[m] = cadd(ev, cmul(od, wk));
+            if (k == 0) nyq = mk<T>(a.x - a.y, (T)0);                                // X[N] = Re Z[0] - Im Z[0]
+        }
+        if (active && j == 0) out[obase + N] = nyq;
+    } else if (MODE == MODE_C2R) {
+        //   Z[k] = (X[k] + conj X[N-k]) + i conj(w^k) (X[k] - conj X[N-k])      (unnormalised, cf. MODE_R2C)
+#pragma unroll
+        for (int m = 0; m < E; ++m) {
+            const int k = j + TPL * m;
+            const C a = v[m];
+            const C bq = active ? in[gbase + (N - k)] : mk<T>((T)0, (T)0);
+            const C s1 = mk<T>(a.x + bq.x, a.y - bq.y);
+            const C d1 = mk<T>(a.x - bq.x, a.y + bq.y);
+            const C t1 = cmulc(d1, sym.rx[k]);                                        // conj(w^k) (a - conj b)
+            v[m] = mk<T>(s1.x - t1.y, s1.y + t1.x);                                   // s1 + i t1
+        }
+        line_fft<T, N, R0, R1, R2, E, +1, TX, XMAP>(v, j, l, sm, tw);
+    } else {
         line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
         apply_symbol<T, N, E, MODE>(v, j, active ? w : 0, gbase, g.SI, g, sym);
         if (NST > 1) __syncthreads();
         line_fft<T, N, R0, R1, R2, E, +1, TX, XMAP>(v, j, l, sm, tw);
-    } else {
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
-            if (pass == 0) {
-                apply_symbol<T, N, E, MODE>(v, j, active ? w : 0, gbase, g.SI, g, sym);
-                if (NST > 1) __syncthreads();
-            }
-#pragma unroll
-            for (int m = 0; m < E; ++m) v[m].y = -v[m].y;
-        }
     }
 
     if (active) {

@@ -125,7 +125,7 @@ __global__ void generic_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> 
     for (int idx = threadIdx.x; idx < n * TX; idx += blockDim.x) {
         const int i = idx / TX, l = idx - i * TX;
         if ((ti * TX + l) < g.lines_inner)
-            *out_ptr<C>(out, g, obase + (long long)l * g.SL, i) = res[idx];
+            *out_ptr<C>(out, g, obase + (long long)l * g.SLo, i) = res[idx];
     }
 }
 

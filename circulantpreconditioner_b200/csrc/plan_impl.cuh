@@ -47,8 +47,7 @@ enum Variant {
 
 template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, variant, mode)
 
-template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF = MINB,
-          bool CL = false>
+template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF = MINB>
 static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
 {
     constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
@@ -60,12 +59,18 @@ static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
     m[FastKey<T>(N, VAR, MODE_FWD)] = e;
     e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_INV, MINB, XM>;
     m[FastKey<T>(N, VAR, MODE_INV)] = e;
+    if constexpr (XM && NST > 1) {
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_R2C, MINB, XM>;
+        m[FastKey<T>(N, VAR, MODE_R2C)] = e;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_C2R, MINB, XM>;
+        m[FastKey<T>(N, VAR, MODE_C2R)] = e;
+    }
     if constexpr (!XM) {
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_SEP, MINBF, XM, CL>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_SEP, MINBF, XM>;
         m[FastKey<T>(N, VAR, MODE_FUSED_SEP)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_TABLE, MINBF, XM, CL>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_TABLE, MINBF, XM>;
         m[FastKey<T>(N, VAR, MODE_FUSED_TABLE)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_WAVE, MINBF, XM, CL>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_WAVE, MINBF, XM>;
         m[FastKey<T>(N, VAR, MODE_FUSED_WAVE)] = e;
     }
 }
@@ -86,6 +91,10 @@ template <> struct FastRegistry<double> {
         register_modes<double, VAR_WIDE,    512,  8,  8,  8,  8,  8,  1, 2, 1>(m);
         register_modes<double, VAR_WIDE,   1024, 16,  8,  8, 16,  8,  1, 1>(m);
         register_modes<double, VAR_WIDE2,   512,  8,  8,  8, 16,  8,  1, 2>(m);
+        register_modes<double, VAR_WIDE2,   256,  8,  8,  4,  8,  8,  2, 2>(m);      // 512 thr, 64 regs
+        register_modes<double, VAR_WIDE2,   128,  8,  4,  4,  8,  8,  4, 2>(m);      // 512 thr, 64 regs
+        register_modes<double, VAR_EXP5,    256,  8,  8,  4,  8,  8,  1, 4>(m);      // 256 thr, 64 regs, 4 CTAs/SM
+        register_modes<double, VAR_EXP4,   1024, 16,  8,  8, 16,  4,  1, 2>(m);      // 256 thr, 64 KB: 2 CTAs/SM
         register_modes<double, VAR_NARROW,   16, 16,  1,  1, 16,  4, 32, 2>(m);
         register_modes<double, VAR_NARROW,   32,  8,  4,  1,  8,  4, 16, 2>(m);
         register_modes<double, VAR_NARROW,   64,  8,  8,  1,  8,  4,  8, 2>(m);
@@ -177,6 +186,19 @@ __global__ void diag_from_invtable_kernel(double2 *__restrict__ diag, const cplx
     }
 }
 
+template <typename T>
+__global__ void real_to_complex_kernel(const T *__restrict__ in, cplx_t<T> *__restrict__ out, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = mk<T>(in[i], (T)0);
+}
+template <typename T>
+__global__ void complex_to_real_kernel(const cplx_t<T> *__restrict__ in, T *__restrict__ out, long long n)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = in[i].x;
+}
+
 // exp(-2 pi i m / n) rounded from long double
 static inline void exact_root(long long m, long long n, double *re, double *im)
 {
@@ -199,6 +221,7 @@ template <typename T> struct PlanT : PlanBase {
     struct AxisCfg {
         bool fast = false;
         int variant = 0;          // enum Variant of the fast kernel
+        int nfast = 0;            // transform length of the fast kernel (nx/2 for the r2c / c2r pass)
         int tx = 1;               // lanes per tile
         int threads = 0;          // generic kernel block size
         size_t smem_generic = 0;
@@ -207,6 +230,12 @@ template <typename T> struct PlanT : PlanBase {
 
     int n[3] = { 1, 1, 1 };
     int nc = 1;
+    // real-scalar plans (CPC_F64 / CPC_F32): b and x are real; the spectrum is the half spectrum [nz][ny][nxp],
+    // nxp = nx/2 + 1 rounded up to a multiple of 8 complex (128-byte rows) -- 5 passes of half the bytes.
+    bool real = false, real_promote = false;
+    int n2 = 0, nxp = 0;
+    long long wx = 0;             // contiguous complex elements per (y, z) row in the y and z passes
+    C *work = nullptr;            // half spectrum (real plans) or the promoted complex copy
     int num_sms = 148;
     int pf_waves = 0;             // L2 prefetch distance in units of (SM count) CTAs; 0 = off
     int nzl = 1, z0 = 0;          // local z slab
@@ -247,6 +276,7 @@ template <typename T> struct PlanT : PlanBase {
             if (sym_tab64[a]) cudaFree(sym_tab64[a]);
         }
         if (inv_table) cudaFree(inv_table);
+        if (work) cudaFree(work);
         if (dbuf) cudaFree(dbuf);
         if (p2p) {
             dist_barrier(dist, stream);
@@ -280,6 +310,12 @@ template <typename T> struct PlanT : PlanBase {
         nyl = yr.count; y0 = yr.start;
         if (desc.nranks == 1) { nyl = n[1]; y0 = 0; }
         nloc = (long long)n[0] * n[1] * nzl * nc;
+        wx = (long long)n[0] * nc;
+        real = (desc.dtype == CPC_F64 || desc.dtype == CPC_F32);
+        if (real) {
+            if (nc != 1) { set_error("real-scalar plans need ncomp == 1"); return CPC_ERR_ARG; }
+            if (desc.nranks != 1) { set_error("real-scalar plans are single-rank in this version"); return CPC_ERR_UNSUPPORTED; }
+        }
         if (desc.nranks > 1 && (n[2] % desc.nranks != 0 || n[1] % desc.nranks != 0)) {
             set_error("multi-rank plans need ny and nz divisible by nranks (ny=%d nz=%d nranks=%d)", n[1], n[2],
                       desc.nranks);
@@ -287,6 +323,18 @@ template <typename T> struct PlanT : PlanBase {
         }
         FastRegistry<T>::fill(reg);
         CPC_TRACE("registry filled");
+        if (real) {
+            n2 = n[0] / 2;
+            if (n[0] % 2 == 0 && reg.find(FastKey<T>(n2, VAR_XMAP, MODE_R2C)) != reg.end()) {
+                nxp = (n2 + 1 + 7) / 8 * 8;
+                wx = nxp;
+                CPC_CUDA(cudaMalloc(&work, sizeof(C) * (size_t)nxp * n[1] * n[2]));
+                CPC_CUDA(cudaMemset(work, 0, sizeof(C) * (size_t)nxp * n[1] * n[2]));
+            } else {
+                real_promote = true;         // odd or unsupported nx: run the complex path on a promoted copy
+                CPC_CUDA(cudaMalloc(&work, sizeof(C) * (size_t)nloc));
+            }
+        }
 
         int dev_smem = 0;
         CPC_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
@@ -311,15 +359,20 @@ template <typename T> struct PlanT : PlanBase {
             int var = (a == 0) ? (nc == 4 ? VAR_NARROW : VAR_XMAP) : VAR_WIDE;
             // the fused pass does two transforms per tile: fewer, fatter threads (2 butterflies each, 2 CTAs/SM)
             // measured 1.18 ms vs 1.98 ms at 512^3 (profiles/r01_notes.md)
-            if (a == 2 && reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
+            if (a == 2 && n[a] == 512 && reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
+            // 256-point y lines: radix 8.8.4 with 8 points per thread and 4 small CTAs per SM (0.090 vs 0.108 ms at 256^3)
+            if (a == 1 && n[a] == 256 && reg.find(FastKey<T>(n[a], VAR_EXP5, MODE_FWD)) != reg.end()) var = VAR_EXP5;
             {
                 const char *names[3] = { "CPC_VARIANT_X", "CPC_VARIANT_Y", "CPC_VARIANT_Z" };
                 const char *ov = getenv(names[a]);
                 if (ov && *ov) var = atoi(ov);      // tuning hook (tools/), not part of the ABI
             }
-            if (reg.find(FastKey<T>(n[a], var, MODE_FWD)) == reg.end() && var != VAR_XMAP) var = VAR_NARROW;
-            auto it = reg.find(FastKey<T>(n[a], var, MODE_FWD));
+            const int nfast = (real && !real_promote && a == 0) ? n2 : n[a];     // r2c: nx real points = nx/2 complex
+            if (real && !real_promote && a == 0) var = VAR_XMAP;
+            if (reg.find(FastKey<T>(nfast, var, MODE_FWD)) == reg.end() && var != VAR_XMAP) var = VAR_NARROW;
+            auto it = reg.find(FastKey<T>(nfast, var, MODE_FWD));
             if (it != reg.end() && a == 2 && reg.find(FastKey<T>(n[a], var, MODE_FUSED_SEP)) == reg.end()) it = reg.end();
+            c.nfast = nfast;
             if (it != reg.end() && it->second.smem <= (size_t)dev_smem) {
                 c.fast = true;
                 c.variant = var;
@@ -405,14 +458,23 @@ template <typename T> struct PlanT : PlanBase {
     PassGeom make_geom(int axis, int tx, int zb, int zc, int layout, long long *ptr_off) const
     {
         PassGeom g{};
-        const long long W = (long long)n[0] * nc;
+        const long long W = wx;
         const int rows = (layout == 1) ? nyl : n[1];
-        g.ncomp = nc; g.nx = n[0]; g.ny = rows; g.y0 = (layout == 1) ? y0 : 0;
+        g.ncomp = nc; g.nx = (int)(wx / nc); g.ny = rows; g.y0 = (layout == 1) ? y0 : 0;
         *ptr_off = 0;
         if (axis == 0) {
             const long long lines = (long long)rows * zc;
             *ptr_off = (long long)zb * rows * W;
-            if (nc == 1) {
+            if (real && !real_promote) {
+                // r2c / c2r: the real line of nx points is read (written) as nx/2 complex points; the half spectrum
+                // row has pitch nxp.  Which side is which is fixed up in run_real_x().
+                g.SI = 1; g.SL = n2;
+                g.tiles_inner = (int)((lines + tx - 1) / tx);
+                g.B0 = (long long)tx * n2; g.B1 = 0;
+                g.lines_inner = (int)lines;
+                g.ntiles = g.tiles_inner;
+                *ptr_off = 0;
+            } else if (nc == 1) {
                 g.SI = 1; g.SL = n[0];
                 g.tiles_inner = (int)((lines + tx - 1) / tx);
                 g.B0 = (long long)tx * n[0]; g.B1 = 0;
@@ -439,7 +501,7 @@ template <typename T> struct PlanT : PlanBase {
             g.lines_inner = (int)inner;
             g.ntiles = g.tiles_inner;
         }
-        g.SIo = g.SI; g.B0o = g.B0; g.B1o = g.B1;
+        g.SIo = g.SI; g.B0o = g.B0; g.B1o = g.B1; g.SLo = g.SL;
         g.SCi = g.SCo = 0; g.Di = g.Do = 0; g.shi = g.sho = -1;
         g.pf_tiles = 0;
         g.npeer = 0;
@@ -459,7 +521,7 @@ template <typename T> struct PlanT : PlanBase {
             g.SIo = W; g.B0o = g.B0; g.B1o = (long long)nyl * W;
             g.Do = nyl; g.sho = sh; g.SCo = (long long)nzl * nyl * W;
         } else {
-            g.B1o = g.B1; g.B0o = g.B0; g.SIo = g.SI;
+            g.B1o = g.B1; g.B0o = g.B0; g.SIo = g.SI; g.SLo = g.SL;
             g.B1 = (long long)nyl * W;
             g.Di = nyl; g.shi = sh; g.SCi = (long long)nzl * nyl * W;
         }
@@ -507,7 +569,7 @@ template <typename T> struct PlanT : PlanBase {
         if (g.ntiles <= 0) return CPC_OK;
         const SymbolArgs<T> s = symbol_args();
         if (c.fast) {
-            const FastEntry<T> &e = reg.at(FastKey<T>(n[axis], c.variant, mode));
+            const FastEntry<T> &e = reg.at(FastKey<T>(c.nfast, c.variant, mode));
             const int grid = (g.ntiles + e.g - 1) / e.g;
             g.pf_tiles = pf_waves > 0 ? pf_waves * num_sms * e.g : 0;
             e.kern<<<grid, e.threads, e.smem, st>>>(in + off, out + off, g, stw[axis], s);
@@ -515,6 +577,35 @@ template <typename T> struct PlanT : PlanBase {
             generic_pass_kernel<T><<<g.ntiles, c.threads, c.smem_generic, st>>>(in + off, out + off, g, tw[axis], s,
                                                                                c.fl, c.tx, mode);
         }
+        ++launches;
+        CPC_CUDA(cudaGetLastError());
+        return CPC_OK;
+    }
+
+    // Real plans: r2c (forward, real array -> half spectrum) or c2r (backward) x pass over z planes [zb, zb+zc).
+    int run_real_x(bool forward, const void *in, void *out, int zb, int zc, cudaStream_t st)
+    {
+        const AxisCfg &c = cfg[0];
+        long long off = 0;
+        PassGeom g = make_geom(0, c.tx, zb, zc, 0, &off);
+        const long long line0 = (long long)zb * n[1];
+        const C *pin;
+        C *pout;
+        if (forward) {       // in: real [lines][nx] viewed as complex pitch n2; out: half spectrum pitch nxp
+            g.SLo = nxp; g.B0o = (long long)c.tx * nxp;
+            pin = (const C *)in + line0 * n2;
+            pout = (C *)out + line0 * nxp;
+        } else {
+            g.SL = nxp; g.B0 = (long long)c.tx * nxp;
+            g.SLo = n2; g.B0o = (long long)c.tx * n2;
+            pin = (const C *)in + line0 * nxp;
+            pout = (C *)out + line0 * n2;
+        }
+        if (g.ntiles <= 0) return CPC_OK;
+        const SymbolArgs<T> s = symbol_args();
+        const FastEntry<T> &e = reg.at(FastKey<T>(c.nfast, c.variant, forward ? MODE_R2C : MODE_C2R));
+        const int grid = (g.ntiles + e.g - 1) / e.g;
+        e.kern<<<grid, e.threads, e.smem, st>>>(pin, pout, g, stw[0], s);
         ++launches;
         CPC_CUDA(cudaGetLastError());
         return CPC_OK;
@@ -534,11 +625,13 @@ template <typename T> struct PlanT : PlanBase {
     int upload_tables(const std::vector<double2> (&h)[3])
     {
         for (int a = 0; a < 3; ++a) {
-            std::vector<C> ht(n[a]);
+            // real plans index the x table with the padded half-spectrum column (< nxp <= nx for nx >= 16)
+            const size_t len = (a == 0 && real && !real_promote && (size_t)nxp > (size_t)n[a]) ? (size_t)nxp : (size_t)n[a];
+            std::vector<C> ht(len, mk<T>((T)1, (T)0));
             for (int m = 0; m < n[a]; ++m) ht[m] = mk<T>((T)h[a][m].x, (T)h[a][m].y);
-            if (!sym_tab[a]) CPC_CUDA(cudaMalloc(&sym_tab[a], sizeof(C) * n[a]));
+            if (!sym_tab[a]) CPC_CUDA(cudaMalloc(&sym_tab[a], sizeof(C) * len));
             if (!sym_tab64[a]) CPC_CUDA(cudaMalloc(&sym_tab64[a], sizeof(double2) * n[a]));
-            CPC_CUDA(cudaMemcpyAsync(sym_tab[a], ht.data(), sizeof(C) * n[a], cudaMemcpyHostToDevice, stream));
+            CPC_CUDA(cudaMemcpyAsync(sym_tab[a], ht.data(), sizeof(C) * len, cudaMemcpyHostToDevice, stream));
             CPC_CUDA(cudaMemcpyAsync(sym_tab64[a], h[a].data(), sizeof(double2) * n[a], cudaMemcpyHostToDevice, stream));
             CPC_CUDA(cudaStreamSynchronize(stream));
         }
@@ -592,6 +685,7 @@ template <typename T> struct PlanT : PlanBase {
     int set_symbol_diag(const void *diag, int mem_kind) override
     {
         if (desc.nranks != 1) { set_error("cpc_set_symbol_diag: single-rank plans only"); return CPC_ERR_UNSUPPORTED; }
+        if (real) { set_error("cpc_set_symbol_diag: complex plans only (real plans take the transport / separable symbol)"); return CPC_ERR_UNSUPPORTED; }
         if (!diag) { set_error("null diag"); return CPC_ERR_ARG; }
         int rc = ensure_inv_table();
         if (rc) return rc;
@@ -616,6 +710,7 @@ template <typename T> struct PlanT : PlanBase {
     int set_symbol_first_column(const void *col, int mem_kind) override
     {
         if (nc != 1) { set_error("first-column symbol needs ncomp == 1"); return CPC_ERR_ARG; }
+        if (real) { set_error("cpc_set_symbol_first_column: complex plans only"); return CPC_ERR_UNSUPPORTED; }
         if (!col) { set_error("null column"); return CPC_ERR_ARG; }
         int rc = ensure_inv_table();
         if (rc) return rc;
@@ -643,6 +738,7 @@ template <typename T> struct PlanT : PlanBase {
     int get_diag(void *diag, int mem_kind) override
     {
         if (desc.nranks != 1) { set_error("cpc_get_diag: single-rank plans only"); return CPC_ERR_UNSUPPORTED; }
+        if (real) { set_error("cpc_get_diag: complex plans only"); return CPC_ERR_UNSUPPORTED; }
         if (symbol_kind != CPC_SYMBOL_SEPARABLE && symbol_kind != CPC_SYMBOL_TABLE) {
             set_error("cpc_get_diag: no scalar symbol set");
             return CPC_ERR_STATE;
@@ -841,11 +937,74 @@ template <typename T> struct PlanT : PlanBase {
         return CPC_OK;
     }
 
+    // Real plan, device pointers: r2c x | Fy | fused z | By | c2r x, the middle three on the half spectrum.
+    int apply_device_real(const T *b, T *x, float *pass_ms, int *npasses)
+    {
+        int np = 0, rc;
+        auto mark = [&](int i) -> int {
+            if (pass_ms) CPC_CUDA(cudaEventRecord(prof_ev[i], stream));
+            return CPC_OK;
+        };
+        if (pass_ms && (rc = ensure_prof_events())) return rc;
+        if ((rc = mark(0))) return rc;
+        const long long N = (long long)n[0] * n[1] * n[2];
+        if (real_promote) {
+            real_to_complex_kernel<T><<<1184, 256, 0, stream>>>(b, work, N);
+            ++launches;
+            if ((rc = apply_device_single(work, work, nullptr, nullptr))) return rc;
+            complex_to_real_kernel<T><<<1184, 256, 0, stream>>>(work, x, N);
+            ++launches;
+            CPC_CUDA(cudaGetLastError());
+            if ((rc = mark(++np))) return rc;
+        } else {
+            if ((rc = run_real_x(true, b, work, 0, n[2], stream))) return rc;
+            if ((rc = mark(++np))) return rc;
+            if (n[1] > 1) {
+                if ((rc = run_pass(1, MODE_FWD, work, work, 0, n[2], 0, stream))) return rc;
+                if ((rc = mark(++np))) return rc;
+            }
+            if ((rc = run_pass(2, fused_mode(), work, work, 0, n[2], 0, stream))) return rc;
+            if ((rc = mark(++np))) return rc;
+            if (n[1] > 1) {
+                if ((rc = run_pass(1, MODE_INV, work, work, 0, n[2], 0, stream))) return rc;
+                if ((rc = mark(++np))) return rc;
+            }
+            if ((rc = run_real_x(false, work, x, 0, n[2], stream))) return rc;
+            if ((rc = mark(++np))) return rc;
+        }
+        if (pass_ms) {
+            CPC_CUDA(cudaEventSynchronize(prof_ev[np]));
+            for (int i = 0; i < np; ++i) CPC_CUDA(cudaEventElapsedTime(&pass_ms[i], prof_ev[i], prof_ev[i + 1]));
+            if (npasses) *npasses = np;
+        }
+        return CPC_OK;
+    }
+
+    int apply_real(const void *b, void *x, int mem_kind, float *pass_ms, int *npasses)
+    {
+        const size_t bytes = sizeof(T) * (size_t)n[0] * n[1] * n[2];
+        if (mem_kind == CPC_MEM_DEVICE) return apply_device_real((const T *)b, (T *)x, pass_ms, npasses);
+        int rc = ensure_dbuf();        // nloc complex >= N reals
+        if (rc) return rc;
+        CPC_CUDA(cudaMemcpyAsync(dbuf, b, bytes, cudaMemcpyHostToDevice, stream));
+        h2d_bytes += bytes;
+        if ((rc = apply_device_real((const T *)dbuf, (T *)dbuf, nullptr, nullptr))) return rc;
+        CPC_CUDA(cudaMemcpyAsync(x, dbuf, bytes, cudaMemcpyDeviceToHost, stream));
+        d2h_bytes += bytes;
+        CPC_CUDA(cudaStreamSynchronize(stream));
+        return CPC_OK;
+    }
+
     int apply(const void *b, void *x, int mem_kind, float *pass_ms, int *npasses) override
     {
         if (fused_mode() < 0) { set_error("cpc_apply: no symbol set (call cpc_set_symbol_* first)"); return CPC_ERR_STATE; }
         if (!b || !x) { set_error("cpc_apply: null pointer"); return CPC_ERR_ARG; }
         CPC_CUDA(cudaSetDevice(device));
+        if (real) {
+            if (mem_kind != CPC_MEM_DEVICE && mem_kind != CPC_MEM_HOST) { set_error("bad mem_kind %d", mem_kind); return CPC_ERR_ARG; }
+            if (pass_ms && mem_kind != CPC_MEM_DEVICE) { set_error("profiled apply needs device pointers"); return CPC_ERR_ARG; }
+            return apply_real(b, x, mem_kind, pass_ms, npasses);
+        }
         if (mem_kind == CPC_MEM_DEVICE) {
             if (desc.nranks == 1) return apply_device_single((const C *)b, (C *)x, pass_ms, npasses);
             return apply_device_dist((const C *)b, (C *)x, pass_ms, npasses);
@@ -904,6 +1063,7 @@ template <typename T> struct PlanT : PlanBase {
 
     int transform(const void *in, void *out, int mem_kind, int dir) override
     {
+        if (real) { set_error("cpc_forward / cpc_inverse: complex plans only (real plans expose cpc_apply)"); return CPC_ERR_UNSUPPORTED; }
         if (!in || !out) { set_error("null pointer"); return CPC_ERR_ARG; }
         if (mem_kind != CPC_MEM_DEVICE && mem_kind != CPC_MEM_HOST) { set_error("bad mem_kind"); return CPC_ERR_ARG; }
         return transform_impl((const C *)in, (C *)out, mem_kind, dir, false);
@@ -920,7 +1080,7 @@ template <typename T> struct PlanT : PlanBase {
         info->dist_mode = desc.nranks == 1 ? 0 : (p2p ? 2 : 1);
         for (int a = 0; a < 3; ++a) info->fast_path[a] = cfg[a].fast ? 1 : 0;
         info->local_elems = nloc;
-        info->bytes_per_apply_alg = 5ll * 2 * nloc * (long long)sizeof(C);
+        info->bytes_per_apply_alg = 5ll * 2 * nloc * (long long)(real ? sizeof(T) : sizeof(C));
         info->kernel_launches = launches;
         info->h2d_bytes = h2d_bytes;
         info->d2h_bytes = d2h_bytes;

@@ -51,7 +51,7 @@ class CirculantPlan:
         self._h = ctypes.c_void_p()
         self.nx, self.ny, self.nz, self.ncomp = int(nx), int(ny), int(nz), int(ncomp)
         self.dtype = dtype
-        self.np_dtype = np.complex128 if dtype == "c128" else np.complex64
+        self.np_dtype = {"c128": np.complex128, "c64": np.complex64, "f64": np.float64, "f32": np.float32}[dtype]
         self._id_buf = ctypes.create_string_buffer(nccl_id, len(nccl_id)) if nccl_id else None
         if stream is None and torch is not None and torch.cuda.is_available():
             stream = torch.cuda.current_stream().cuda_stream

@@ -44,7 +44,11 @@ enum cpc_status {
 
 enum cpc_dtype {
     CPC_C128 = 0,             /* PetscScalar of a complex PETSc build: complex128 in, complex128 out */
-    CPC_C64 = 1               /* fp32 option: complex64 in/out */
+    CPC_C64 = 1,              /* fp32 option: complex64 in/out */
+    CPC_F64 = 2,              /* PetscScalar of a real PETSc build: float64 in, float64 out; r2c / c2r inside, half
+                                 the bytes per pass (the reference's unfinished real branch, FftLinearSolver_3D.c:7-78,
+                                 176,186).  ncomp == 1, single rank, transport / separable symbol. */
+    CPC_F32 = 3               /* float32 in/out */
 };
 
 enum cpc_mem {

@@ -263,3 +263,50 @@ def test_roundtrip_and_linearity_at_baseline_sizes(n):
         # linearity: apply(2 b + i b) == (2 + i) apply(b)
         y = p.apply((2.0 + 1.0j) * b)
         assert (torch.linalg.vector_norm(y - (2.0 + 1.0j) * x) / torch.linalg.vector_norm(x)).item() < TOL64
+
+
+# ----------------------------------------------------------------------------------------------------
+# real-scalar plans (CPC_F64 / CPC_F32): r2c / c2r inside, half the bytes
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(64, 32, 16), (512, 8, 16), (128, 64, 32), (256, 16, 1), (1024, 4, 2), (64, 1, 1),
+                                   (20, 12, 9), (30, 1, 17), (16, 16, 16)])
+def test_real_scalar_plan_matches_oracle(shape):
+    nx, ny, nz = shape
+    rng = np.random.default_rng(nx + ny + nz)
+    lam = (55.5556, 0.3, 2.5)
+    x_ref = rng.standard_normal(nx * ny * nz)
+    b = O.apply_transport_matrix(x_ref, nx, ny, nz, *lam)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b.astype(np.complex128))
+    assert np.abs(want.imag).max() < 1e-9
+    with cpc.CirculantPlan(nx, ny, nz, dtype="f64") as p:
+        p.set_symbol_transport(*lam)
+        d = torch.from_numpy(b).cuda()
+        out = torch.empty_like(d)
+        p.apply(d, out)
+        assert rel_l2(host(out), want.real) < TOL64
+        assert np.array_equal(host(d), b)
+        p.apply(d, d)                                  # in place
+        assert rel_l2(host(d), want.real) < TOL64
+        xh = np.empty_like(b)
+        p.apply(b, xh)                                 # host pointers
+        assert rel_l2(xh, want.real) < TOL64
+        assert p.info()["bytes_per_apply_alg"] == 80 * b.size
+        with pytest.raises(cpc.CpcError):
+            p.forward(d)
+    with cpc.CirculantPlan(nx, ny, nz, dtype="f32") as p:
+        p.set_symbol_transport(*lam)
+        out = p.apply(torch.from_numpy(b.astype(np.float32)).cuda())
+        assert rel_l2(host(out), want.real) < TOL32
+
+
+def test_real_scalar_plan_512cube_roundtrip():
+    n = 512
+    lam = (55.5556, 55.5556, 55.5556)
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    xr = torch.randn(n, n, n, dtype=torch.float64, device="cuda", generator=gen)
+    b = _transport_matrix_torch(xr, lam).reshape(-1)
+    with cpc.CirculantPlan(n, n, n, dtype="f64") as p:
+        p.set_symbol_transport(*lam)
+        x = p.apply(b)
+    err = (torch.linalg.vector_norm(x - xr.reshape(-1)) / torch.linalg.vector_norm(xr)).item()
+    assert err < TOL64, err
