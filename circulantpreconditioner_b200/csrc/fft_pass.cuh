@@ -297,8 +297,15 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
 
     C v[E];
     if (active) {
+        if (g.Di == 0) {      // plain strided line (every pass except the multi-rank backward y pass)
+            const C *p = in + gbase + (long long)j * g.SI;
+            const long long step = (long long)TPL * g.SI;
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = in[gbase + point_off(j + TPL * m, g.SI, g.Di, g.shi, g.SCi)];
+            for (int m = 0; m < E; ++m) v[m] = p[m * step];
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = in[gbase + point_off(j + TPL * m, g.SI, g.Di, g.shi, g.SCi)];
+        }
     } else {
 #pragma unroll
         for (int m = 0; m < E; ++m) v[m] = mk<T>((T)0, (T)0);
@@ -351,8 +358,15 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
     }
 
     if (active) {
+        if (g.Do == 0) {      // plain strided line
+            C *p = out + obase + (long long)j * g.SIo;
+            const long long step = (long long)TPL * g.SIo;
 #pragma unroll
-        for (int m = 0; m < E; ++m) *out_ptr<C>(out, g, obase, j + TPL * m) = v[m];
+            for (int m = 0; m < E; ++m) p[m * step] = v[m];
+        } else {              // chunked layout or peer push (multi-rank plans)
+#pragma unroll
+            for (int m = 0; m < E; ++m) *out_ptr<C>(out, g, obase, j + TPL * m) = v[m];
+        }
     }
 }
 

@@ -74,7 +74,7 @@ def test_transport_iteration_parity_gpu_vs_oracle(n, quirk):
     assert (its_g, reason_g) == (its_c, reason_c)
     # identical counts are the criterion; the residual histories agree to rounding amplified by the conditioning of
     # the Arnoldi recurrence (the sign-quirk system is far from the circulant model)
-    assert np.allclose(hist_g, hist_c, rtol=1e-2)
+    assert np.allclose(hist_g, hist_c, rtol=5e-2, atol=1e-7 * hist_c[0])
     assert (torch.linalg.vector_norm(x_g.cpu() - x_c) / torch.linalg.vector_norm(x_c)).item() < 1e-8
 
 
@@ -93,7 +93,7 @@ def test_wave_iteration_parity_gpu_vs_oracle(n):
         plan.set_symbol_wave(C0, *MU)
         x_g, its_g, reason_g, hist_g = K.gmres(K.wave_operator(shape, C0, MU), b.cuda(), lambda v: plan.apply(v.contiguous()))
     assert (its_g, reason_g) == (its_c, reason_c)
-    assert np.allclose(hist_g, hist_c, rtol=1e-2)
+    assert np.allclose(hist_g, hist_c, rtol=5e-2, atol=1e-7 * hist_c[0])
 
 
 @pytest.mark.gpu
