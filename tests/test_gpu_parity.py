@@ -98,7 +98,9 @@ def test_config0_32cube_fast_path(tag):
 # ----------------------------------------------------------------------------------------------------
 SHAPES = [(16, 16, 16), (32, 64, 16), (64, 16, 128), (128, 32, 16), (256, 16, 32), (16, 256, 16), (512, 16, 8),
           (16, 8, 512), (1024, 4, 4), (8, 1024, 2), (2048, 2, 2), (2, 4, 2048), (48, 20, 36), (7, 11, 13),
-          (64, 64, 1), (128, 1, 1), (1, 1, 64), (1, 1, 1), (30, 1, 17)]
+          (64, 64, 1), (128, 1, 1), (1, 1, 64), (1, 1, 1), (30, 1, 17),
+          # fast kernels with partial tiles (lines not a multiple of the tile width) and mixed fast / generic axes
+          (64, 3, 5), (128, 5, 3), (512, 3, 1), (12, 64, 5), (3, 5, 256), (256, 7, 32)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -154,7 +156,8 @@ def test_general_first_column_and_diag_table():
         assert rel_l2(host(p.apply(dev(b))), want) < TOL64
 
 
-@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 16, 64), (64, 32, 16), (6, 5, 4), (16, 16, 1), (128, 16, 32)])
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 16, 64), (64, 32, 16), (6, 5, 4), (16, 16, 1), (128, 16, 32),
+                                   (32, 3, 16), (5, 16, 64), (256, 2, 3)])
 def test_wave_block_matches_oracle(shape):
     nx, ny, nz = shape
     rng = np.random.default_rng(17)
