@@ -50,6 +50,8 @@ ABI = {
     "cpc_apply": (_i, [_vp, _vp, _vp, _i]),
     "cpc_forward": (_i, [_vp, _vp, _vp, _i]),
     "cpc_inverse": (_i, [_vp, _vp, _vp, _i]),
+    "cpc_set_projection": (_i, [_vp, ctypes.c_int64, _i64p, ctypes.POINTER(ctypes.c_int32), _dp]),
+    "cpc_apply_projected": (_i, [_vp, _vp, _vp, _i]),
     "cpc_apply_profiled": (_i, [_vp, _vp, _vp, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i)]),
     "cpc_get_info": (_i, [_vp, ctypes.POINTER(PlanInfo)]),
     "cpc_last_error": (ctypes.c_char_p, []),

@@ -190,6 +190,23 @@ int cpc_inverse(cpc_plan plan, const void *in, void *out, int mem_kind)
     return plan->impl->transform(in, out, mem_kind, +1);
 }
 
+int cpc_set_projection(cpc_plan plan, int64_t cols, const int64_t *rowptr, const int32_t *colidx, const double *val)
+{
+    CHECK_PLAN(plan);
+    if (cols < 1 || !rowptr || !colidx || !val) { set_error("cpc_set_projection: bad argument"); return CPC_ERR_ARG; }
+    CPC_CUDA(cudaSetDevice(plan->impl->device));
+    return plan->impl->set_projection(cols, rowptr, colidx, val);
+}
+
+int cpc_apply_projected(cpc_plan plan, const void *b, void *x, int mem_kind)
+{
+    CHECK_PLAN(plan);
+    if (!b || !x) { set_error("cpc_apply_projected: null pointer"); return CPC_ERR_ARG; }
+    if (mem_kind != CPC_MEM_DEVICE && mem_kind != CPC_MEM_HOST) { set_error("bad mem_kind %d", mem_kind); return CPC_ERR_ARG; }
+    CPC_CUDA(cudaSetDevice(plan->impl->device));
+    return plan->impl->apply_projected(b, x, mem_kind);
+}
+
 int cpc_get_info(cpc_plan plan, cpc_plan_info *info)
 {
     CHECK_PLAN(plan);

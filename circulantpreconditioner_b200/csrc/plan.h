@@ -44,6 +44,8 @@ struct PlanBase {
     virtual int apply(const void *b, void *x, int mem_kind, float *pass_ms, int *npasses) = 0;
     virtual int transform(const void *in, void *out, int mem_kind, int dir) = 0;
     virtual int get_info(cpc_plan_info *info) = 0;
+    virtual int set_projection(int64_t cols, const int64_t *rowptr, const int32_t *colidx, const double *val) = 0;
+    virtual int apply_projected(const void *b, void *x, int mem_kind) = 0;
 };
 
 PlanBase *make_plan_f64();

@@ -199,6 +199,22 @@ __global__ void complex_to_real_kernel(const cplx_t<T> *__restrict__ in, T *__re
         out[i] = in[i].x;
 }
 
+// y[i] = sum_p val[p] * x[col[p]] over CSR row i (rows of the projection have a handful of entries: one thread per row)
+template <typename T>
+__global__ void csr_spmv_kernel(long long rows, const long long *__restrict__ rowptr, const int *__restrict__ colidx,
+                                const double *__restrict__ val, const cplx_t<T> *__restrict__ x, cplx_t<T> *__restrict__ y)
+{
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+        double sr = 0.0, si = 0.0;
+        for (long long p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+            const cplx_t<T> v = x[colidx[p]];
+            sr += val[p] * (double)v.x;
+            si += val[p] * (double)v.y;
+        }
+        y[i] = mk<T>((T)sr, (T)si);
+    }
+}
+
 // exp(-2 pi i m / n) rounded from long double
 static inline void exact_root(long long m, long long n, double *re, double *im)
 {
@@ -253,6 +269,13 @@ template <typename T> struct PlanT : PlanBase {
     C *inv_table = nullptr;
     double wave_c0 = 0, wave_mu[3] = { 0, 0, 0 };
 
+    // projection (unstructured mesh <-> Cartesian grid): P and P^T in CSR
+    long long proj_cols = 0;
+    long long *p_rowptr = nullptr, *pt_rowptr = nullptr;
+    int *p_colidx = nullptr, *pt_colidx = nullptr;
+    double *p_val = nullptr, *pt_val = nullptr;
+    C *pbuf = nullptr, *pio = nullptr;
+
     // host staging
     C *dbuf = nullptr;
     cudaStream_t copy_stream = nullptr;
@@ -277,6 +300,7 @@ template <typename T> struct PlanT : PlanBase {
         }
         if (inv_table) cudaFree(inv_table);
         if (work) cudaFree(work);
+        free_projection();
         if (dbuf) cudaFree(dbuf);
         if (p2p) {
             dist_barrier(dist, stream);
@@ -1067,6 +1091,87 @@ template <typename T> struct PlanT : PlanBase {
         if (!in || !out) { set_error("null pointer"); return CPC_ERR_ARG; }
         if (mem_kind != CPC_MEM_DEVICE && mem_kind != CPC_MEM_HOST) { set_error("bad mem_kind"); return CPC_ERR_ARG; }
         return transform_impl((const C *)in, (C *)out, mem_kind, dir, false);
+    }
+
+    void free_projection()
+    {
+        void *ptrs[] = { p_rowptr, pt_rowptr, p_colidx, pt_colidx, p_val, pt_val, pbuf, pio };
+        for (void *q : ptrs)
+            if (q) cudaFree(q);
+        p_rowptr = pt_rowptr = nullptr; p_colidx = pt_colidx = nullptr; p_val = pt_val = nullptr; pbuf = pio = nullptr;
+        proj_cols = 0;
+    }
+
+    int set_projection(int64_t cols, const int64_t *rowptr, const int32_t *colidx, const double *val) override
+    {
+        if (real || nc != 1 || desc.nranks != 1) { set_error("cpc_set_projection: complex scalar single-rank plans only"); return CPC_ERR_UNSUPPORTED; }
+        const long long rows = ntot;
+        const long long nnz = rowptr[rows];
+        if (rowptr[0] != 0 || nnz < 0) { set_error("cpc_set_projection: malformed rowptr"); return CPC_ERR_ARG; }
+        for (long long p = 0; p < nnz; ++p)
+            if (colidx[p] < 0 || colidx[p] >= cols) { set_error("cpc_set_projection: column index %d out of range", colidx[p]); return CPC_ERR_ARG; }
+        // transpose on the host (counting sort by column)
+        std::vector<long long> trp((size_t)cols + 1, 0);
+        for (long long p = 0; p < nnz; ++p) ++trp[(size_t)colidx[p] + 1];
+        for (long long c = 0; c < cols; ++c) trp[(size_t)c + 1] += trp[(size_t)c];
+        std::vector<int> tci((size_t)(nnz > 0 ? nnz : 1));
+        std::vector<double> tv((size_t)(nnz > 0 ? nnz : 1));
+        std::vector<long long> fill(trp.begin(), trp.end() - 1);
+        for (long long i = 0; i < rows; ++i)
+            for (long long p = rowptr[i]; p < rowptr[i + 1]; ++p) {
+                const long long q = fill[(size_t)colidx[p]]++;
+                tci[(size_t)q] = (int)i;
+                tv[(size_t)q] = val[p];
+            }
+        free_projection();
+        const size_t nz = (size_t)(nnz > 0 ? nnz : 1);
+        CPC_CUDA(cudaMalloc(&p_rowptr, sizeof(long long) * (size_t)(rows + 1)));
+        CPC_CUDA(cudaMalloc(&pt_rowptr, sizeof(long long) * (size_t)(cols + 1)));
+        CPC_CUDA(cudaMalloc(&p_colidx, sizeof(int) * nz));
+        CPC_CUDA(cudaMalloc(&pt_colidx, sizeof(int) * nz));
+        CPC_CUDA(cudaMalloc(&p_val, sizeof(double) * nz));
+        CPC_CUDA(cudaMalloc(&pt_val, sizeof(double) * nz));
+        CPC_CUDA(cudaMalloc(&pbuf, sizeof(C) * (size_t)rows));
+        CPC_CUDA(cudaMalloc(&pio, sizeof(C) * (size_t)cols));
+        CPC_CUDA(cudaMemcpy(p_rowptr, rowptr, sizeof(long long) * (size_t)(rows + 1), cudaMemcpyHostToDevice));
+        CPC_CUDA(cudaMemcpy(pt_rowptr, trp.data(), sizeof(long long) * (size_t)(cols + 1), cudaMemcpyHostToDevice));
+        CPC_CUDA(cudaMemcpy(p_colidx, colidx, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CPC_CUDA(cudaMemcpy(pt_colidx, tci.data(), sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CPC_CUDA(cudaMemcpy(p_val, val, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CPC_CUDA(cudaMemcpy(pt_val, tv.data(), sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice));
+        proj_cols = cols;
+        return CPC_OK;
+    }
+
+    // x = P^T solve_3D(P b): reference applyFFT3DPrecTransport (PCSHELLFft_3D.cxx:10-24) plus the back-projection
+    int apply_projected(const void *b, void *x, int mem_kind) override
+    {
+        if (!proj_cols) { set_error("cpc_apply_projected: no projection set"); return CPC_ERR_STATE; }
+        if (fused_mode() < 0) { set_error("cpc_apply_projected: no symbol set"); return CPC_ERR_STATE; }
+        const C *bin = (const C *)b;
+        C *xout = (C *)x;
+        if (mem_kind == CPC_MEM_HOST) {
+            CPC_CUDA(cudaMemcpyAsync(pio, b, sizeof(C) * (size_t)proj_cols, cudaMemcpyHostToDevice, stream));
+            h2d_bytes += sizeof(C) * (size_t)proj_cols;
+            bin = pio;
+            xout = pio;
+        }
+        const int grid_r = (int)((ntot + 255) / 256 < 148 * 16 ? (ntot + 255) / 256 : 148 * 16);
+        csr_spmv_kernel<T><<<grid_r > 0 ? grid_r : 1, 256, 0, stream>>>(ntot, p_rowptr, p_colidx, p_val, bin, pbuf);
+        ++launches;
+        CPC_CUDA(cudaGetLastError());
+        int rc = apply_device_single(pbuf, pbuf, nullptr, nullptr);
+        if (rc) return rc;
+        const int grid_c = (int)((proj_cols + 255) / 256 < 148 * 16 ? (proj_cols + 255) / 256 : 148 * 16);
+        csr_spmv_kernel<T><<<grid_c > 0 ? grid_c : 1, 256, 0, stream>>>(proj_cols, pt_rowptr, pt_colidx, pt_val, pbuf, xout);
+        ++launches;
+        CPC_CUDA(cudaGetLastError());
+        if (mem_kind == CPC_MEM_HOST) {
+            CPC_CUDA(cudaMemcpyAsync(x, pio, sizeof(C) * (size_t)proj_cols, cudaMemcpyDeviceToHost, stream));
+            d2h_bytes += sizeof(C) * (size_t)proj_cols;
+            CPC_CUDA(cudaStreamSynchronize(stream));
+        }
+        return CPC_OK;
     }
 
     int get_info(cpc_plan_info *info) override

@@ -52,6 +52,7 @@ struct _p_Mat {
     cpc_plan plan;
     const void *diag_seen;      /* Diag array + state last uploaded through solve_3D */
     unsigned long diag_state;
+    const void *proj_seen;      /* projection Mat last handed to cpc_set_projection */
     /* SHIM_MAT_CSR: projection matrix (intersectionMatrix) */
     PetscInt rows, cols;
     PetscInt *rowptr, *colidx;

@@ -137,6 +137,23 @@ class CirculantPlan:
             out = torch.empty_like(v) if (torch is not None and isinstance(v, torch.Tensor)) else np.empty_like(v)
         return self._call(lib().cpc_inverse, v, out)
 
+    def set_projection(self, cols, rowptr, colidx, val):
+        """CSR projection P (N Cartesian rows x `cols` mesh cells, real weights): ctx->intersectionMatrix."""
+        rp = np.ascontiguousarray(rowptr, dtype=np.int64)
+        ci = np.ascontiguousarray(colidx, dtype=np.int32)
+        v = np.ascontiguousarray(val, dtype=np.float64)
+        if rp.size != self.nx * self.ny * self.nz + 1 or ci.size != v.size or ci.size < rp[-1]:
+            raise ValueError("malformed CSR arrays")
+        check(lib().cpc_set_projection(self._h, int(cols), rp.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                       ci.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                       v.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+
+    def apply_projected(self, b, x=None):
+        """x = P^T solve_3D(P b)  (reference applyFFT3DPrecTransport, PCSHELLFft_3D.cxx:10-24, plus back-projection)."""
+        if x is None:
+            x = torch.empty_like(b) if (torch is not None and isinstance(b, torch.Tensor)) else np.empty_like(b)
+        return self._call(lib().cpc_apply_projected, b, x)
+
     def apply_profiled(self, b, x):
         """Device-pointer apply that also returns the per-pass durations in ms (CUDA events on the plan stream)."""
         pb, kb, _ = _ptr_and_kind(b)

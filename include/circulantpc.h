@@ -119,6 +119,17 @@ int cpc_get_diag(cpc_plan plan, void *diag_c128, int mem_kind);
 int cpc_apply(cpc_plan plan, const void *b, void *x, int mem_kind);
 int cpc_forward(cpc_plan plan, const void *in, void *out, int mem_kind);
 int cpc_inverse(cpc_plan plan, const void *in, void *out, int mem_kind);
+/* ---- unstructured meshes: projection onto the Cartesian grid ------------------------------------------
+ * cpc_set_projection  <- ctx->intersectionMatrix (reference src/PCSHELLFft_3D.hxx:17; never built there, ToDo.md
+ *                        last item): CSR matrix P with N = nx*ny*nz rows (Cartesian cells) and `cols` columns
+ *                        (cells of the unstructured mesh), real weights; host arrays, copied to HBM with its transpose.
+ * cpc_apply_projected <- applyFFT3DPrecTransport (src/PCSHELLFft_3D.cxx:10-24): x = P^T solve_3D( P b ); b and x
+ *                        have `cols` entries.  (The reference stops after solve_3D and leaves x on the Cartesian
+ *                        grid; the transpose brings it back to the mesh the Krylov vectors live on.)
+ * Complex single-rank plans only. */
+int cpc_set_projection(cpc_plan plan, int64_t cols, const int64_t *rowptr, const int32_t *colidx, const double *val);
+int cpc_apply_projected(cpc_plan plan, const void *b, void *x, int mem_kind);
+
 /* Same as cpc_apply on device pointers, but records CUDA events around each of the passes on the plan's
  * stream and returns their durations (ms).  pass_ms must hold CPC_MAX_PASSES floats; *npasses gets the count. */
 #define CPC_MAX_PASSES 16

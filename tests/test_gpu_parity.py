@@ -313,3 +313,26 @@ def test_real_scalar_plan_512cube_roundtrip():
         x = p.apply(b)
     err = (torch.linalg.vector_norm(x - xr.reshape(-1)) / torch.linalg.vector_norm(xr)).item()
     assert err < TOL64, err
+
+
+def test_projected_apply_unstructured_to_cartesian():
+    # applyFFT3DPrecTransport with an intersection matrix (reference PCSHELLFft_3D.cxx:17-21): x = P^T solve_3D(P b)
+    import scipy.sparse as sp
+    nx, ny, nz = 16, 8, 32
+    N, M = nx * ny * nz, 3000                      # Cartesian cells, cells of the "unstructured" mesh
+    rng = np.random.default_rng(41)
+    P = sp.random(N, M, density=4.0 / M, random_state=np.random.RandomState(3), format="csr", dtype=np.float64)
+    P.data[:] = rng.random(P.nnz)
+    lam = (2.0, 0.5, 1.5)
+    b = rand_c(rng, M)
+    want = P.T @ O.FftTransportSolver(nx, ny, nz, *lam, P @ b)
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        p.set_symbol_transport(*lam)
+        with pytest.raises(cpc.CpcError):
+            p.apply_projected(dev(b))              # no projection yet
+        p.set_projection(M, P.indptr, P.indices, P.data)
+        got = host(p.apply_projected(dev(b)))
+        assert rel_l2(got, want) < TOL64
+        xh = np.empty_like(b)
+        p.apply_projected(b, xh)                   # host pointers
+        assert rel_l2(xh, want) < TOL64
