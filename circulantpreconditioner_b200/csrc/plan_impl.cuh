@@ -45,34 +45,47 @@ enum Variant {
     VAR_COUNT = 8
 };
 
-template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, variant, mode)
+template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, variant, mode + 16 * general-addressing)
 
-template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF = MINB>
-static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
+constexpr int GEN_BIT = 16;   // key offset of the kernels compiled with chunked-layout / peer-push addressing
+
+template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF, bool GEN>
+static void register_modes_gen(std::map<FastKey<T>, FastEntry<T>> &m)
 {
     constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
     constexpr bool XM = (VAR == VAR_XMAP);
     constexpr int threads = (N / E) * TX * G;
     constexpr size_t smem = NST > 1 ? (size_t)G * SmemTile<N, TX, Log2<R0>::v, XM>::elems * sizeof(cplx_t<T>) : 0;
+    constexpr int KB = GEN ? GEN_BIT : 0;
     FastEntry<T> e{ nullptr, threads, smem, G, TX, { R0, R1, R2 } };
-    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FWD, MINB, XM>;
-    m[FastKey<T>(N, VAR, MODE_FWD)] = e;
-    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_INV, MINB, XM>;
-    m[FastKey<T>(N, VAR, MODE_INV)] = e;
-    if constexpr (XM && NST > 1) {
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_R2C, MINB, XM>;
+    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FWD, MINB, XM, GEN>;
+    m[FastKey<T>(N, VAR, MODE_FWD + KB)] = e;
+    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_INV, MINB, XM, GEN>;
+    m[FastKey<T>(N, VAR, MODE_INV + KB)] = e;
+    if constexpr (XM && NST > 1 && !GEN) {
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_R2C, MINB, XM, false>;
         m[FastKey<T>(N, VAR, MODE_R2C)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_C2R, MINB, XM>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_C2R, MINB, XM, false>;
         m[FastKey<T>(N, VAR, MODE_C2R)] = e;
     }
     if constexpr (!XM) {
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_SEP, MINBF, XM>;
-        m[FastKey<T>(N, VAR, MODE_FUSED_SEP)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_TABLE, MINBF, XM>;
-        m[FastKey<T>(N, VAR, MODE_FUSED_TABLE)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_WAVE, MINBF, XM>;
-        m[FastKey<T>(N, VAR, MODE_FUSED_WAVE)] = e;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_SEP, MINBF, XM, GEN>;
+        m[FastKey<T>(N, VAR, MODE_FUSED_SEP + KB)] = e;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_TABLE, MINBF, XM, GEN>;
+        m[FastKey<T>(N, VAR, MODE_FUSED_TABLE + KB)] = e;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_WAVE, MINBF, XM, GEN>;
+        m[FastKey<T>(N, VAR, MODE_FUSED_WAVE + KB)] = e;
     }
+}
+
+// Every variant is compiled with plain strided addressing; the variants used for the y and z passes of power-of-two
+// grids (VAR_WIDE and the tuned 512 / 256 ones) also get the general-addressing build needed by multi-rank plans.
+template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF = MINB>
+static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
+{
+    register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, false>(m);
+    if constexpr (VAR == VAR_WIDE || VAR == VAR_WIDE2 || VAR == VAR_EXP5)
+        register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, true>(m);
 }
 
 template <typename T> struct FastRegistry;
@@ -396,6 +409,13 @@ template <typename T> struct PlanT : PlanBase {
             if (reg.find(FastKey<T>(nfast, var, MODE_FWD)) == reg.end() && var != VAR_XMAP) var = VAR_NARROW;
             auto it = reg.find(FastKey<T>(nfast, var, MODE_FWD));
             if (it != reg.end() && a == 2 && reg.find(FastKey<T>(n[a], var, MODE_FUSED_SEP)) == reg.end()) it = reg.end();
+            // multi-rank plans push / chunk their y and z stores: only variants with a general-addressing build
+            if (it != reg.end() && desc.nranks > 1 && a >= 1 &&
+                reg.find(FastKey<T>(nfast, var, MODE_FWD + GEN_BIT)) == reg.end()) {
+                var = VAR_WIDE;
+                it = reg.find(FastKey<T>(nfast, var, MODE_FWD + GEN_BIT)) != reg.end() ? reg.find(FastKey<T>(nfast, var, MODE_FWD))
+                                                                                  : reg.end();
+            }
             c.nfast = nfast;
             if (it != reg.end() && it->second.smem <= (size_t)dev_smem) {
                 c.fast = true;
@@ -593,7 +613,8 @@ template <typename T> struct PlanT : PlanBase {
         if (g.ntiles <= 0) return CPC_OK;
         const SymbolArgs<T> s = symbol_args();
         if (c.fast) {
-            const FastEntry<T> &e = reg.at(FastKey<T>(c.nfast, c.variant, mode));
+            // multi-rank y / z passes need the general-addressing build (init() made sure it exists)
+            const FastEntry<T> &e = reg.at(FastKey<T>(c.nfast, c.variant, mode + (split != 0 ? GEN_BIT : 0)));
             const int grid = (g.ntiles + e.g - 1) / e.g;
             g.pf_tiles = pf_waves > 0 ? pf_waves * num_sms * e.g : 0;
             e.kern<<<grid, e.threads, e.smem, st>>>(in + off, out + off, g, stw[axis], s);
