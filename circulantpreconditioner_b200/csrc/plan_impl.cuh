@@ -40,9 +40,9 @@ enum Variant {
     VAR_WIDE = 0,     // strided lines, TX lanes = one 128-byte row (y, z passes)
     VAR_NARROW = 1,   // strided lines, TX = 4 (wave x pass: the 4 components of a cell; long lines)
     VAR_XMAP = 2,     // contiguous lines (scalar x pass)
-    VAR_WIDE2 = 3,    // as VAR_WIDE with twice the points per thread (fewer, fatter threads)
-    VAR_EXP4 = 4, VAR_EXP5 = 5, VAR_EXP6 = 6, VAR_EXP7 = 7,   // tuning experiments (tools/sweep)
-    VAR_COUNT = 8
+    VAR_WIDE2 = 3,    // as VAR_WIDE with a different points-per-thread / radix split (512: two butterflies per thread)
+    VAR_SMALL = 4,    // as VAR_WIDE with small CTAs, 4 per SM (256-point y lines)
+    VAR_COUNT = 5
 };
 
 template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, variant, mode + 16 * general-addressing)
@@ -84,7 +84,7 @@ template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int
 static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
 {
     register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, false>(m);
-    if constexpr (VAR == VAR_WIDE || VAR == VAR_WIDE2 || VAR == VAR_EXP5)
+    if constexpr (VAR == VAR_WIDE || VAR == VAR_WIDE2 || VAR == VAR_SMALL)
         register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, true>(m);
 }
 
@@ -106,8 +106,7 @@ template <> struct FastRegistry<double> {
         register_modes<double, VAR_WIDE2,   512,  8,  8,  8, 16,  8,  1, 2>(m);
         register_modes<double, VAR_WIDE2,   256,  8,  8,  4,  8,  8,  2, 2>(m);      // 512 thr, 64 regs
         register_modes<double, VAR_WIDE2,   128,  8,  4,  4,  8,  8,  4, 2>(m);      // 512 thr, 64 regs
-        register_modes<double, VAR_EXP5,    256,  8,  8,  4,  8,  8,  1, 4>(m);      // 256 thr, 64 regs, 4 CTAs/SM
-        register_modes<double, VAR_EXP4,   1024, 16,  8,  8, 16,  4,  1, 2>(m);      // 256 thr, 64 KB: 2 CTAs/SM
+        register_modes<double, VAR_SMALL,    256,  8,  8,  4,  8,  8,  1, 4>(m);      // 256 thr, 64 regs, 4 CTAs/SM
         register_modes<double, VAR_NARROW,   16, 16,  1,  1, 16,  4, 32, 2>(m);
         register_modes<double, VAR_NARROW,   32,  8,  4,  1,  8,  4, 16, 2>(m);
         register_modes<double, VAR_NARROW,   64,  8,  8,  1,  8,  4,  8, 2>(m);
@@ -398,7 +397,7 @@ template <typename T> struct PlanT : PlanBase {
             // measured 1.18 ms vs 1.98 ms at 512^3 (profiles/r01_notes.md)
             if (a == 2 && n[a] == 512 && reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
             // 256-point y lines: radix 8.8.4 with 8 points per thread and 4 small CTAs per SM (0.090 vs 0.108 ms at 256^3)
-            if (a == 1 && n[a] == 256 && reg.find(FastKey<T>(n[a], VAR_EXP5, MODE_FWD)) != reg.end()) var = VAR_EXP5;
+            if (a == 1 && n[a] == 256 && reg.find(FastKey<T>(n[a], VAR_SMALL, MODE_FWD)) != reg.end()) var = VAR_SMALL;
             {
                 const char *names[3] = { "CPC_VARIANT_X", "CPC_VARIANT_Y", "CPC_VARIANT_Z" };
                 const char *ov = getenv(names[a]);

@@ -1,4 +1,7 @@
-"""Tuning aid: time each pass of cpc_apply for several kernel variants (CPC_VARIANT_X/Y/Z env hooks)."""
+"""Tuning aid: time each pass of cpc_apply for several kernel variants (CPC_VARIANT_X/Y/Z env hooks).
+
+Variant ids (csrc/plan_impl.cuh enum Variant): 0 wide, 1 narrow, 2 xmap (scalar x pass), 3 wide2, 4 small.
+Usage: python tools/sweep_variants.py N  vx,vy,vz[,prefetch_waves] ...   (env NCOMP=4 for the wave block)"""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
