@@ -85,22 +85,70 @@ template <int DIR, typename C> struct Butterfly<8, DIR, C> {
         C o[4] = { u[1], u[3], u[5], u[7] };
         Butterfly<4, DIR, C>::run(e);
         Butterfly<4, DIR, C>::run(o);
-        // W8^1 = (1 + DIR*i)/sqrt2, W8^2 = DIR*i, W8^3 = (-1 + DIR*i)/sqrt2
-        C w1, w3;
+        // X[k] = E[k] + W8^k O[k], X[k+4] = E[k] - W8^k O[k];  W8^1 = (1 + DIR i)/sqrt2, W8^2 = DIR i,
+        // W8^3 = (-1 + DIR i)/sqrt2.  The 1/sqrt2 factor is folded into the final add as an FMA:
+        // (a +- b) h + e  ->  fma(a +- b, h, e): 2 adds + 4 FMAs per pair instead of 2 adds + 2 muls + 4 adds.
+        T p1, q1, p3, q3;     // W8^1 O[1] = (p1, q1) h,  W8^3 O[3] = (p3, q3) h
         if (DIR < 0) {
-            w1.x = (o[1].x + o[1].y) * h;  w1.y = (o[1].y - o[1].x) * h;
-            w3.x = (o[3].y - o[3].x) * h;  w3.y = -(o[3].x + o[3].y) * h;
+            p1 = o[1].x + o[1].y;  q1 = o[1].y - o[1].x;
+            p3 = o[3].y - o[3].x;  q3 = -(o[3].x + o[3].y);
         } else {
-            w1.x = (o[1].x - o[1].y) * h;  w1.y = (o[1].x + o[1].y) * h;
-            w3.x = -(o[3].x + o[3].y) * h; w3.y = (o[3].x - o[3].y) * h;
+            p1 = o[1].x - o[1].y;  q1 = o[1].x + o[1].y;
+            p3 = -(o[3].x + o[3].y); q3 = o[3].x - o[3].y;
         }
-        C w2 = mul_dir_i<DIR>(o[2]);
+        const C w2 = mul_dir_i<DIR>(o[2]);
         u[0] = cadd(e[0], o[0]); u[4] = csub(e[0], o[0]);
-        u[1] = cadd(e[1], w1);   u[5] = csub(e[1], w1);
+        u[1].x = fma(p1, h, e[1].x);  u[1].y = fma(q1, h, e[1].y);
+        u[5].x = fma(-p1, h, e[1].x); u[5].y = fma(-q1, h, e[1].y);
         u[2] = cadd(e[2], w2);   u[6] = csub(e[2], w2);
-        u[3] = cadd(e[3], w3);   u[7] = csub(e[3], w3);
+        u[3].x = fma(p3, h, e[3].x);  u[3].y = fma(q3, h, e[3].y);
+        u[7].x = fma(-p3, h, e[3].x); u[7].y = fma(-q3, h, e[3].y);
     }
 };
+
+// plus = a + w' b, minus = a - w' b with w' = w (forward) or conj(w) (backward): 6 FMAs instead of a complex
+// multiply (4) plus an add and a subtract (4).  minus = 2a - plus.
+template <int DIR, typename C> __device__ __forceinline__ void cfma_pm(C a, C w, C b, C &plus, C &minus)
+{
+    using T = decltype(a.x);
+    const T wy = DIR < 0 ? w.y : -w.y;
+    plus.x = fma(w.x, b.x, fma(-wy, b.y, a.x));
+    plus.y = fma(w.x, b.y, fma(wy, b.x, a.y));
+    minus.x = fma((T)2, a.x, -plus.x);
+    minus.y = fma((T)2, a.y, -plus.y);
+}
+
+// Radix-8 butterfly of the twiddled inputs u[r] * w[r-1] (r = 1..7): the twiddles are folded into the first add /
+// subtract level (36 instead of 44 fp64 instructions for that level).
+template <int DIR, typename C> __device__ __forceinline__ void butterfly8_twiddled(C *u, const C *w)
+{
+    using T = decltype(u[0].x);
+    const T h = (T)0.70710678118654752440084436210484903928;
+    C t0, t1, t2, t3, s0, s1, s2, s3;
+    cfma_pm<DIR>(u[0], w[3], u[4], t0, t1);                          // u0 +- w4 u4
+    cfma_pm<DIR>(twmul<DIR>(u[2], w[1]), w[5], u[6], t2, t3);        // w2 u2 +- w6 u6
+    cfma_pm<DIR>(twmul<DIR>(u[1], w[0]), w[4], u[5], s0, s1);        // w1 u1 +- w5 u5
+    cfma_pm<DIR>(twmul<DIR>(u[3], w[2]), w[6], u[7], s2, s3);        // w3 u3 +- w7 u7
+    t3 = mul_dir_i<DIR>(t3);
+    s3 = mul_dir_i<DIR>(s3);
+    const C e0 = cadd(t0, t2), e2 = csub(t0, t2), e1 = cadd(t1, t3), e3 = csub(t1, t3);
+    const C o0 = cadd(s0, s2), o2 = csub(s0, s2), o1 = cadd(s1, s3), o3 = csub(s1, s3);
+    T p1, q1, p3, q3;
+    if (DIR < 0) {
+        p1 = o1.x + o1.y;  q1 = o1.y - o1.x;
+        p3 = o3.y - o3.x;  q3 = -(o3.x + o3.y);
+    } else {
+        p1 = o1.x - o1.y;  q1 = o1.x + o1.y;
+        p3 = -(o3.x + o3.y); q3 = o3.x - o3.y;
+    }
+    const C w2 = mul_dir_i<DIR>(o2);
+    u[0] = cadd(e0, o0); u[4] = csub(e0, o0);
+    u[1].x = fma(p1, h, e1.x);  u[1].y = fma(q1, h, e1.y);
+    u[5].x = fma(-p1, h, e1.x); u[5].y = fma(-q1, h, e1.y);
+    u[2] = cadd(e2, w2);     u[6] = csub(e2, w2);
+    u[3].x = fma(p3, h, e3.x);  u[3].y = fma(q3, h, e3.y);
+    u[7].x = fma(-p3, h, e3.x); u[7].y = fma(-q3, h, e3.y);
+}
 
 template <int DIR, typename C> struct Butterfly<16, DIR, C> {
     __device__ __forceinline__ static void run(C *u)

@@ -133,11 +133,18 @@ __device__ __forceinline__ void stockham_stage(cplx_t<T> (&v)[E], int j, int l, 
 #pragma unroll
         for (int r = 0; r < R; ++r) u[r] = v[b + r * NB];
         const int k = (P > 1) ? (jb & (P - 1)) : 0;
-        if (P > 1) {
+        if constexpr (P > 1 && R == 8) {
+            C w[7];
 #pragma unroll
-            for (int r = 1; r < R; ++r) u[r] = twmul<DIR>(u[r], __ldg(&tw[(r - 1) * P + k]));
+            for (int r = 1; r < 8; ++r) w[r - 1] = __ldg(&tw[(r - 1) * P + k]);
+            butterfly8_twiddled<DIR>(u, w);
+        } else {
+            if (P > 1) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) u[r] = twmul<DIR>(u[r], __ldg(&tw[(r - 1) * P + k]));
+            }
+            Butterfly<R, DIR, C>::run(u);
         }
-        Butterfly<R, DIR, C>::run(u);
         if (TO_SMEM) {
             const int j0 = (jb - k) * R + k;
 #pragma unroll
@@ -157,11 +164,20 @@ __device__ __forceinline__ void smem_gather(cplx_t<T> (&v)[E], int j, int l, con
     for (int m = 0; m < E; ++m) v[m] = sm[sm_index<N, TX, PADSH, XMAP>(j + TPL * m, l)];
 }
 
+// Barrier over the threads that share lines.  With NG > 1 a tile's TX lines are split into NG independent
+// sub-groups (lines never exchange data with each other), each with its own named barrier, so the sub-groups of a
+// CTA drift apart and one group's butterfly (fp64) phase overlaps another group's shared-memory (LSU) phase.
+template <int NTHREADS> __device__ __forceinline__ void group_sync(int bar_id)
+{
+    if (NTHREADS == 0) __syncthreads();      // whole CTA (too many groups for the 16 named barriers, or partial warps)
+    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(NTHREADS) : "memory");
+}
+
 // Full 1-D transform of the thread's line: registers -> registers (through shared memory).
 // Stage tables are concatenated: stage 1 at tw, stage 2 at tw + (R1-1)*R0.
-template <typename T, int N, int R0, int R1, int R2, int E, int DIR, int TX, bool XMAP>
+template <typename T, int N, int R0, int R1, int R2, int E, int DIR, int TX, bool XMAP, int NT>
 __device__ __forceinline__ void line_fft(cplx_t<T> (&v)[E], int j, int l, cplx_t<T> *sm,
-                                         const cplx_t<T> *__restrict__ tw)
+                                         const cplx_t<T> *__restrict__ tw, int bar)
 {
     constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
     constexpr int PS = Log2<R0>::v;
@@ -170,16 +186,16 @@ __device__ __forceinline__ void line_fft(cplx_t<T> (&v)[E], int j, int l, cplx_t
         stockham_stage<T, N, E, R0, 1, DIR, false, TX, PS, XMAP>(v, j, l, sm, tw);
     } else if (NST == 2) {
         stockham_stage<T, N, E, R0, 1, DIR, true, TX, PS, XMAP>(v, j, l, sm, tw);
-        __syncthreads();
+        group_sync<NT>(bar);
         smem_gather<T, N, E, TX, PS, XMAP>(v, j, l, sm);
         stockham_stage<T, N, E, R1, R0, DIR, false, TX, PS, XMAP>(v, j, l, sm, tw);
     } else {
         stockham_stage<T, N, E, R0, 1, DIR, true, TX, PS, XMAP>(v, j, l, sm, tw);
-        __syncthreads();
+        group_sync<NT>(bar);
         smem_gather<T, N, E, TX, PS, XMAP>(v, j, l, sm);
-        __syncthreads();
+        group_sync<NT>(bar);
         stockham_stage<T, N, E, R1, R0, DIR, true, TX, PS, XMAP>(v, j, l, sm, tw);
-        __syncthreads();
+        group_sync<NT>(bar);
         smem_gather<T, N, E, TX, PS, XMAP>(v, j, l, sm);
         stockham_stage<T, N, E, R2, R0 * R1, DIR, false, TX, PS, XMAP>(v, j, l, sm, tw2);
     }
@@ -188,24 +204,24 @@ __device__ __forceinline__ void line_fft(cplx_t<T> (&v)[E], int j, int l, cplx_t
 // ---------------------------------------------------------------------------------------------------------------
 // Eigenvalue division, applied on the registers between the forward and the backward z transform.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int N, int E, int MODE>
-__device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int j, int w, long long gbase_l, long long SI,
+// Point m of the thread sits at frequency index k0 + kstep * m of the line.
+template <typename T, int E, int MODE>
+__device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int k0, int kstep, int w, long long gbase_l, long long SI,
                                              const PassGeom &g, const SymbolArgs<T> &s)
 {
     using C = cplx_t<T>;
-    constexpr int TPL = N / E;
     if (MODE == MODE_FUSED_SEP) {
         // Lambda[k,j,i] = 1 + lx cx[i] + ly cy[j] + lz cz[k]   (reference FftLinearSolver_3D.c:146-157)
         const int x = w % g.nx, y = w / g.nx + g.y0;
         const C a = cadd(s.ax[x], s.ay[y]);
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-            const C lam = cadd(a, s.az[j + TPL * m]);
+            const C lam = cadd(a, s.az[k0 + kstep * m]);
             v[m] = cmul(v[m], crecip_scaled<T>(lam, s.scale));   // b_hat / Diag (:174) and 1/size (:184)
         }
     } else if (MODE == MODE_FUSED_TABLE) {
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = cmul(v[m], s.inv_table[gbase_l + (long long)(j + TPL * m) * SI]);
+        for (int m = 0; m < E; ++m) v[m] = cmul(v[m], s.inv_table[gbase_l + (long long)(k0 + kstep * m) * SI]);
     } else if (MODE == MODE_FUSED_WAVE) {
         // 4 consecutive lanes hold (p, rho0 u, rho0 v, rho0 w) of one cell.  Arrow-matrix Schur solve
         // (blocks from reference src/WaveSystem.cxx:92-107):
@@ -220,7 +236,7 @@ __device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int j, int w, lo
         const T sxx = sx * sx * iDx, syy = sy * sy * iDy;
 #pragma unroll
         for (int m = 0; m < E; ++m) {
-            const C rz = s.rz[j + TPL * m];
+            const C rz = s.rz[k0 + kstep * m];
             const T sz = -rz.y * s.muz, oz = ((T)1 - rz.x) * s.muz;
             const T Dz = (T)1 + c0 * oz, iDz = fast_rcp(Dz);
             const T m00 = (T)1 + c0 * (ox + oy + oz);
@@ -252,7 +268,8 @@ __device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int j, int w, lo
 // ---------------------------------------------------------------------------------------------------------------
 // GEN = false compiles the chunked-layout / peer-push addressing out (single-rank plans): ~15 % less code, which
 // matters for the fused kernel whose straight-line SASS otherwise exceeds the 32 KB instruction cache.
-template <typename T, int N, int R0, int R1, int R2, int E, int TX, int G, int MODE, int MINB, bool XMAP, bool GEN = true>
+template <typename T, int N, int R0, int R1, int R2, int E, int TX, int G, int MODE, int MINB, bool XMAP, bool GEN = true,
+          int NG = 1>
 __global__ void __launch_bounds__((N / E) * TX * G, MINB)
 fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
                 const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
@@ -264,11 +281,22 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
     static_assert(E % R0 == 0 && E % R1 == 0 && E % R2 == 0, "each radix must divide the register tile");
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
+    // thread -> (tile of the CTA, sub-group of the tile, line, butterfly column)
+    constexpr int TXG = TX / NG;                  // lines per sub-group
+    constexpr int NTG = TXG * TPL;                // threads per sub-group
+    // participants of the sub-group's named barrier; 0 = fall back to __syncthreads()
+    constexpr int NT = (G * NG <= 15 && NTG % 32 == 0 && G * NG > 1) ? NTG : 0;
+    static_assert(TX % NG == 0 && (NG == 1 || (!XMAP && NTG % 32 == 0)), "sub-groups must be whole warps");
     const int tid = threadIdx.x;
-    const int l = XMAP ? (tid / TPL) % TX : tid % TX;
-    const int j = XMAP ? tid % TPL : (tid / TX) % TPL;
     const int grp = tid / (TX * TPL);
-    C *sm = reinterpret_cast<C *>(smem_raw) + (size_t)grp * (NST > 1 ? SmemTile<N, TX, Log2<R0>::v, XMAP>::elems : 0);
+    const int sg = (tid / NTG) % NG;
+    const int ts = tid % NTG;
+    const int lg = XMAP ? (ts / TPL) % TXG : ts % TXG;      // line within the sub-group (shared-memory lane)
+    const int l = sg * TXG + lg;                            // line within the tile
+    const int j = XMAP ? ts % TPL : (ts / TXG) % TPL;
+    const int bar = 1 + grp * NG + sg;                      // named barrier of this sub-group (0 is __syncthreads)
+    C *sm = reinterpret_cast<C *>(smem_raw) +
+            (size_t)(grp * NG + sg) * (NST > 1 ? SmemTile<N, TXG, Log2<R0>::v, XMAP>::elems : 0);
 
     const int t = blockIdx.x * G + grp;
     const bool tile_ok = t < g.ntiles;
@@ -314,24 +342,24 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
     }
 
     if (MODE == MODE_FWD) {
-        line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
+        line_fft<T, N, R0, R1, R2, E, -1, TXG, XMAP, NT>(v, j, lg, sm, tw, bar);
     } else if (MODE == MODE_INV) {
-        line_fft<T, N, R0, R1, R2, E, +1, TX, XMAP>(v, j, l, sm, tw);
+        line_fft<T, N, R0, R1, R2, E, +1, TXG, XMAP, NT>(v, j, lg, sm, tw, bar);
     } else if (MODE == MODE_R2C) {
         // Untangle (reference a2/a4 rows of SURVEY.md 8a: the real-scalar build's r2c transform):
         //   X[k] = E[k] + w^k O[k],  E[k] = (Z[k] + conj Z[N-k]) / 2,  O[k] = -i (Z[k] - conj Z[N-k]) / 2,  w = exp(-i pi / N)
-        line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
+        line_fft<T, N, R0, R1, R2, E, -1, TXG, XMAP, NT>(v, j, lg, sm, tw, bar);
         constexpr int PS = Log2<R0>::v;
-        __syncthreads();
+        group_sync<NT>(bar);
 #pragma unroll
-        for (int m = 0; m < E; ++m) sm[sm_index<N, TX, PS, XMAP>(j + TPL * m, l)] = v[m];
-        __syncthreads();
+        for (int m = 0; m < E; ++m) sm[sm_index<N, TXG, PS, XMAP>(j + TPL * m, lg)] = v[m];
+        group_sync<NT>(bar);
         C nyq = mk<T>((T)0, (T)0);
 #pragma unroll
         for (int m = 0; m < E; ++m) {
             const int k = j + TPL * m;
             const C a = v[m];
-            const C bq = sm[sm_index<N, TX, PS, XMAP>((N - k) & (N - 1), l)];
+            const C bq = sm[sm_index<N, TXG, PS, XMAP>((N - k) & (N - 1), lg)];
             const C ev = mk<T>((T)0.5 * (a.x + bq.x), (T)0.5 * (a.y - bq.y));
             const C od = mk<T>((T)0.5 * (a.y + bq.y), (T)-0.5 * (a.x - bq.x));       // -i (a - conj b) / 2
             const C wk = sym.rx[k];                                                   // exp(-2 pi i k / (2N))
@@ -351,12 +379,12 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
             const C t1 = cmulc(d1, sym.rx[k]);                                        // conj(w^k) (a - conj b)
             v[m] = mk<T>(s1.x - t1.y, s1.y + t1.x);                                   // s1 + i t1
         }
-        line_fft<T, N, R0, R1, R2, E, +1, TX, XMAP>(v, j, l, sm, tw);
+        line_fft<T, N, R0, R1, R2, E, +1, TXG, XMAP, NT>(v, j, lg, sm, tw, bar);
     } else {
-        line_fft<T, N, R0, R1, R2, E, -1, TX, XMAP>(v, j, l, sm, tw);
-        apply_symbol<T, N, E, MODE>(v, j, active ? w : 0, gbase, g.SI, g, sym);
-        if (NST > 1) __syncthreads();
-        line_fft<T, N, R0, R1, R2, E, +1, TX, XMAP>(v, j, l, sm, tw);
+        line_fft<T, N, R0, R1, R2, E, -1, TXG, XMAP, NT>(v, j, lg, sm, tw, bar);
+        apply_symbol<T, E, MODE>(v, j, TPL, active ? w : 0, gbase, g.SI, g, sym);
+        if (NST > 1) group_sync<NT>(bar);
+        line_fft<T, N, R0, R1, R2, E, +1, TXG, XMAP, NT>(v, j, lg, sm, tw, bar);
     }
 
     if (active) {

@@ -1,0 +1,145 @@
+// fft_r2x.cuh -- 2H-point strided-line pass as  2 x (16 x 16)  with H = 256:  one radix-2 level in registers, a warp
+// shuffle, and a two-stage radix-16 Stockham transform per half -- ONE shared-memory exchange per transform instead
+// of the two that the 8.8.8 kernel needs.  The fused z pass is limited by LSU wavefronts and barrier-serialised
+// phases, not by HBM (profiles/r01_notes.md); this variant cuts its shared-memory traffic by half.
+//
+// Decimation in frequency for the first level (forward):
+//     a[k] = x[k] + x[k+H],   b[k] = (x[k] - x[k+H]) W_{2H}^k,   X[2q] = FFT_H(a)[q],   X[2q+1] = FFT_H(b)[q]
+// and its mirror (decimation in time) for the backward transform:
+//     x[n] = yA[n] + W_{2H}^{-n} yB[n],   x[n+H] = yA[n] - W_{2H}^{-n} yB[n],   yA = IFFT_H(X[2q]),  yB = IFFT_H(X[2q+1]).
+// A line is handled by 32 threads: thread (s, j), s = which half-transform it runs after the exchange, j in [0,16).
+// Thread (s, j) loads the pairs (k, k+H) for k = j + 16 m, m in [8s, 8s+8): both members of a pair sit in one thread,
+// so the radix-2 level needs no exchange; the partner (1-s, j) is 8 lanes away in the same warp, and the two swap
+// half of their points with shfl.xor.  After that each thread holds the 16 points {j + 16 m} of its half-line: the
+// standard input of the 16 x 16 Stockham kernel code.
+#pragma once
+#include "fft_pass.cuh"
+
+namespace cpc {
+
+template <typename C> __device__ __forceinline__ C shfl_xor_c(C v, int mask)
+{
+    C r;
+    r.x = __shfl_xor_sync(0xffffffffu, v.x, mask);
+    r.y = __shfl_xor_sync(0xffffffffu, v.y, mask);
+    return r;
+}
+
+// H-point (16 x 16) transform of the 16 points {j + 16 m} of half-line s; shared memory [point][s][lane l].
+template <typename T, int DIR>
+__device__ __forceinline__ void half_fft_16x16(cplx_t<T> (&u)[16], int j, int s, int l, cplx_t<T> *sm,
+                                               const cplx_t<T> *__restrict__ tw)
+{
+    using C = cplx_t<T>;
+    Butterfly<16, DIR, C>::run(u);                                   // stage 0: p = 1, no twiddles
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[((j * 16 + r) * 2 + s) * 8 + l] = u[r];
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) u[m] = sm[((j + 16 * m) * 2 + s) * 8 + l];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) u[r] = twmul<DIR>(u[r], __ldg(&tw[(r - 1) * 16 + j]));   // stage 1: p = 16, k = j
+    Butterfly<16, DIR, C>::run(u);                                   // u[m] = point j + 16 m, natural order
+}
+
+template <typename T, int MODE, bool GEN>
+__global__ void __launch_bounds__(256, 2)
+fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
+                  const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
+{
+    using C = cplx_t<T>;
+    constexpr int H = 256, TX = 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, wrp = tid >> 5;
+    const int l = lane & 7;
+    const int qd = lane >> 3;
+    const int s = qd & 1;
+    const int j = (qd >> 1) + 2 * wrp;
+
+    const int t = blockIdx.x;
+    const int ti = t % g.tiles_inner, to = t / g.tiles_inner;
+    const int w = ti * TX + l;
+    const bool active = w < g.lines_inner;
+    const long long gbase = (long long)to * g.B1 + (long long)ti * g.B0 + (long long)l * g.SL;
+    const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)l * g.SLo;
+    const C *rt = sym.rz;                 // roots exp(-2 pi i k / 512) of the transformed axis
+
+    C u[16];
+    constexpr bool FORWARD_FIRST = (MODE != MODE_INV);
+    if (FORWARD_FIRST) {
+        // ---- load pairs, radix-2 level (decimation in frequency) -------------------------------------------------
+        C a[8], b[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int k = j + 16 * (8 * s + i);
+            C x0 = mk<T>((T)0, (T)0), x1 = x0;
+            if (active) {
+                x0 = in[gbase + ((!GEN || g.Di == 0) ? (long long)k * g.SI : point_off(k, g.SI, g.Di, g.shi, g.SCi))];
+                x1 = in[gbase + ((!GEN || g.Di == 0) ? (long long)(k + H) * g.SI : point_off(k + H, g.SI, g.Di, g.shi, g.SCi))];
+            }
+            a[i] = cadd(x0, x1);
+            b[i] = cmul(csub(x0, x1), __ldg(&rt[k]));
+        }
+        // ---- swap halves with the partner thread (lane ^ 8) ---------------------------------------------------------
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const C send = s ? a[i] : b[i];
+            const C recv = shfl_xor_c(send, 8);
+            u[i] = s ? recv : a[i];
+            u[i + 8] = s ? b[i] : recv;
+        }
+        half_fft_16x16<T, -1>(u, j, s, l, sm, tw);                   // u[m] = X[2 (j + 16 m) + s]
+    } else {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int K = 2 * (j + 16 * m) + s;
+            u[m] = active ? in[gbase + ((!GEN || g.Di == 0) ? (long long)K * g.SI : point_off(K, g.SI, g.Di, g.shi, g.SCi))]
+                          : mk<T>((T)0, (T)0);
+        }
+    }
+
+    if (MODE == MODE_FWD) {
+        if (active) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int K = 2 * (j + 16 * m) + s;
+                if (!GEN || g.Do == 0) out[obase + (long long)K * g.SIo] = u[m];
+                else *out_ptr<C>(out, g, obase, K) = u[m];
+            }
+        }
+        return;
+    }
+
+    if (MODE != MODE_INV) {
+        apply_symbol<T, 16, MODE>(u, 2 * j + s, 32, active ? w : 0, gbase, g.SI, g, sym);
+        __syncthreads();                                             // shared memory is reused by the backward transform
+    }
+
+    half_fft_16x16<T, +1>(u, j, s, l, sm, tw);                       // u[m] = y_s[j + 16 m]
+
+    // ---- swap back and radix-2 level (decimation in time) ----------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const C send = s ? u[i] : u[i + 8];                          // s = 0 gives away yA[8+i], s = 1 gives away yB[i]
+        const C recv = shfl_xor_c(send, 8);
+        const C ya = s ? recv : u[i];
+        const C yb = s ? u[i + 8] : recv;
+        const int n = j + 16 * (8 * s + i);
+        const C tt = cmulc(yb, __ldg(&rt[n]));                       // conj(W^n) yB[n]
+        const C x0 = cadd(ya, tt), x1 = csub(ya, tt);
+        if (active) {
+            if (!GEN || g.Do == 0) {
+                out[obase + (long long)n * g.SIo] = x0;
+                out[obase + (long long)(n + H) * g.SIo] = x1;
+            } else {
+                *out_ptr<C>(out, g, obase, n) = x0;
+                *out_ptr<C>(out, g, obase, n + H) = x1;
+            }
+        }
+    }
+}
+
+}  // namespace cpc

@@ -18,6 +18,7 @@
 
 #include "dist.h"
 #include "fft_pass.cuh"
+#include "fft_r2x.cuh"
 #include "generic_pass.cuh"
 #include "plan.h"
 
@@ -42,50 +43,66 @@ enum Variant {
     VAR_XMAP = 2,     // contiguous lines (scalar x pass)
     VAR_WIDE2 = 3,    // as VAR_WIDE with a different points-per-thread / radix split (512: two butterflies per thread)
     VAR_SMALL = 4,    // as VAR_WIDE with small CTAs, 4 per SM (256-point y lines)
-    VAR_COUNT = 5
+    VAR_R2X = 5,      // 512 = 2 x (16 x 16): radix-2 level in registers + warp shuffle, one shared-memory exchange
+    VAR_COUNT = 6
 };
 
 template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, variant, mode + 16 * general-addressing)
 
 constexpr int GEN_BIT = 16;   // key offset of the kernels compiled with chunked-layout / peer-push addressing
 
-template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF, bool GEN>
+template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF, bool GEN, int NG>
 static void register_modes_gen(std::map<FastKey<T>, FastEntry<T>> &m)
 {
     constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
     constexpr bool XM = (VAR == VAR_XMAP);
     constexpr int threads = (N / E) * TX * G;
-    constexpr size_t smem = NST > 1 ? (size_t)G * SmemTile<N, TX, Log2<R0>::v, XM>::elems * sizeof(cplx_t<T>) : 0;
+    constexpr size_t smem = NST > 1 ? (size_t)G * NG * SmemTile<N, TX / NG, Log2<R0>::v, XM>::elems * sizeof(cplx_t<T>) : 0;
     constexpr int KB = GEN ? GEN_BIT : 0;
     FastEntry<T> e{ nullptr, threads, smem, G, TX, { R0, R1, R2 } };
-    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FWD, MINB, XM, GEN>;
+    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FWD, MINB, XM, GEN, NG>;
     m[FastKey<T>(N, VAR, MODE_FWD + KB)] = e;
-    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_INV, MINB, XM, GEN>;
+    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_INV, MINB, XM, GEN, NG>;
     m[FastKey<T>(N, VAR, MODE_INV + KB)] = e;
     if constexpr (XM && NST > 1 && !GEN) {
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_R2C, MINB, XM, false>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_R2C, MINB, XM, false, NG>;
         m[FastKey<T>(N, VAR, MODE_R2C)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_C2R, MINB, XM, false>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_C2R, MINB, XM, false, NG>;
         m[FastKey<T>(N, VAR, MODE_C2R)] = e;
     }
     if constexpr (!XM) {
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_SEP, MINBF, XM, GEN>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_SEP, MINBF, XM, GEN, NG>;
         m[FastKey<T>(N, VAR, MODE_FUSED_SEP + KB)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_TABLE, MINBF, XM, GEN>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_TABLE, MINBF, XM, GEN, NG>;
         m[FastKey<T>(N, VAR, MODE_FUSED_TABLE + KB)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_WAVE, MINBF, XM, GEN>;
+        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_WAVE, MINBF, XM, GEN, NG>;
         m[FastKey<T>(N, VAR, MODE_FUSED_WAVE + KB)] = e;
     }
 }
 
 // Every variant is compiled with plain strided addressing; the variants used for the y and z passes of power-of-two
 // grids (VAR_WIDE and the tuned 512 / 256 ones) also get the general-addressing build needed by multi-rank plans.
-template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF = MINB>
+template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF = MINB, int NG = 1>
 static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
 {
-    register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, false>(m);
+    register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, false, NG>(m);
     if constexpr (VAR == VAR_WIDE || VAR == VAR_WIDE2 || VAR == VAR_SMALL)
-        register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, true>(m);
+        register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, true, NG>(m);
+}
+
+// 512-point strided lines as 2 x (16 x 16) (fft_r2x.cuh)
+template <typename T> static void register_r2x512(std::map<FastKey<T>, FastEntry<T>> &m)
+{
+    FastEntry<T> e{ nullptr, 256, (size_t)256 * 16 * sizeof(cplx_t<T>), 1, 8, { 16, 16, 1 } };
+#define CPC_R2X(MODE)                                                                   \
+    e.kern = fft_r2x512_kernel<T, MODE, false>; m[FastKey<T>(512, VAR_R2X, MODE)] = e;           \
+    e.kern = fft_r2x512_kernel<T, MODE, true>;  m[FastKey<T>(512, VAR_R2X, MODE + GEN_BIT)] = e;
+    CPC_R2X(MODE_FWD)
+    CPC_R2X(MODE_INV)
+    CPC_R2X(MODE_FUSED_SEP)
+    CPC_R2X(MODE_FUSED_TABLE)
+    CPC_R2X(MODE_FUSED_WAVE)
+#undef CPC_R2X
 }
 
 template <typename T> struct FastRegistry;
@@ -104,6 +121,7 @@ template <> struct FastRegistry<double> {
         register_modes<double, VAR_WIDE,    512,  8,  8,  8,  8,  8,  1, 2, 1>(m);
         register_modes<double, VAR_WIDE,   1024, 16,  8,  8, 16,  8,  1, 1>(m);
         register_modes<double, VAR_WIDE2,   512,  8,  8,  8, 16,  8,  1, 2>(m);
+        register_r2x512<double>(m);
         register_modes<double, VAR_WIDE2,   256,  8,  8,  4,  8,  8,  2, 2>(m);      // 512 thr, 64 regs
         register_modes<double, VAR_WIDE2,   128,  8,  4,  4,  8,  8,  4, 2>(m);      // 512 thr, 64 regs
         register_modes<double, VAR_SMALL,    256,  8,  8,  4,  8,  8,  1, 4>(m);      // 256 thr, 64 regs, 4 CTAs/SM
@@ -393,9 +411,13 @@ template <typename T> struct PlanT : PlanBase {
             // a cell as lanes (narrow strided); y and z lines are strided with >= 128 contiguous bytes across lanes.
             AxisCfg &c = cfg[a];
             int var = (a == 0) ? (nc == 4 ? VAR_NARROW : VAR_XMAP) : VAR_WIDE;
-            // the fused pass does two transforms per tile: fewer, fatter threads (2 butterflies each, 2 CTAs/SM)
-            // measured 1.18 ms vs 1.98 ms at 512^3 (profiles/r01_notes.md)
-            if (a == 2 && n[a] == 512 && reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
+            // the fused pass does two transforms per tile and is LSU / issue bound: 512 = 2 x (16 x 16) with a register
+            // radix-2 level and one shared-memory exchange per transform (fft_r2x.cuh) measured 1.23 ms at 512^3, the
+            // 8.8.8 kernel with two butterflies per thread 1.31 ms, with one butterfly per thread 1.98 ms
+            if (a == 2 && n[a] == 512) {
+                if (sizeof(T) == 8 && reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FUSED_SEP)) != reg.end()) var = VAR_R2X;
+                else if (reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
+            }
             // 256-point y lines: radix 8.8.4 with 8 points per thread and 4 small CTAs per SM (0.090 vs 0.108 ms at 256^3)
             if (a == 1 && n[a] == 256 && reg.find(FastKey<T>(n[a], VAR_SMALL, MODE_FWD)) != reg.end()) var = VAR_SMALL;
             {

