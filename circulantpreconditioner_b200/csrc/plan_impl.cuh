@@ -267,6 +267,7 @@ template <typename T> struct PlanT : PlanBase {
     struct AxisCfg {
         bool fast = false;
         int variant = 0;          // enum Variant of the fast kernel
+        int variant_fwd = -1;     // >= 0: a different variant for the plain forward pass (same tile width)
         int nfast = 0;            // transform length of the fast kernel (nx/2 for the r2c / c2r pass)
         int tx = 1;               // lanes per tile
         int threads = 0;          // generic kernel block size
@@ -292,6 +293,7 @@ template <typename T> struct PlanT : PlanBase {
     AxisCfg cfg[3];
     C *tw[3] = { nullptr, nullptr, nullptr };    // roots exp(-2 pi i m / n)
     C *stw[3] = { nullptr, nullptr, nullptr };   // per-stage twiddle tables of the fast kernel chosen for the axis
+    C *stw_fwd[3] = { nullptr, nullptr, nullptr };   // same for the separate forward-only variant, if any
 
     // symbol state
     C *sym_tab[3] = { nullptr, nullptr, nullptr };       // ax, ay(+1), az in T
@@ -325,6 +327,7 @@ template <typename T> struct PlanT : PlanBase {
         for (int a = 0; a < 3; ++a) {
             if (tw[a]) cudaFree(tw[a]);
             if (stw[a]) cudaFree(stw[a]);
+            if (stw_fwd[a]) cudaFree(stw_fwd[a]);
             if (sym_tab[a]) cudaFree(sym_tab[a]);
             if (sym_tab64[a]) cudaFree(sym_tab64[a]);
         }
@@ -442,23 +445,16 @@ template <typename T> struct PlanT : PlanBase {
                 c.fast = true;
                 c.variant = var;
                 c.tx = it->second.tx;
-                // per-stage twiddle tables [r-1][k]: exp(-2 pi i r k / (P R)) for the 2nd and 3rd radix
-                const int *R = it->second.radix;
-                std::vector<C> st;
-                int P = R[0];
-                for (int sidx = 1; sidx < 3; ++sidx) {
-                    if (R[sidx] <= 1) break;
-                    for (int r = 1; r < R[sidx]; ++r)
-                        for (int k = 0; k < P; ++k) {
-                            double re, im;
-                            exact_root((long long)r * k, (long long)P * R[sidx], &re, &im);
-                            st.push_back(mk<T>((T)re, (T)im));
-                        }
-                    P *= R[sidx];
-                }
-                if (!st.empty()) {
-                    CPC_CUDA(cudaMalloc(&stw[a], sizeof(C) * st.size()));
-                    CPC_CUDA(cudaMemcpy(stw[a], st.data(), sizeof(C) * st.size(), cudaMemcpyHostToDevice));
+                int rc_t = build_stage_table(it->second.radix, &stw[a]);
+                if (rc_t) return rc_t;
+                // 512-point y lines, fp64: the 2 x (16 x 16) kernel is faster for the plain forward pass (0.64 vs
+                // 0.70 ms at 512^3) but slower for the backward one (0.81 ms), so it serves the forward pass only
+                if (a == 1 && nfast == 512 && sizeof(T) == 8 && !getenv("CPC_VARIANT_Y")) {
+                    auto itf = reg.find(FastKey<T>(nfast, VAR_R2X, MODE_FWD));
+                    if (itf != reg.end() && itf->second.tx == c.tx && itf->second.smem <= (size_t)dev_smem) {
+                        c.variant_fwd = VAR_R2X;
+                        if ((rc_t = build_stage_table(itf->second.radix, &stw_fwd[a]))) return rc_t;
+                    }
                 }
             } else {
                 c.fast = false;
@@ -513,6 +509,28 @@ template <typename T> struct PlanT : PlanBase {
                 p2p = (r1 == CPC_OK && r2 == CPC_OK);
                 if (!p2p && r1 != CPC_ERR_UNSUPPORTED && r2 != CPC_ERR_UNSUPPORTED) return r1 ? r1 : r2;
             }
+        }
+        return CPC_OK;
+    }
+
+    // per-stage twiddle tables [r-1][k]: exp(-2 pi i r k / (P R)) for the 2nd and 3rd radix of a kernel
+    int build_stage_table(const int *R, C **dst)
+    {
+        std::vector<C> st;
+        int P = R[0];
+        for (int sidx = 1; sidx < 3; ++sidx) {
+            if (R[sidx] <= 1) break;
+            for (int r = 1; r < R[sidx]; ++r)
+                for (int k = 0; k < P; ++k) {
+                    double re, im;
+                    exact_root((long long)r * k, (long long)P * R[sidx], &re, &im);
+                    st.push_back(mk<T>((T)re, (T)im));
+                }
+            P *= R[sidx];
+        }
+        if (!st.empty()) {
+            CPC_CUDA(cudaMalloc(dst, sizeof(C) * st.size()));
+            CPC_CUDA(cudaMemcpy(*dst, st.data(), sizeof(C) * st.size(), cudaMemcpyHostToDevice));
         }
         return CPC_OK;
     }
@@ -632,13 +650,15 @@ template <typename T> struct PlanT : PlanBase {
             }
         }
         if (g.ntiles <= 0) return CPC_OK;
-        const SymbolArgs<T> s = symbol_args();
+        SymbolArgs<T> s = symbol_args();
+        s.rz = tw[axis];          // roots of the transformed axis (fft_r2x.cuh); the fused pass is always axis 2
         if (c.fast) {
             // multi-rank y / z passes need the general-addressing build (init() made sure it exists)
-            const FastEntry<T> &e = reg.at(FastKey<T>(c.nfast, c.variant, mode + (split != 0 ? GEN_BIT : 0)));
+            const bool alt = (mode == MODE_FWD && c.variant_fwd >= 0);
+            const FastEntry<T> &e = reg.at(FastKey<T>(c.nfast, alt ? c.variant_fwd : c.variant, mode + (split != 0 ? GEN_BIT : 0)));
             const int grid = (g.ntiles + e.g - 1) / e.g;
             g.pf_tiles = pf_waves > 0 ? pf_waves * num_sms * e.g : 0;
-            e.kern<<<grid, e.threads, e.smem, st>>>(in + off, out + off, g, stw[axis], s);
+            e.kern<<<grid, e.threads, e.smem, st>>>(in + off, out + off, g, alt ? stw_fwd[axis] : stw[axis], s);
         } else {
             generic_pass_kernel<T><<<g.ntiles, c.threads, c.smem_generic, st>>>(in + off, out + off, g, tw[axis], s,
                                                                                c.fl, c.tx, mode);

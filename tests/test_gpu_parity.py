@@ -100,7 +100,9 @@ SHAPES = [(16, 16, 16), (32, 64, 16), (64, 16, 128), (128, 32, 16), (256, 16, 32
           (16, 8, 512), (1024, 4, 4), (8, 1024, 2), (2048, 2, 2), (2, 4, 2048), (48, 20, 36), (7, 11, 13),
           (64, 64, 1), (128, 1, 1), (1, 1, 64), (1, 1, 1), (30, 1, 17),
           # fast kernels with partial tiles (lines not a multiple of the tile width) and mixed fast / generic axes
-          (64, 3, 5), (128, 5, 3), (512, 3, 1), (12, 64, 5), (3, 5, 256), (256, 7, 32)]
+          (64, 3, 5), (128, 5, 3), (512, 3, 1), (12, 64, 5), (3, 5, 256), (256, 7, 32),
+          # 512-point y / z lines take the 2 x (16 x 16) kernel (its root table must be the transformed axis' own)
+          (16, 512, 32), (8, 512, 512), (24, 512, 6)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
