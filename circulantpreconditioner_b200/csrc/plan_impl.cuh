@@ -421,6 +421,8 @@ template <typename T> struct PlanT : PlanBase {
                 if (sizeof(T) == 8 && reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FUSED_SEP)) != reg.end()) var = VAR_R2X;
                 else if (reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
             }
+            // the same kernel for the plain y passes of 512-point lines: 0.64 ms against 0.70 ms (8.8.8, 512 threads)
+            if (a == 1 && n[a] == 512 && sizeof(T) == 8 && reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FWD)) != reg.end()) var = VAR_R2X;
             // 256-point y lines: radix 8.8.4 with 8 points per thread and 4 small CTAs per SM (0.090 vs 0.108 ms at 256^3)
             if (a == 1 && n[a] == 256 && reg.find(FastKey<T>(n[a], VAR_SMALL, MODE_FWD)) != reg.end()) var = VAR_SMALL;
             {
@@ -447,9 +449,8 @@ template <typename T> struct PlanT : PlanBase {
                 c.tx = it->second.tx;
                 int rc_t = build_stage_table(it->second.radix, &stw[a]);
                 if (rc_t) return rc_t;
-                // 512-point y lines, fp64: the 2 x (16 x 16) kernel is faster for the plain forward pass (0.64 vs
-                // 0.70 ms at 512^3) but slower for the backward one (0.81 ms), so it serves the forward pass only
-                if (a == 1 && nfast == 512 && sizeof(T) == 8 && !getenv("CPC_VARIANT_Y")) {
+                // (hook for a separate forward-only variant; unused since the 2 x (16 x 16) kernel serves both directions)
+                if (false && a == 1 && nfast == 512 && sizeof(T) == 8 && !getenv("CPC_VARIANT_Y")) {
                     auto itf = reg.find(FastKey<T>(nfast, VAR_R2X, MODE_FWD));
                     if (itf != reg.end() && itf->second.tx == c.tx && itf->second.smem <= (size_t)dev_smem) {
                         c.variant_fwd = VAR_R2X;
