@@ -48,6 +48,7 @@ struct PassGeom {
     long long SIo, B0o, B1o;
     long long SCi, SCo;
     int Di, Do, shi, sho;
+    int maski, masko;     // Di - 1 / Do - 1 for power-of-two splits, 0x7fffffff (with sh = 31) when there is no split
     // symbol addressing (fused pass only): line index w = (t % tiles_inner) * TX + l decomposes as
     //   c = w % ncomp, x = (w / ncomp) % nx, y = w / (ncomp * nx)
     int ncomp, nx, ny;
@@ -90,6 +91,20 @@ __device__ __forceinline__ C *out_ptr(C *out, const PassGeom &g, long long obase
     if (g.Do == 0) return out + obase + (long long)i * g.SIo;
     if (g.sho >= 0) return out + obase + (long long)(i >> g.sho) * g.SCo + (long long)(i & (g.Do - 1)) * g.SIo;
     return out + obase + (long long)(i / g.Do) * g.SCo + (long long)(i % g.Do) * g.SIo;
+}
+
+// Branch-free forms used by the general-addressing builds of the fast kernels (power-of-two splits only; the host
+// sets sh = 31, mask = 0x7fffffff, SC = 0 and peer[q] = out when a side is a plain strided line).
+__device__ __forceinline__ long long gen_in_off(const PassGeom &g, int i)
+{
+    return (long long)(i >> g.shi) * g.SCi + (long long)(i & g.maski) * g.SI;
+}
+template <typename C> __device__ __forceinline__ C *gen_out_ptr(const PassGeom &g, long long obase, int i)
+{
+    const int q = i >> g.sho;
+    C *base = reinterpret_cast<C *>(g.peer[0]);                      // the local output unless peers are mapped
+    if (g.npeer > 0) base = reinterpret_cast<C *>(g.peer[q]);        // (indexed kernel-parameter load only then)
+    return base + obase + (long long)q * g.SCo + (long long)(i & g.masko) * g.SIo;
 }
 
 __device__ __forceinline__ long long point_off(int i, long long S, int D, int sh, long long SC)
@@ -327,14 +342,14 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
 
     C v[E];
     if (active) {
-        if (!GEN || g.Di == 0) {      // plain strided line (every pass except the multi-rank backward y pass)
+        if (!GEN) {      // plain strided line
             const C *p = in + gbase + (long long)j * g.SI;
             const long long step = (long long)TPL * g.SI;
 #pragma unroll
             for (int m = 0; m < E; ++m) v[m] = p[m * step];
-        } else {
+        } else {         // chunked layout on the load side (multi-rank backward y pass), branch-free
 #pragma unroll
-            for (int m = 0; m < E; ++m) v[m] = in[gbase + point_off(j + TPL * m, g.SI, g.Di, g.shi, g.SCi)];
+            for (int m = 0; m < E; ++m) v[m] = in[gbase + gen_in_off(g, j + TPL * m)];
         }
     } else {
 #pragma unroll
@@ -388,14 +403,14 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
     }
 
     if (active) {
-        if (!GEN || g.Do == 0) {      // plain strided line
+        if (!GEN) {      // plain strided line
             C *p = out + obase + (long long)j * g.SIo;
             const long long step = (long long)TPL * g.SIo;
 #pragma unroll
             for (int m = 0; m < E; ++m) p[m * step] = v[m];
-        } else {              // chunked layout or peer push (multi-rank plans)
+        } else {         // chunked layout or peer push (multi-rank plans), branch-free
 #pragma unroll
-            for (int m = 0; m < E; ++m) *out_ptr<C>(out, g, obase, j + TPL * m) = v[m];
+            for (int m = 0; m < E; ++m) *gen_out_ptr<C>(g, obase, j + TPL * m) = v[m];
         }
     }
 }

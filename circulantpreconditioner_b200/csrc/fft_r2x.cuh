@@ -80,8 +80,8 @@ fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out,
             const int k = j + 16 * (8 * s + i);
             C x0 = mk<T>((T)0, (T)0), x1 = x0;
             if (active) {
-                x0 = in[gbase + ((!GEN || g.Di == 0) ? (long long)k * g.SI : point_off(k, g.SI, g.Di, g.shi, g.SCi))];
-                x1 = in[gbase + ((!GEN || g.Di == 0) ? (long long)(k + H) * g.SI : point_off(k + H, g.SI, g.Di, g.shi, g.SCi))];
+                x0 = in[gbase + (GEN ? gen_in_off(g, k) : (long long)k * g.SI)];
+                x1 = in[gbase + (GEN ? gen_in_off(g, k + H) : (long long)(k + H) * g.SI)];
             }
             a[i] = cadd(x0, x1);
             b[i] = twmul<D1>(csub(x0, x1), __ldg(&rt[k]));
@@ -102,8 +102,8 @@ fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out,
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
                 const int K = 2 * (j + 16 * m) + s;
-                if (!GEN || g.Do == 0) out[obase + (long long)K * g.SIo] = u[m];
-                else *out_ptr<C>(out, g, obase, K) = u[m];
+                if (!GEN) out[obase + (long long)K * g.SIo] = u[m];
+                else *gen_out_ptr<C>(g, obase, K) = u[m];
             }
         }
         return;
@@ -125,12 +125,12 @@ fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out,
         const C tt = cmulc(yb, __ldg(&rt[n]));                       // conj(W^n) yB[n]
         const C x0 = cadd(ya, tt), x1 = csub(ya, tt);
         if (active) {
-            if (!GEN || g.Do == 0) {
+            if (!GEN) {
                 out[obase + (long long)n * g.SIo] = x0;
                 out[obase + (long long)(n + H) * g.SIo] = x1;
             } else {
-                *out_ptr<C>(out, g, obase, n) = x0;
-                *out_ptr<C>(out, g, obase, n + H) = x1;
+                *gen_out_ptr<C>(g, obase, n) = x0;
+                *gen_out_ptr<C>(g, obase, n + H) = x1;
             }
         }
     }

@@ -422,7 +422,10 @@ template <typename T> struct PlanT : PlanBase {
                 else if (reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
             }
             // the same kernel for the plain y passes of 512-point lines: 0.64 ms against 0.70 ms (8.8.8, 512 threads)
-            if (a == 1 && n[a] == 512 && sizeof(T) == 8 && reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FWD)) != reg.end()) var = VAR_R2X;
+            // (single-rank only: in the chunked multi-rank layout its paired loads k / k+256 sit exactly one chunk,
+            // a large power of two, apart and collide in the L2 / DRAM address hash: 0.57 vs 0.35 ms per half slab)
+            if (a == 1 && n[a] == 512 && sizeof(T) == 8 && desc.nranks == 1 &&
+                reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FWD)) != reg.end()) var = VAR_R2X;
             // 256-point y lines: radix 8.8.4 with 8 points per thread and 4 small CTAs per SM (0.090 vs 0.108 ms at 256^3)
             if (a == 1 && n[a] == 256 && reg.find(FastKey<T>(n[a], VAR_SMALL, MODE_FWD)) != reg.end()) var = VAR_SMALL;
             {
@@ -435,6 +438,8 @@ template <typename T> struct PlanT : PlanBase {
             if (reg.find(FastKey<T>(nfast, var, MODE_FWD)) == reg.end() && var != VAR_XMAP) var = VAR_NARROW;
             auto it = reg.find(FastKey<T>(nfast, var, MODE_FWD));
             if (it != reg.end() && a == 2 && reg.find(FastKey<T>(n[a], var, MODE_FUSED_SEP)) == reg.end()) it = reg.end();
+            // multi-rank fast kernels address chunks with shifts: ny/nranks and nz/nranks must be powers of two
+            if (it != reg.end() && desc.nranks > 1 && a >= 1 && ((nyl & (nyl - 1)) != 0 || (nzl & (nzl - 1)) != 0)) it = reg.end();
             // multi-rank plans push / chunk their y and z stores: only variants with a general-addressing build
             if (it != reg.end() && desc.nranks > 1 && a >= 1 &&
                 reg.find(FastKey<T>(nfast, var, MODE_FWD + GEN_BIT)) == reg.end()) {
@@ -587,6 +592,7 @@ template <typename T> struct PlanT : PlanBase {
         }
         g.SIo = g.SI; g.B0o = g.B0; g.B1o = g.B1; g.SLo = g.SL;
         g.SCi = g.SCo = 0; g.Di = g.Do = 0; g.shi = g.sho = -1;
+        g.maski = g.masko = 0x7fffffff;
         g.pf_tiles = 0;
         g.npeer = 0;
         for (int q = 0; q < CPC_MAX_PEERS; ++q) g.peer[q] = nullptr;
@@ -604,7 +610,9 @@ template <typename T> struct PlanT : PlanBase {
         if (split_out) {
             g.SIo = W; g.B0o = g.B0; g.B1o = (long long)nyl * W;
             g.Do = nyl; g.sho = sh; g.SCo = (long long)nzl * nyl * W;
+            g.masko = nyl - 1;
         } else {
+            g.maski = nyl - 1;
             g.B1o = g.B1; g.B0o = g.B0; g.SIo = g.SI; g.SLo = g.SL;
             g.B1 = (long long)nyl * W;
             g.Di = nyl; g.shi = sh; g.SCi = (long long)nzl * nyl * W;
@@ -640,6 +648,7 @@ template <typename T> struct PlanT : PlanBase {
                 if ((1 << b) == D) sh = b;
             g.npeer = desc.nranks;
             g.Do = D; g.sho = sh; g.SCo = 0;
+            g.masko = D - 1;
             if (split == 3) {
                 // point ky of the y line at (z_loc, x) -> rank q = ky / nyl, element [(z0 + z_loc)][ky % nyl][x]
                 g.SIo = W; g.B0o = g.B0; g.B1o = (long long)nyl * W;
@@ -655,6 +664,15 @@ template <typename T> struct PlanT : PlanBase {
         s.rz = tw[axis];          // roots of the transformed axis (fft_r2x.cuh); the fused pass is always axis 2
         if (c.fast) {
             // multi-rank y / z passes need the general-addressing build (init() made sure it exists)
+            if (split != 0) {
+                // branch-free general addressing: a side without a split behaves as one chunk of 2^31 points, and
+                // without peers every "peer" is the local output
+                if (g.Di == 0) { g.shi = 31; g.maski = 0x7fffffff; g.SCi = 0; }
+                if (g.Do == 0) { g.sho = 31; g.masko = 0x7fffffff; g.SCo = 0; }
+                if (g.npeer == 0)
+                    for (int q = 0; q < CPC_MAX_PEERS; ++q) g.peer[q] = (void *)(out + off);
+                if (g.shi < 0 || g.sho < 0) { set_error("multi-rank fast path needs power-of-two ny/nranks and nz/nranks"); return CPC_ERR_UNSUPPORTED; }
+            }
             const bool alt = (mode == MODE_FWD && c.variant_fwd >= 0);
             const FastEntry<T> &e = reg.at(FastKey<T>(c.nfast, alt ? c.variant_fwd : c.variant, mode + (split != 0 ? GEN_BIT : 0)));
             const int grid = (g.ntiles + e.g - 1) / e.g;
