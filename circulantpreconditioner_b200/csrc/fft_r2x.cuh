@@ -137,3 +137,77 @@ fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out,
 }
 
 }  // namespace cpc
+
+namespace cpc {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Contiguous 512-point lines (the scalar x pass): ONE WARP PER LINE, no block-wide barrier at all.
+// Lane L loads the pairs (k, k+256) for k = L + 32 i (a warp reads 512 contiguous bytes per instruction), does the
+// radix-2 level, swaps half of its points with lane L ^ 16, and then lanes 0-15 transform half-line A, lanes 16-31
+// half-line B with the 16 x 16 Stockham code; the exchange between its two stages goes through a warp-private
+// 8 KB shared-memory slab (XOR-swizzled 16-byte chunks, conflict-free for both access patterns) fenced by
+// __syncwarp only.  Plain transforms only (MODE_FWD / MODE_INV), decimation in frequency in both directions.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int MODE, int LINES>
+__global__ void __launch_bounds__(32 * LINES, 2)
+fft_r2x512_line_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
+                       const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
+{
+    using C = cplx_t<T>;
+    constexpr int H = 256;
+    constexpr int D1 = (MODE == MODE_INV) ? +1 : -1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    C *sm = reinterpret_cast<C *>(smem_raw) + (size_t)wrp * 512;
+    const int sg = lane >> 4;             // half-line this lane transforms after the swap
+    const int j = lane & 15;
+
+    const int t = blockIdx.x;
+    const int ti = t % g.tiles_inner, to = t / g.tiles_inner;
+    const int w = ti * LINES + wrp;
+    const bool active = w < g.lines_inner;
+    const long long gbase = (long long)to * g.B1 + (long long)ti * g.B0 + (long long)wrp * g.SL;
+    const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)wrp * g.SLo;
+    const C *rt = sym.rz;
+
+    C u[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = lane + 32 * i;
+        C x0 = mk<T>((T)0, (T)0), x1 = x0;
+        if (active) {
+            x0 = in[gbase + (long long)k * g.SI];
+            x1 = in[gbase + (long long)(k + H) * g.SI];
+        }
+        const C a = cadd(x0, x1);
+        const C b = twmul<D1>(csub(x0, x1), __ldg(&rt[k]));
+        // lanes 0-15 keep a (point k = j + 16 (2i)) and get the partner's a (k = j + 16 (2i+1)); lanes 16-31 keep b
+        // (k = j + 16 (2i+1)) and get the partner's b (k = j + 16 (2i))
+        const C recv = shfl_xor_c(sg ? a : b, 16);
+        u[2 * i] = sg ? recv : a;
+        u[2 * i + 1] = sg ? b : recv;
+    }
+
+    Butterfly<16, D1, C>::run(u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const int idx = j * 16 + r;
+        sm[sg * H + (idx ^ (j & 7))] = u[r];                      // (idx >> 4) & 7 == j & 7
+    }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+        const int idx = j + 16 * m;
+        u[m] = sm[sg * H + (idx ^ (m & 7))];                      // (idx >> 4) & 7 == m & 7
+    }
+#pragma unroll
+    for (int r = 1; r < 16; ++r) u[r] = twmul<D1>(u[r], __ldg(&tw[(r - 1) * 16 + j]));
+    Butterfly<16, D1, C>::run(u);
+
+    if (active) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) out[obase + (long long)(2 * (j + 16 * m) + sg) * g.SIo] = u[m];
+    }
+}
+
+}  // namespace cpc

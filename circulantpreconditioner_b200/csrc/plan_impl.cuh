@@ -44,7 +44,8 @@ enum Variant {
     VAR_WIDE2 = 3,    // as VAR_WIDE with a different points-per-thread / radix split (512: two butterflies per thread)
     VAR_SMALL = 4,    // as VAR_WIDE with small CTAs, 4 per SM (256-point y lines)
     VAR_R2X = 5,      // 512 = 2 x (16 x 16): radix-2 level in registers + warp shuffle, one shared-memory exchange
-    VAR_COUNT = 6
+    VAR_XR2X = 6,     // the same for contiguous lines: one warp per line, no block barrier (scalar x pass)
+    VAR_COUNT = 7
 };
 
 template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, variant, mode + 16 * general-addressing)
@@ -105,6 +106,15 @@ template <typename T> static void register_r2x512(std::map<FastKey<T>, FastEntry
 #undef CPC_R2X
 }
 
+// contiguous 512-point lines, one warp per line (fft_r2x.cuh); plain transforms only
+template <typename T> static void register_r2x512_line(std::map<FastKey<T>, FastEntry<T>> &m)
+{
+    constexpr int LINES = 8;
+    FastEntry<T> e{ nullptr, 32 * LINES, (size_t)LINES * 512 * sizeof(cplx_t<T>), 1, LINES, { 16, 16, 1 } };
+    e.kern = fft_r2x512_line_kernel<T, MODE_FWD, LINES>; m[FastKey<T>(512, VAR_XR2X, MODE_FWD)] = e;
+    e.kern = fft_r2x512_line_kernel<T, MODE_INV, LINES>; m[FastKey<T>(512, VAR_XR2X, MODE_INV)] = e;
+}
+
 template <typename T> struct FastRegistry;
 
 #ifdef CPC_INSTANTIATE_F64
@@ -122,6 +132,7 @@ template <> struct FastRegistry<double> {
         register_modes<double, VAR_WIDE,   1024, 16,  8,  8, 16,  8,  1, 1>(m);
         register_modes<double, VAR_WIDE2,   512,  8,  8,  8, 16,  8,  1, 2>(m);
         register_r2x512<double>(m);
+        register_r2x512_line<double>(m);
         register_modes<double, VAR_WIDE2,   256,  8,  8,  4,  8,  8,  2, 2>(m);      // 512 thr, 64 regs
         register_modes<double, VAR_WIDE2,   128,  8,  4,  4,  8,  8,  4, 2>(m);      // 512 thr, 64 regs
         register_modes<double, VAR_SMALL,    256,  8,  8,  4,  8,  8,  1, 4>(m);      // 256 thr, 64 regs, 4 CTAs/SM
@@ -421,7 +432,10 @@ template <typename T> struct PlanT : PlanBase {
                 if (sizeof(T) == 8 && reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FUSED_SEP)) != reg.end()) var = VAR_R2X;
                 else if (reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
             }
-            // the same kernel for the plain y passes of 512-point lines: 0.64 ms against 0.70 ms (8.8.8, 512 threads)
+            // contiguous 512-point x lines: one warp per line, no block barrier (0.62 vs 0.69 ms at 512^3)
+            if (a == 0 && nc == 1 && !real && n[a] == 512 && sizeof(T) == 8 && !getenv("CPC_VARIANT_X") &&
+                reg.find(FastKey<T>(n[a], VAR_XR2X, MODE_FWD)) != reg.end()) var = VAR_XR2X;
+            // the 2 x (16 x 16) kernel also for the plain y passes of 512-point lines: 0.64 ms against 0.70 ms (8.8.8)
             // (single-rank only: in the chunked multi-rank layout its paired loads k / k+256 sit exactly one chunk,
             // a large power of two, apart and collide in the L2 / DRAM address hash: 0.57 vs 0.35 ms per half slab)
             if (a == 1 && n[a] == 512 && sizeof(T) == 8 && desc.nranks == 1 &&
