@@ -167,6 +167,7 @@ template <> struct FastRegistry<float> {
         register_modes<float, VAR_WIDE,    256, 16, 16,  1, 16, 16,  1, 2>(m);
         register_modes<float, VAR_WIDE,    512, 16,  8,  4, 16, 16,  1, 2>(m);
         register_modes<float, VAR_WIDE,   1024, 16,  8,  8, 16, 16,  1, 1>(m);
+        register_r2x512_line<float>(m);
         register_modes<float, VAR_NARROW,   16, 16,  1,  1, 16,  4, 32, 2>(m);
         register_modes<float, VAR_NARROW,   32,  8,  4,  1,  8,  4, 16, 2>(m);
         register_modes<float, VAR_NARROW,   64,  8,  8,  1,  8,  4,  8, 2>(m);
@@ -433,7 +434,7 @@ template <typename T> struct PlanT : PlanBase {
                 else if (reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
             }
             // contiguous 512-point x lines: one warp per line, no block barrier (0.62 vs 0.69 ms at 512^3)
-            if (a == 0 && nc == 1 && !real && n[a] == 512 && sizeof(T) == 8 && !getenv("CPC_VARIANT_X") &&
+            if (a == 0 && nc == 1 && !real && n[a] == 512 && !getenv("CPC_VARIANT_X") &&
                 reg.find(FastKey<T>(n[a], VAR_XR2X, MODE_FWD)) != reg.end()) var = VAR_XR2X;
             // the 2 x (16 x 16) kernel also for the plain y passes of 512-point lines: 0.64 ms against 0.70 ms (8.8.8)
             // (single-rank only: in the chunked multi-rank layout its paired loads k / k+256 sit exactly one chunk,
