@@ -469,14 +469,6 @@ template <typename T> struct PlanT : PlanBase {
                 c.tx = it->second.tx;
                 int rc_t = build_stage_table(it->second.radix, &stw[a]);
                 if (rc_t) return rc_t;
-                // (hook for a separate forward-only variant; unused since the 2 x (16 x 16) kernel serves both directions)
-                if (false && a == 1 && nfast == 512 && sizeof(T) == 8 && !getenv("CPC_VARIANT_Y")) {
-                    auto itf = reg.find(FastKey<T>(nfast, VAR_R2X, MODE_FWD));
-                    if (itf != reg.end() && itf->second.tx == c.tx && itf->second.smem <= (size_t)dev_smem) {
-                        c.variant_fwd = VAR_R2X;
-                        if ((rc_t = build_stage_table(itf->second.radix, &stw_fwd[a]))) return rc_t;
-                    }
-                }
             } else {
                 c.fast = false;
                 c.fl.n = n[a];

@@ -338,3 +338,46 @@ def test_projected_apply_unstructured_to_cartesian():
         xh = np.empty_like(b)
         p.apply_projected(b, xh)                   # host pointers
         assert rel_l2(xh, want) < TOL64
+
+
+def test_wave_block_fp32():
+    nx, ny, nz = 32, 16, 64
+    rng = np.random.default_rng(19)
+    c0, mu = 3.0, (0.0793651, 0.05, 0.03)
+    y = rng.standard_normal(nx * ny * nz * 4)
+    b = O.apply_wave_matrix(y, nx, ny, nz, c0, *mu).astype(np.complex128)
+    want = O.solve_wave_block(b, nx, ny, nz, c0, *mu)
+    with cpc.CirculantPlan(nx, ny, nz, ncomp=4, dtype="c64") as p:
+        p.set_symbol_wave(c0, *mu)
+        got = host(p.apply(dev(b, torch.complex64)))
+    assert rel_l2(got, want) < TOL32
+
+
+def test_two_plans_and_streams_do_not_interfere():
+    # two plans on two torch streams, interleaved applies: per-plan state only
+    n = 64
+    rng = np.random.default_rng(31)
+    lam1, lam2 = (1.0, 2.0, 3.0), (55.5556, 0.0, 0.0)
+    b = rand_c(rng, n ** 3)
+    w1 = O.FftTransportSolver(n, n, n, *lam1, b)
+    w2 = O.FftTransportSolver(n, n, n, *lam2, b)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    d = dev(b)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        p1 = cpc.CirculantPlan(n, n, n)
+        p1.set_symbol_transport(*lam1)
+    with torch.cuda.stream(s2):
+        p2 = cpc.CirculantPlan(n, n, n)
+        p2.set_symbol_transport(*lam2)
+    outs = []
+    for _ in range(3):
+        with torch.cuda.stream(s1):
+            o1 = p1.apply(d)
+        with torch.cuda.stream(s2):
+            o2 = p2.apply(d)
+        outs.append((o1, o2))
+    torch.cuda.synchronize()
+    for o1, o2 in outs:
+        assert rel_l2(host(o1), w1) < TOL64 and rel_l2(host(o2), w2) < TOL64
+    p1.destroy(); p2.destroy()
