@@ -102,7 +102,8 @@ SHAPES = [(16, 16, 16), (32, 64, 16), (64, 16, 128), (128, 32, 16), (256, 16, 32
           # fast kernels with partial tiles (lines not a multiple of the tile width) and mixed fast / generic axes
           (64, 3, 5), (128, 5, 3), (512, 3, 1), (12, 64, 5), (3, 5, 256), (256, 7, 32),
           # 512-point y / z lines take the 2 x (16 x 16) kernel (its root table must be the transformed axis' own)
-          (16, 512, 32), (8, 512, 512), (24, 512, 6)]
+          (16, 512, 32), (8, 512, 512), (24, 512, 6),
+          (16, 1024, 8), (8, 4, 1024)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
