@@ -53,6 +53,8 @@ struct PassGeom {
     //   c = w % ncomp, x = (w / ncomp) % nx, y = w / (ncomp * nx)
     int ncomp, nx, ny;
     int y0;               // global y of local y index 0 (multi-rank transposed slab)
+    int stagger;          // > 0: CTAs of the second resident slot of every SM start this many cycles late, so that
+    int num_sms;          //      the two CTAs sharing an SM are not in the same (fp64 vs LSU) phase all the time
     int pf_tiles;         // > 0: prefetch into L2 the tile `pf_tiles` after this one (about one wave of CTAs ahead)
     // Fused transpose (multi-rank plans with peer access): with npeer > 0 the chunk index i / Do selects the rank
     // whose buffer receives the point, and the store goes straight to that rank's HBM over NVLink

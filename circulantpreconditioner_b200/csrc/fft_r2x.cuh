@@ -67,6 +67,15 @@ fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out,
     const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)l * g.SLo;
     const C *rt = sym.rz;                 // roots exp(-2 pi i k / 512) of the transformed axis
 
+    // Tuning hook (CPC_STAGGER, default 0 = no delay): start every SM's second resident CTA late.  The delay itself
+    // made no difference (profiles/r01_notes.md), but the loop is an instruction-scheduling fence at the top of the
+    // kernel: with it ptxas keeps the fused kernel's spills at 8 B instead of 64 B and the pass runs 1.05 ms instead
+    // of 1.22 ms.  It is compiled into the fused modes only (it costs the plain backward pass 0.09 ms).
+    if (MODE >= MODE_FUSED_SEP && g.stagger > 0 && blockIdx.x >= (unsigned)g.num_sms && blockIdx.x < 2u * (unsigned)g.num_sms) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < g.stagger) { }
+    }
+
     C u[16];
     // Plain transforms (forward and backward) both use the decimation-in-frequency structure, with conjugated
     // twiddles for the backward one: it measured 0.64 ms for a 512^3 y pass against 0.81 ms for the decimation-in-time

@@ -297,6 +297,7 @@ template <typename T> struct PlanT : PlanBase {
     C *work = nullptr;            // half spectrum (real plans) or the promoted complex copy
     int num_sms = 148;
     int pf_waves = 0;             // L2 prefetch distance in units of (SM count) CTAs; 0 = off
+    int stagger = 0;              // start offset (cycles) of every SM's second resident CTA (tuning hook)
     int nzl = 1, z0 = 0;          // local z slab
     int nyl = 1, y0 = 0;          // local y range in the transposed distribution
     long long nloc = 0;           // local elements (slab distribution)
@@ -409,6 +410,7 @@ template <typename T> struct PlanT : PlanBase {
         CPC_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         if (const char *pf = getenv("CPC_PREFETCH_WAVES")) pf_waves = atoi(pf);   // tuning hook
+        if (const char *sg = getenv("CPC_STAGGER")) stagger = atoi(sg);           // tuning hook
         CPC_TRACE("got smem attribute");
 
         for (int a = 0; a < 3; ++a) {
@@ -601,6 +603,7 @@ template <typename T> struct PlanT : PlanBase {
         g.SCi = g.SCo = 0; g.Di = g.Do = 0; g.shi = g.sho = -1;
         g.maski = g.masko = 0x7fffffff;
         g.pf_tiles = 0;
+        g.stagger = stagger; g.num_sms = num_sms;
         g.npeer = 0;
         for (int q = 0; q < CPC_MAX_PEERS; ++q) g.peer[q] = nullptr;
         return g;
