@@ -74,6 +74,45 @@ def test_two_rank_wave_block():
         assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
 
 
+def _worker_table(rank, P, port, shape, col, b_full, want, errs):
+    import circulantpreconditioner_b200 as cpc
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=P, device_id=torch.device("cuda", rank))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(cpc.nccl_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    nx, ny, nz = shape
+    z0, nzl = cpc.slab_range(nz, P, rank)
+    plane = nx * ny
+    sl = slice(z0 * plane, (z0 + nzl) * plane)
+    with cpc.CirculantPlan(nx, ny, nz, nranks=P, rank=rank, nccl_id=idt.cpu().numpy().tobytes()) as p:
+        p.set_symbol_first_column(torch.from_numpy(col[sl].copy()).cuda())      # each rank passes its z-slab of the column
+        out = p.apply(torch.from_numpy(b_full[sl].copy()).cuda())
+        errs[rank] = float(np.linalg.norm(out.cpu().numpy() - want[sl]) / np.linalg.norm(want))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_general_first_column():
+    from oracle import circulant_oracle as O
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    nx, ny, nz = 32, 64, 16
+    rng = np.random.default_rng(9)
+    col = np.zeros((nz, ny, nx), dtype=np.complex128)
+    col[0, 0, 0] = 7.0
+    col[0, 0, 1] = -1.0; col[0, 1, 0] = -1.5; col[1, 0, 0] = -0.5; col[-1, 0, 0] = -0.75; col[0, -1, 0] = 0.3j
+    b = rng.standard_normal(nx * ny * nz) + 1j * rng.standard_normal(nx * ny * nz)
+    want = O.solve_first_column(col.ravel(), b, nx, ny, nz)
+    mgr = mp.Manager()
+    errs = mgr.dict()
+    mp.spawn(_worker_table, args=(2, 29700 + (os.getpid() % 2000), (nx, ny, nz), col.ravel(), b, want, errs), nprocs=2, join=True)
+    for r, e in dict(errs).items():
+        assert e < 1e-12, (r, e)
+
+
 def test_four_rank_transport():
     errs = _run((64, 64, 64), (1.0, 2.0, 3.0), P=4)
     for r, (e1, e2, e3) in errs.items():
