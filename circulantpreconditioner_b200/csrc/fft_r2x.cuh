@@ -220,3 +220,89 @@ fft_r2x512_line_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__
 }
 
 }  // namespace cpc
+
+namespace cpc {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Contiguous 256-point lines (16 x 16), HALF A WARP PER LINE, no block-wide barrier: the x pass of 256-wide grids
+// and -- through MODE_R2C / MODE_C2R -- the r2c / c2r x pass of real-scalar plans with nx = 512 (a real line of 512
+// points is transformed as 256 complex points and untangled / tangled, see fft_pass.cuh).  Each half warp owns a
+// 4 KB XOR-swizzled shared-memory slab used for the exchange between the two radix-16 stages and, in r2c mode, for
+// fetching the mirror point Z[256 - k]; everything is fenced by __syncwarp.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int MODE, int LINES>
+__global__ void __launch_bounds__(16 * LINES, 2)
+fft_line256_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
+                   const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
+{
+    using C = cplx_t<T>;
+    constexpr int N = 256;
+    constexpr int DIR = (MODE == MODE_INV || MODE == MODE_C2R) ? +1 : -1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lw = threadIdx.x >> 4;                 // line within the tile
+    const int j = threadIdx.x & 15;
+    C *sm = reinterpret_cast<C *>(smem_raw) + (size_t)lw * N;
+
+    const int t = blockIdx.x;
+    const int ti = t % g.tiles_inner, to = t / g.tiles_inner;
+    const int w = ti * LINES + lw;
+    const bool active = w < g.lines_inner;
+    const long long gbase = (long long)to * g.B1 + (long long)ti * g.B0 + (long long)lw * g.SL;
+    const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)lw * g.SLo;
+
+    C u[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) u[m] = active ? in[gbase + (j + 16 * m)] : mk<T>((T)0, (T)0);
+
+    if (MODE == MODE_C2R) {
+        // Z[k] = (X[k] + conj X[N-k]) + i conj(w^k) (X[k] - conj X[N-k]),  w = exp(-i pi / N)   (cf. fft_pass.cuh)
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int k = j + 16 * m;
+            const C a = u[m];
+            const C bq = active ? in[gbase + (N - k)] : mk<T>((T)0, (T)0);
+            const C s1 = mk<T>(a.x + bq.x, a.y - bq.y);
+            const C d1 = mk<T>(a.x - bq.x, a.y + bq.y);
+            const C t1 = cmulc(d1, __ldg(&sym.rx[k]));
+            u[m] = mk<T>(s1.x - t1.y, s1.y + t1.x);
+        }
+    }
+
+    Butterfly<16, DIR, C>::run(u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[(j * 16 + r) ^ (j & 7)] = u[r];
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 16; ++m) u[m] = sm[(j + 16 * m) ^ (m & 7)];
+#pragma unroll
+    for (int r = 1; r < 16; ++r) u[r] = twmul<DIR>(u[r], __ldg(&tw[(r - 1) * 16 + j]));
+    Butterfly<16, DIR, C>::run(u);                   // u[m] = point j + 16 m
+
+    if (MODE == MODE_R2C) {
+        // X[k] = E[k] + w^k O[k],  E = (Z[k] + conj Z[N-k]) / 2,  O = -i (Z[k] - conj Z[N-k]) / 2;  X[N] = Re Z[0] - Im Z[0]
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < 16; ++m) sm[(j + 16 * m) ^ (m & 7)] = u[m];
+        __syncwarp();
+        C nyq = mk<T>((T)0, (T)0);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int k = j + 16 * m;
+            const int km = (N - k) & (N - 1);
+            const C a = u[m];
+            const C bq = sm[km ^ ((km >> 4) & 7)];
+            const C ev = mk<T>((T)0.5 * (a.x + bq.x), (T)0.5 * (a.y - bq.y));
+            const C od = mk<T>((T)0.5 * (a.y + bq.y), (T)-0.5 * (a.x - bq.x));
+            u[m] = cadd(ev, cmul(od, __ldg(&sym.rx[k])));
+            if (k == 0) nyq = mk<T>(a.x - a.y, (T)0);
+        }
+        if (active && j == 0) out[obase + N] = nyq;
+    }
+
+    if (active) {
+#pragma unroll
+        for (int m = 0; m < 16; ++m) out[obase + (j + 16 * m)] = u[m];
+    }
+}
+
+}  // namespace cpc

@@ -115,6 +115,17 @@ template <typename T> static void register_r2x512_line(std::map<FastKey<T>, Fast
     e.kern = fft_r2x512_line_kernel<T, MODE_INV, LINES>; m[FastKey<T>(512, VAR_XR2X, MODE_INV)] = e;
 }
 
+// contiguous 256-point lines, half a warp per line (fft_r2x.cuh): plain transforms and the r2c / c2r pair
+template <typename T> static void register_line256(std::map<FastKey<T>, FastEntry<T>> &m)
+{
+    constexpr int LINES = 16;
+    FastEntry<T> e{ nullptr, 16 * LINES, (size_t)LINES * 256 * sizeof(cplx_t<T>), 1, LINES, { 16, 16, 1 } };
+    e.kern = fft_line256_kernel<T, MODE_FWD, LINES>; m[FastKey<T>(256, VAR_XR2X, MODE_FWD)] = e;
+    e.kern = fft_line256_kernel<T, MODE_INV, LINES>; m[FastKey<T>(256, VAR_XR2X, MODE_INV)] = e;
+    e.kern = fft_line256_kernel<T, MODE_R2C, LINES>; m[FastKey<T>(256, VAR_XR2X, MODE_R2C)] = e;
+    e.kern = fft_line256_kernel<T, MODE_C2R, LINES>; m[FastKey<T>(256, VAR_XR2X, MODE_C2R)] = e;
+}
+
 template <typename T> struct FastRegistry;
 
 #ifdef CPC_INSTANTIATE_F64
@@ -133,6 +144,7 @@ template <> struct FastRegistry<double> {
         register_modes<double, VAR_WIDE2,   512,  8,  8,  8, 16,  8,  1, 2>(m);
         register_r2x512<double>(m);
         register_r2x512_line<double>(m);
+        register_line256<double>(m);
         register_modes<double, VAR_WIDE2,   256,  8,  8,  4,  8,  8,  2, 2>(m);      // 512 thr, 64 regs
         register_modes<double, VAR_WIDE2,   128,  8,  4,  4,  8,  8,  4, 2>(m);      // 512 thr, 64 regs
         register_modes<double, VAR_SMALL,    256,  8,  8,  4,  8,  8,  1, 4>(m);      // 256 thr, 64 regs, 4 CTAs/SM
@@ -168,6 +180,7 @@ template <> struct FastRegistry<float> {
         register_modes<float, VAR_WIDE,    512, 16,  8,  4, 16, 16,  1, 2>(m);
         register_modes<float, VAR_WIDE,   1024, 16,  8,  8, 16, 16,  1, 1>(m);
         register_r2x512_line<float>(m);
+        register_line256<float>(m);
         register_modes<float, VAR_NARROW,   16, 16,  1,  1, 16,  4, 32, 2>(m);
         register_modes<float, VAR_NARROW,   32,  8,  4,  1,  8,  4, 16, 2>(m);
         register_modes<float, VAR_NARROW,   64,  8,  8,  1,  8,  4,  8, 2>(m);
@@ -452,6 +465,9 @@ template <typename T> struct PlanT : PlanBase {
             }
             const int nfast = (real && !real_promote && a == 0) ? n2 : n[a];     // r2c: nx real points = nx/2 complex
             if (real && !real_promote && a == 0) var = VAR_XMAP;
+            // contiguous 256-point lines (complex nx = 256, or the r2c / c2r pass of real nx = 512): half a warp per line
+            if (a == 0 && nc == 1 && nfast == 256 && !getenv("CPC_VARIANT_X") &&
+                reg.find(FastKey<T>(256, VAR_XR2X, real ? MODE_R2C : MODE_FWD)) != reg.end()) var = VAR_XR2X;
             if (reg.find(FastKey<T>(nfast, var, MODE_FWD)) == reg.end() && var != VAR_XMAP) var = VAR_NARROW;
             auto it = reg.find(FastKey<T>(nfast, var, MODE_FWD));
             if (it != reg.end() && a == 2 && reg.find(FastKey<T>(n[a], var, MODE_FUSED_SEP)) == reg.end()) it = reg.end();
