@@ -1,5 +1,5 @@
-// fft_r2x.cuh -- 2H-point strided-line pass as  2 x (16 x 16)  with H = 256:  one radix-2 level in registers, a warp
-// shuffle, and a two-stage radix-16 Stockham transform per half -- ONE shared-memory exchange per transform instead
+// fft_r2x.cuh -- 2H-point strided-line pass as  2 x (R0 x R1)  (512 = 2 x 16 x 16, 256 = 2 x 16 x 8):  one radix-2
+// level in registers, a warp shuffle, and a two-stage Stockham transform per half -- ONE shared-memory exchange per transform instead
 // of the two that the 8.8.8 kernel needs.  The fused z pass is limited by LSU wavefronts and barrier-serialised
 // phases, not by HBM (profiles/r01_notes.md); this variant cuts its shared-memory traffic by half.
 //
@@ -25,39 +25,26 @@ template <typename C> __device__ __forceinline__ C shfl_xor_c(C v, int mask)
     return r;
 }
 
-// H-point (16 x 16) transform of the 16 points {j + 16 m} of half-line s; shared memory [point][s][lane l].
-template <typename T, int DIR>
-__device__ __forceinline__ void half_fft_16x16(cplx_t<T> (&u)[16], int j, int s, int l, cplx_t<T> *sm,
-                                               const cplx_t<T> *__restrict__ tw)
+// N = 2 H points per line, H = R0 * R1 (two radix stages, 16 points per thread): 512 = 2 x (16 x 16) and
+// 256 = 2 x (16 x 8).  The half-line transform is the generic Stockham code of fft_pass.cuh run with the 16 "lanes"
+// (s, l): shared memory [point][s][l], so the 8 lanes of a quarter warp still hit one 128-byte row.
+template <typename T, int H, int R0, int R1, int MODE, bool GEN>
+__global__ void __launch_bounds__(H, 512 / H)
+fft_r2x_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
+               const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
 {
     using C = cplx_t<T>;
-    Butterfly<16, DIR, C>::run(u);                                   // stage 0: p = 1, no twiddles
-#pragma unroll
-    for (int r = 0; r < 16; ++r) sm[((j * 16 + r) * 2 + s) * 8 + l] = u[r];
-    __syncthreads();
-#pragma unroll
-    for (int m = 0; m < 16; ++m) u[m] = sm[((j + 16 * m) * 2 + s) * 8 + l];
-#pragma unroll
-    for (int r = 1; r < 16; ++r) u[r] = twmul<DIR>(u[r], __ldg(&tw[(r - 1) * 16 + j]));   // stage 1: p = 16, k = j
-    Butterfly<16, DIR, C>::run(u);                                   // u[m] = point j + 16 m, natural order
-}
-
-template <typename T, int MODE, bool GEN>
-__global__ void __launch_bounds__(256, 2)
-fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
-                  const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
-{
-    using C = cplx_t<T>;
-    constexpr int H = 256, TX = 8;
+    constexpr int TX = 8;
+    constexpr int TP = H / 16;            // threads per half-line = stride between a thread's points
+    static_assert(R0 * R1 == H && 16 % R0 == 0 && 16 % R1 == 0, "half-line must be two radix stages of 16 points per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *sm = reinterpret_cast<C *>(smem_raw);
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31, wrp = tid >> 5;
-    const int l = lane & 7;
-    const int qd = lane >> 3;
-    const int s = qd & 1;
-    const int j = (qd >> 1) + 2 * wrp;
+    const int l = tid & 7;
+    const int s = (tid >> 3) & 1;
+    const int j = tid >> 4;               // in [0, TP)
+    const int ls = s * 8 + l;             // the (s, l) "lane" of the half-line transform
 
     const int t = blockIdx.x;
     const int ti = t % g.tiles_inner, to = t / g.tiles_inner;
@@ -65,7 +52,7 @@ fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out,
     const bool active = w < g.lines_inner;
     const long long gbase = (long long)to * g.B1 + (long long)ti * g.B0 + (long long)l * g.SL;
     const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)l * g.SLo;
-    const C *rt = sym.rz;                 // roots exp(-2 pi i k / 512) of the transformed axis
+    const C *rt = sym.rz;                 // roots exp(-2 pi i k / N) of the transformed axis
 
     // Tuning hook (CPC_STAGGER, default 0 = no delay): start every SM's second resident CTA late.  The delay itself
     // made no difference (profiles/r01_notes.md), but the loop is an instruction-scheduling fence at the top of the
@@ -86,7 +73,7 @@ fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out,
         C a[8], b[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int k = j + 16 * (8 * s + i);
+            const int k = j + TP * (8 * s + i);
             C x0 = mk<T>((T)0, (T)0), x1 = x0;
             if (active) {
                 x0 = in[gbase + (GEN ? gen_in_off(g, k) : (long long)k * g.SI)];
@@ -103,14 +90,14 @@ fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out,
             u[i] = s ? recv : a[i];
             u[i + 8] = s ? b[i] : recv;
         }
-        half_fft_16x16<T, D1>(u, j, s, l, sm, tw);                   // u[m] = X[2 (j + 16 m) + s]
+        line_fft<T, H, R0, R1, 1, 16, D1, 16, false, 0>(u, j, ls, sm, tw, 0);   // u[m] = X[2 (j + TP m) + s]
     }
 
     if (MODE == MODE_FWD || MODE == MODE_INV) {
         if (active) {
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
-                const int K = 2 * (j + 16 * m) + s;
+                const int K = 2 * (j + TP * m) + s;
                 if (!GEN) out[obase + (long long)K * g.SIo] = u[m];
                 else *gen_out_ptr<C>(g, obase, K) = u[m];
             }
@@ -118,10 +105,10 @@ fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out,
         return;
     }
 
-    apply_symbol<T, 16, MODE>(u, 2 * j + s, 32, active ? w : 0, gbase, g.SI, g, sym);
+    apply_symbol<T, 16, MODE>(u, 2 * j + s, 2 * TP, active ? w : 0, gbase, g.SI, g, sym);
     __syncthreads();                                                 // shared memory is reused by the backward transform
 
-    half_fft_16x16<T, +1>(u, j, s, l, sm, tw);                       // u[m] = y_s[j + 16 m]
+    line_fft<T, H, R0, R1, 1, 16, +1, 16, false, 0>(u, j, ls, sm, tw, 0);       // u[m] = y_s[j + TP m]
 
     // ---- swap back and radix-2 level (decimation in time) ----------------------------------------------------------
 #pragma unroll
@@ -130,7 +117,7 @@ fft_r2x512_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out,
         const C recv = shfl_xor_c(send, 8);
         const C ya = s ? recv : u[i];
         const C yb = s ? u[i + 8] : recv;
-        const int n = j + 16 * (8 * s + i);
+        const int n = j + TP * (8 * s + i);
         const C tt = cmulc(yb, __ldg(&rt[n]));                       // conj(W^n) yB[n]
         const C x0 = cadd(ya, tt), x1 = csub(ya, tt);
         if (active) {

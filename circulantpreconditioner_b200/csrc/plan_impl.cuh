@@ -91,13 +91,13 @@ static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
         register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, true, NG>(m);
 }
 
-// 512-point strided lines as 2 x (16 x 16) (fft_r2x.cuh)
-template <typename T> static void register_r2x512(std::map<FastKey<T>, FastEntry<T>> &m)
+// strided lines of 2 H points as 2 x (R0 x R1) (fft_r2x.cuh)
+template <typename T, int H, int R0, int R1> static void register_r2x(std::map<FastKey<T>, FastEntry<T>> &m)
 {
-    FastEntry<T> e{ nullptr, 256, (size_t)256 * 16 * sizeof(cplx_t<T>), 1, 8, { 16, 16, 1 } };
-#define CPC_R2X(MODE)                                                                   \
-    e.kern = fft_r2x512_kernel<T, MODE, false>; m[FastKey<T>(512, VAR_R2X, MODE)] = e;           \
-    e.kern = fft_r2x512_kernel<T, MODE, true>;  m[FastKey<T>(512, VAR_R2X, MODE + GEN_BIT)] = e;
+    FastEntry<T> e{ nullptr, H, (size_t)H * 16 * sizeof(cplx_t<T>), 1, 8, { R0, R1, 1 } };
+#define CPC_R2X(MODE)                                                                            \
+    e.kern = fft_r2x_kernel<T, H, R0, R1, MODE, false>; m[FastKey<T>(2 * H, VAR_R2X, MODE)] = e;           \
+    e.kern = fft_r2x_kernel<T, H, R0, R1, MODE, true>;  m[FastKey<T>(2 * H, VAR_R2X, MODE + GEN_BIT)] = e;
     CPC_R2X(MODE_FWD)
     CPC_R2X(MODE_INV)
     CPC_R2X(MODE_FUSED_SEP)
@@ -142,7 +142,8 @@ template <> struct FastRegistry<double> {
         register_modes<double, VAR_WIDE,    512,  8,  8,  8,  8,  8,  1, 2, 1>(m);
         register_modes<double, VAR_WIDE,   1024, 16,  8,  8, 16,  8,  1, 1>(m);
         register_modes<double, VAR_WIDE2,   512,  8,  8,  8, 16,  8,  1, 2>(m);
-        register_r2x512<double>(m);
+        register_r2x<double, 256, 16, 16>(m);
+        register_r2x<double, 128, 16, 8>(m);
         register_r2x512_line<double>(m);
         register_line256<double>(m);
         register_modes<double, VAR_WIDE2,   256,  8,  8,  4,  8,  8,  2, 2>(m);      // 512 thr, 64 regs
@@ -444,9 +445,9 @@ template <typename T> struct PlanT : PlanBase {
             // the fused pass does two transforms per tile and is LSU / issue bound: 512 = 2 x (16 x 16) with a register
             // radix-2 level and one shared-memory exchange per transform (fft_r2x.cuh) measured 1.23 ms at 512^3, the
             // 8.8.8 kernel with two butterflies per thread 1.31 ms, with one butterfly per thread 1.98 ms
-            if (a == 2 && n[a] == 512) {
+            if (a == 2 && (n[a] == 512 || n[a] == 256)) {
                 if (sizeof(T) == 8 && reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FUSED_SEP)) != reg.end()) var = VAR_R2X;
-                else if (reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
+                else if (n[a] == 512 && reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
             }
             // contiguous 512-point x lines: one warp per line, no block barrier (0.62 vs 0.69 ms at 512^3)
             if (a == 0 && nc == 1 && !real && n[a] == 512 && !getenv("CPC_VARIANT_X") &&
@@ -454,10 +455,11 @@ template <typename T> struct PlanT : PlanBase {
             // the 2 x (16 x 16) kernel also for the plain y passes of 512-point lines: 0.64 ms against 0.70 ms (8.8.8)
             // (single-rank only: in the chunked multi-rank layout its paired loads k / k+256 sit exactly one chunk,
             // a large power of two, apart and collide in the L2 / DRAM address hash: 0.57 vs 0.35 ms per half slab)
-            if (a == 1 && n[a] == 512 && sizeof(T) == 8 && desc.nranks == 1 &&
-                reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FWD)) != reg.end()) var = VAR_R2X;
-            // 256-point y lines: radix 8.8.4 with 8 points per thread and 4 small CTAs per SM (0.090 vs 0.108 ms at 256^3)
+            // 256-point y lines otherwise: radix 8.8.4 with 8 points per thread and 4 small CTAs per SM (0.090 vs 0.108 ms
+            // at 256^3; the 2 x (16 x 8) kernel: 0.086 ms)
             if (a == 1 && n[a] == 256 && reg.find(FastKey<T>(n[a], VAR_SMALL, MODE_FWD)) != reg.end()) var = VAR_SMALL;
+            if (a == 1 && (n[a] == 512 || n[a] == 256) && sizeof(T) == 8 && desc.nranks == 1 &&
+                reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FWD)) != reg.end()) var = VAR_R2X;
             {
                 const char *names[3] = { "CPC_VARIANT_X", "CPC_VARIANT_Y", "CPC_VARIANT_Z" };
                 const char *ov = getenv(names[a]);
