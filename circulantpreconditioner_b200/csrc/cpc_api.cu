@@ -165,9 +165,20 @@ int cpc_get_diag(cpc_plan plan, void *diag, int mem_kind)
     return plan->impl->get_diag(diag, mem_kind);
 }
 
+// device arrays are accessed with 16-byte vector loads / stores (complex128; two complex64, two float64, four float32)
+static int check_alignment(const void *a, const void *b, int mem_kind, const char *who)
+{
+    if (mem_kind == CPC_MEM_DEVICE && ((((uintptr_t)a) | ((uintptr_t)b)) & 15u) != 0) {
+        set_error("%s: device pointers must be 16-byte aligned", who);
+        return CPC_ERR_ARG;
+    }
+    return CPC_OK;
+}
+
 int cpc_apply(cpc_plan plan, const void *b, void *x, int mem_kind)
 {
     CHECK_PLAN(plan);
+    if (int rc = check_alignment(b, x, mem_kind, "cpc_apply")) return rc;
     return plan->impl->apply(b, x, mem_kind, nullptr, nullptr);
 }
 
@@ -175,18 +186,21 @@ int cpc_apply_profiled(cpc_plan plan, const void *b, void *x, float *pass_ms, in
 {
     CHECK_PLAN(plan);
     if (!pass_ms || !npasses) { set_error("null output"); return CPC_ERR_ARG; }
+    if (int rc = check_alignment(b, x, CPC_MEM_DEVICE, "cpc_apply_profiled")) return rc;
     return plan->impl->apply(b, x, CPC_MEM_DEVICE, pass_ms, npasses);
 }
 
 int cpc_forward(cpc_plan plan, const void *in, void *out, int mem_kind)
 {
     CHECK_PLAN(plan);
+    if (int rc = check_alignment(in, out, mem_kind, "cpc_forward")) return rc;
     return plan->impl->transform(in, out, mem_kind, -1);
 }
 
 int cpc_inverse(cpc_plan plan, const void *in, void *out, int mem_kind)
 {
     CHECK_PLAN(plan);
+    if (int rc = check_alignment(in, out, mem_kind, "cpc_inverse")) return rc;
     return plan->impl->transform(in, out, mem_kind, +1);
 }
 
@@ -203,6 +217,7 @@ int cpc_apply_projected(cpc_plan plan, const void *b, void *x, int mem_kind)
     CHECK_PLAN(plan);
     if (!b || !x) { set_error("cpc_apply_projected: null pointer"); return CPC_ERR_ARG; }
     if (mem_kind != CPC_MEM_DEVICE && mem_kind != CPC_MEM_HOST) { set_error("bad mem_kind %d", mem_kind); return CPC_ERR_ARG; }
+    if (int rc = check_alignment(b, x, mem_kind, "cpc_apply_projected")) return rc;
     CPC_CUDA(cudaSetDevice(plan->impl->device));
     return plan->impl->apply_projected(b, x, mem_kind);
 }

@@ -233,6 +233,12 @@ def test_error_behaviour_on_device():
     with cpc.CirculantPlan(16, 16, 16, ncomp=4) as p:
         with pytest.raises(cpc.CpcError):
             p.set_symbol_transport(1, 1, 1)
+    with cpc.CirculantPlan(16, 16, 16, dtype="c64") as p:
+        p.set_symbol_transport(1, 1, 1)
+        buf = torch.zeros(16 ** 3 + 1, dtype=torch.complex64, device="cuda")
+        with pytest.raises(cpc.CpcError) as e:
+            p.apply(buf[1:], buf[1:])                # 8-byte aligned only: rejected, not a misaligned-address fault
+        assert e.value.status == 1
 
 
 # ----------------------------------------------------------------------------------------------------
