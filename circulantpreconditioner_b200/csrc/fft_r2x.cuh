@@ -111,6 +111,9 @@ fft_r2x_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, co
     line_fft<T, H, R0, R1, 1, 16, +1, 16, false, 0>(u, j, ls, sm, tw, 0);       // u[m] = y_s[j + TP m]
 
     // ---- swap back and radix-2 level (decimation in time) ----------------------------------------------------------
+    C rn[8];                                                         // the eight roots first: one latency, not eight
+#pragma unroll
+    for (int i = 0; i < 8; ++i) rn[i] = __ldg(&rt[j + TP * (8 * s + i)]);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const C send = s ? u[i] : u[i + 8];                          // s = 0 gives away yA[8+i], s = 1 gives away yB[i]
@@ -118,7 +121,7 @@ fft_r2x_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, co
         const C ya = s ? recv : u[i];
         const C yb = s ? u[i + 8] : recv;
         const int n = j + TP * (8 * s + i);
-        const C tt = cmulc(yb, __ldg(&rt[n]));                       // conj(W^n) yB[n]
+        const C tt = cmulc(yb, rn[i]);                               // conj(W^n) yB[n]
         const C x0 = cadd(ya, tt), x1 = csub(ya, tt);
         if (active) {
             if (!GEN) {
