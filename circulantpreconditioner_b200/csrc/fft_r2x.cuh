@@ -28,23 +28,26 @@ template <typename C> __device__ __forceinline__ C shfl_xor_c(C v, int mask)
 // N = 2 H points per line, H = R0 * R1 (two radix stages, 16 points per thread): 512 = 2 x (16 x 16) and
 // 256 = 2 x (16 x 8).  The half-line transform is the generic Stockham code of fft_pass.cuh run with the 16 "lanes"
 // (s, l): shared memory [point][s][l], so the 8 lanes of a quarter warp still hit one 128-byte row.
-template <typename T, int H, int R0, int R1, int MODE, bool GEN>
-__global__ void __launch_bounds__(H, 512 / H)
+template <typename T, int H, int R0, int R1, int MODE, bool GEN, int TX = 128 / (int)sizeof(cplx_t<T>)>
+__global__ void __launch_bounds__(H * TX / 8, (TX == 16 ? 8192 : 4096) / (H * TX))
 fft_r2x_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
                const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
 {
     using C = cplx_t<T>;
-    constexpr int TX = 8;
+    // TX lanes x sizeof(C) = one 128-byte row: 8 lanes for complex128, 16 for complex64 (the partner lane of the
+    // radix-2 swap is TX lanes away, still inside the warp)
+    static_assert(TX == 8 || TX == 16, "TX must be 8 or 16");
+    constexpr int LTX = TX == 8 ? 3 : 4;
     constexpr int TP = H / 16;            // threads per half-line = stride between a thread's points
     static_assert(R0 * R1 == H && 16 % R0 == 0 && 16 % R1 == 0, "half-line must be two radix stages of 16 points per thread");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *sm = reinterpret_cast<C *>(smem_raw);
 
     const int tid = threadIdx.x;
-    const int l = tid & 7;
-    const int s = (tid >> 3) & 1;
-    const int j = tid >> 4;               // in [0, TP)
-    const int ls = s * 8 + l;             // the (s, l) "lane" of the half-line transform
+    const int l = tid & (TX - 1);
+    const int s = (tid >> LTX) & 1;
+    const int j = tid >> (LTX + 1);       // in [0, TP)
+    const int ls = s * TX + l;            // the (s, l) "lane" of the half-line transform
 
     const int t = blockIdx.x;
     const int ti = t % g.tiles_inner, to = t / g.tiles_inner;
@@ -86,11 +89,11 @@ fft_r2x_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, co
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const C send = s ? a[i] : b[i];
-            const C recv = shfl_xor_c(send, 8);
+            const C recv = shfl_xor_c(send, TX);
             u[i] = s ? recv : a[i];
             u[i + 8] = s ? b[i] : recv;
         }
-        line_fft<T, H, R0, R1, 1, 16, D1, 16, false, 0>(u, j, ls, sm, tw, 0);   // u[m] = X[2 (j + TP m) + s]
+        line_fft<T, H, R0, R1, 1, 16, D1, 2 * TX, false, 0>(u, j, ls, sm, tw, 0);   // u[m] = X[2 (j + TP m) + s]
     }
 
     if (MODE == MODE_FWD || MODE == MODE_INV) {
@@ -108,7 +111,7 @@ fft_r2x_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, co
     apply_symbol<T, 16, MODE>(u, 2 * j + s, 2 * TP, active ? w : 0, gbase, g.SI, g, sym);
     __syncthreads();                                                 // shared memory is reused by the backward transform
 
-    line_fft<T, H, R0, R1, 1, 16, +1, 16, false, 0>(u, j, ls, sm, tw, 0);       // u[m] = y_s[j + TP m]
+    line_fft<T, H, R0, R1, 1, 16, +1, 2 * TX, false, 0>(u, j, ls, sm, tw, 0);       // u[m] = y_s[j + TP m]
 
     // ---- swap back and radix-2 level (decimation in time) ----------------------------------------------------------
     C rn[8];                                                         // the eight roots first: one latency, not eight
@@ -117,7 +120,7 @@ fft_r2x_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, co
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const C send = s ? u[i] : u[i + 8];                          // s = 0 gives away yA[8+i], s = 1 gives away yB[i]
-        const C recv = shfl_xor_c(send, 8);
+        const C recv = shfl_xor_c(send, TX);
         const C ya = s ? recv : u[i];
         const C yb = s ? u[i + 8] : recv;
         const int n = j + TP * (8 * s + i);

@@ -94,7 +94,8 @@ static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
 // strided lines of 2 H points as 2 x (R0 x R1) (fft_r2x.cuh)
 template <typename T, int H, int R0, int R1> static void register_r2x(std::map<FastKey<T>, FastEntry<T>> &m)
 {
-    FastEntry<T> e{ nullptr, H, (size_t)H * 16 * sizeof(cplx_t<T>), 1, 8, { R0, R1, 1 } };
+    constexpr int TX = 128 / (int)sizeof(cplx_t<T>);      // 8 lanes (complex128) or 16 (complex64) = one 128-byte row
+    FastEntry<T> e{ nullptr, H * TX / 8, (size_t)H * 2 * TX * sizeof(cplx_t<T>), 1, TX, { R0, R1, 1 } };
 #define CPC_R2X(MODE)                                                                            \
     e.kern = fft_r2x_kernel<T, H, R0, R1, MODE, false>; m[FastKey<T>(2 * H, VAR_R2X, MODE)] = e;           \
     e.kern = fft_r2x_kernel<T, H, R0, R1, MODE, true>;  m[FastKey<T>(2 * H, VAR_R2X, MODE + GEN_BIT)] = e;
@@ -181,6 +182,8 @@ template <> struct FastRegistry<float> {
         register_modes<float, VAR_WIDE,    512, 16,  8,  4, 16, 16,  1, 2>(m);
         register_modes<float, VAR_WIDE,   1024, 16,  8,  8, 16, 16,  1, 1>(m);
         register_r2x512_line<float>(m);
+        register_r2x<float, 256, 16, 16>(m);
+        register_r2x<float, 128, 16, 8>(m);
         register_line256<float>(m);
         register_modes<float, VAR_NARROW,   16, 16,  1,  1, 16,  4, 32, 2>(m);
         register_modes<float, VAR_NARROW,   32,  8,  4,  1,  8,  4, 16, 2>(m);
@@ -446,7 +449,7 @@ template <typename T> struct PlanT : PlanBase {
             // radix-2 level and one shared-memory exchange per transform (fft_r2x.cuh) measured 1.23 ms at 512^3, the
             // 8.8.8 kernel with two butterflies per thread 1.31 ms, with one butterfly per thread 1.98 ms
             if (a == 2 && (n[a] == 512 || n[a] == 256)) {
-                if (sizeof(T) == 8 && reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FUSED_SEP)) != reg.end()) var = VAR_R2X;
+                if (reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FUSED_SEP)) != reg.end()) var = VAR_R2X;
                 else if (n[a] == 512 && reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
             }
             // contiguous 512-point x lines: one warp per line, no block barrier (0.62 vs 0.69 ms at 512^3)
@@ -458,7 +461,7 @@ template <typename T> struct PlanT : PlanBase {
             // 256-point y lines otherwise: radix 8.8.4 with 8 points per thread and 4 small CTAs per SM (0.090 vs 0.108 ms
             // at 256^3; the 2 x (16 x 8) kernel: 0.086 ms)
             if (a == 1 && n[a] == 256 && reg.find(FastKey<T>(n[a], VAR_SMALL, MODE_FWD)) != reg.end()) var = VAR_SMALL;
-            if (a == 1 && (n[a] == 512 || n[a] == 256) && sizeof(T) == 8 && desc.nranks == 1 &&
+            if (a == 1 && (n[a] == 512 || n[a] == 256) && desc.nranks == 1 &&
                 reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FWD)) != reg.end()) var = VAR_R2X;
             {
                 const char *names[3] = { "CPC_VARIANT_X", "CPC_VARIANT_Y", "CPC_VARIANT_Z" };

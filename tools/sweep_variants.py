@@ -12,14 +12,15 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 combos = [tuple(int(c) for c in a.split(",")) for a in sys.argv[2:]] or [(2, 0, 0), (1, 3, 3), (2, 4, 4), (2, 5, 5), (2, 6, 6), (2, 7, 7)]
 combos = [c if len(c) == 4 else c + (0,) for c in combos]
 NC = int(os.environ.get("NCOMP", "1"))
-b = torch.randn(NC * n ** 3, dtype=torch.float64, device="cuda").to(torch.complex128)
+DT = os.environ.get("DTYPE", "c128")
+b = torch.randn(NC * n ** 3, dtype=torch.float64, device="cuda").to(torch.complex128 if DT == "c128" else torch.complex64)
 x = torch.empty_like(b)
 ref = None
 for vx, vy, vz, pf in combos:
     os.environ["CPC_VARIANT_X"], os.environ["CPC_VARIANT_Y"], os.environ["CPC_VARIANT_Z"] = str(vx), str(vy), str(vz)
     os.environ["CPC_PREFETCH_WAVES"] = str(pf)
     try:
-        with cpc.CirculantPlan(n, n, n, ncomp=NC) as p:
+        with cpc.CirculantPlan(n, n, n, ncomp=NC, dtype=DT) as p:
             if NC == 4:
                 p.set_symbol_wave(700.0, 0.0793651, 0.0793651, 0.0793651)
             else:
