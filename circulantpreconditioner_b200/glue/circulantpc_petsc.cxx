@@ -36,6 +36,53 @@ PetscErrorCode build_transport_col(Vec c, PetscInt size)
     PetscFunctionReturn(PETSC_SUCCESS);
 }
 
+// reference FftLinearSolver_3D.c:92-112: res = (1_{id_size} (x) lambda c), i.e. res[j*c_size + i] = lambda*c[i]
+// ("tile").  Kept for callers that assemble Diag by hand; build_diag_mat_vec_3D below does not need it.
+// One pass over the arrays instead of the reference's c_size*id_size VecSetValue calls.
+PetscErrorCode vec_kronecker_product_identity_left(Vec c, Vec res, PetscInt c_size, PetscInt id_size, PetscScalar lambda)
+{
+    PetscFunctionBeginUser;
+    PetscInt sc, sr;
+    PetscCall(VecGetSize(c, &sc));
+    PetscCall(VecGetSize(res, &sr));
+    PetscCheck(sc == c_size && sr == c_size * id_size, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
+               "vec_kronecker_product_identity_left: c has %d entries, res %d, expected %d and %d", sc, sr, c_size,
+               c_size * id_size);
+    const PetscScalar *cc;
+    PetscScalar *rr;
+    PetscCall(VecGetArrayRead(c, &cc));
+    PetscCall(VecGetArray(res, &rr));
+    for (PetscInt j = 0; j < id_size; ++j)
+        for (PetscInt i = 0; i < c_size; ++i) rr[(size_t)j * c_size + i] = lambda * cc[i];
+    PetscCall(VecRestoreArray(res, &rr));
+    PetscCall(VecRestoreArrayRead(c, &cc));
+    PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+// reference FftLinearSolver_3D.c:114-134: res = (lambda c (x) 1_{id_size}), i.e. res[i*id_size + j] = lambda*c[i]
+// ("repeat").
+PetscErrorCode vec_kronecker_product_identity_right(Vec c, Vec res, PetscInt c_size, PetscInt id_size, PetscScalar lambda)
+{
+    PetscFunctionBeginUser;
+    PetscInt sc, sr;
+    PetscCall(VecGetSize(c, &sc));
+    PetscCall(VecGetSize(res, &sr));
+    PetscCheck(sc == c_size && sr == c_size * id_size, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
+               "vec_kronecker_product_identity_right: c has %d entries, res %d, expected %d and %d", sc, sr, c_size,
+               c_size * id_size);
+    const PetscScalar *cc;
+    PetscScalar *rr;
+    PetscCall(VecGetArrayRead(c, &cc));
+    PetscCall(VecGetArray(res, &rr));
+    for (PetscInt i = 0; i < c_size; ++i) {
+        const PetscScalar v = lambda * cc[i];
+        for (PetscInt j = 0; j < id_size; ++j) rr[(size_t)i * id_size + j] = v;
+    }
+    PetscCall(VecRestoreArray(res, &rr));
+    PetscCall(VecRestoreArrayRead(c, &cc));
+    PetscFunctionReturn(PETSC_SUCCESS);
+}
+
 // reference FftLinearSolver_3D.c:136-164: Diag[k,j,i] = 1 + lx cx[i] + ly cy[j] + lz cz[k].
 // The three 1-D tables go to the GPU (cpc_set_symbol_separable) and the N eigenvalues are produced there
 // (cpc_get_diag) -- no per-element VecSetValue loops (reference :92-134 does 3N of them).

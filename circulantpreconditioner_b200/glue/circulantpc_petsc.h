@@ -41,6 +41,8 @@ struct StructuredTransportContext {
 
 /* ---- eigenvalue set-up (reference FftLinearSolver_3D.c:80-164) ---- */
 PetscErrorCode build_transport_col(Vec c, PetscInt size);
+PetscErrorCode vec_kronecker_product_identity_left(Vec c, Vec res, PetscInt c_size, PetscInt id_size, PetscScalar lambda);
+PetscErrorCode vec_kronecker_product_identity_right(Vec c, Vec res, PetscInt c_size, PetscInt id_size, PetscScalar lambda);
 PetscErrorCode build_diag_mat_vec_3D(Vec Diag, Vec c_x_hat, Vec c_y_hat, Vec c_z_hat, PetscInt n_x, PetscInt n_y,
                                      PetscInt n_z, PetscScalar lambda_x, PetscScalar lambda_y, PetscScalar lambda_z);
 

@@ -4,6 +4,7 @@
 //   matrix-free; Fft{1,2,3}DTransportSolver must return X_ref; residual and error <= 1e-12.
 // Also drives the PCShell life cycle the way KSP would (PCSetUp once, PCApply many times, PCDestroy).
 // Needs a GPU (there is no CPU fallback); run by tests/test_glue.py under -m gpu.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <vector>
@@ -102,6 +103,24 @@ static int explicit_diag_case()
     // Lambda[0..5]
     const PetscScalar want[6] = { { 1, 0 }, { 2, 1 }, { 3, 0 }, { 2, -1 }, { 2.5, 0.8660254037844386 }, { 3.5, 1.8660254037844386 } };
     for (int m = 0; m < 6; ++m) EXPECT(std::abs(Diag->array[m] - want[m]) < 1e-14, "Diag[%d] = (%g,%g)", m, Diag->array[m].real(), Diag->array[m].imag());
+    {
+        // the reference's assembly (FftLinearSolver_3D.c:146-157) with the Kronecker helpers gives the same Diag
+        Vec kx, kyi, ky, kz;
+        CHK(VecCreateSeq(PETSC_COMM_WORLD, N, &kx));
+        CHK(VecCreateSeq(PETSC_COMM_WORLD, ny * nz, &kyi));
+        CHK(VecCreateSeq(PETSC_COMM_WORLD, N, &ky));
+        CHK(VecCreateSeq(PETSC_COMM_WORLD, N, &kz));
+        CHK(vec_kronecker_product_identity_left(ch[0], kx, nx, ny * nz, 1.0));
+        CHK(vec_kronecker_product_identity_left(ch[1], kyi, ny, nz, 1.0));
+        CHK(vec_kronecker_product_identity_right(kyi, ky, ny * nz, nx, 1.0));
+        CHK(vec_kronecker_product_identity_right(ch[2], kz, nz, nx * ny, 1.0));
+        double worst = 0;
+        for (int m = 0; m < N; ++m)
+            worst = std::max(worst, std::abs(Diag->array[m] - (1.0 + kx->array[m] + ky->array[m] + kz->array[m])));
+        EXPECT(worst < 1e-14, "Kronecker assembly differs from build_diag_mat_vec_3D by %g", worst);
+        EXPECT(vec_kronecker_product_identity_left(ch[0], kyi, nx, ny * nz, 1.0) == PETSC_ERR_ARG_WRONG, "kron size check");
+        CHK(VecDestroy(&kx)); CHK(VecDestroy(&kyi)); CHK(VecDestroy(&ky)); CHK(VecDestroy(&kz));
+    }
     std::vector<PetscScalar> xref(N), b;
     for (int m = 0; m < N; ++m) xref[m] = (double)m * m * m;
     apply_C(xref, b, nx, ny, nz, 1, 1, 1);

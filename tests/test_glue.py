@@ -17,7 +17,8 @@ from tests.conftest import GOLDEN, ROOT, rel_l2
 GLUE = os.path.join(ROOT, "circulantpreconditioner_b200", "glue")
 LIB = os.path.join(GLUE, "libfftpreconditioner_b200.so")
 
-C_NAMES = ["build_transport_col", "build_diag_mat_vec_3D", "solve_3D", "Fft3DSolver", "FftTransportSolver",
+C_NAMES = ["build_transport_col", "vec_kronecker_product_identity_left", "vec_kronecker_product_identity_right",
+           "build_diag_mat_vec_3D", "solve_3D", "Fft3DSolver", "FftTransportSolver",
            "Fft3DTransportSolver", "Fft2DTransportSolver", "Fft1DTransportSolver", "PetscFft3DTransportSolver",
            "PCShellFFT3DAttach", "getFFTPrec3DContextCreate"]
 CXX_NAMES = ["applyFFT3DPrecTransport", "setupFFTPrec3D", "destroyFFTPrec3D", "getFFTPrec3DContext"]
