@@ -17,10 +17,10 @@ template <> struct cplx_of<float> { using type = float2; };
 template <typename T> using cplx_t = typename cplx_of<T>::type;
 
 template <typename T> __host__ __device__ __forceinline__ cplx_t<T> mk(T a, T b) { cplx_t<T> r; r.x = a; r.y = b; return r; }
-template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
-template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C> __host__ __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __host__ __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
 // a * b
-template <typename C> __device__ __forceinline__ C cmul(C a, C b)
+template <typename C> __host__ __device__ __forceinline__ C cmul(C a, C b)
 {
     C r;
     r.x = a.x * b.x - a.y * b.y;
@@ -28,7 +28,7 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b)
     return r;
 }
 // a * conj(b)
-template <typename C> __device__ __forceinline__ C cmulc(C a, C b)
+template <typename C> __host__ __device__ __forceinline__ C cmulc(C a, C b)
 {
     C r;
     r.x = a.x * b.x + a.y * b.y;
@@ -36,12 +36,12 @@ template <typename C> __device__ __forceinline__ C cmulc(C a, C b)
     return r;
 }
 // multiply by the table root w = exp(-2 pi i e / n): forward uses w, backward uses conj(w)
-template <int DIR, typename C> __device__ __forceinline__ C twmul(C a, C w)
+template <int DIR, typename C> __host__ __device__ __forceinline__ C twmul(C a, C w)
 {
     return DIR < 0 ? cmul(a, w) : cmulc(a, w);
 }
 // multiply by DIR * i  (forward: -i, backward: +i)
-template <int DIR, typename C> __device__ __forceinline__ C mul_dir_i(C a)
+template <int DIR, typename C> __host__ __device__ __forceinline__ C mul_dir_i(C a)
 {
     C r;
     if (DIR < 0) { r.x = a.y; r.y = -a.x; }
@@ -52,11 +52,11 @@ template <int DIR, typename C> __device__ __forceinline__ C mul_dir_i(C a)
 template <int R, int DIR, typename C> struct Butterfly;
 
 template <int DIR, typename C> struct Butterfly<1, DIR, C> {
-    __device__ __forceinline__ static void run(C *) {}
+    __host__ __device__ __forceinline__ static void run(C *) {}
 };
 
 template <int DIR, typename C> struct Butterfly<2, DIR, C> {
-    __device__ __forceinline__ static void run(C *u)
+    __host__ __device__ __forceinline__ static void run(C *u)
     {
         C a = u[0], b = u[1];
         u[0] = cadd(a, b);
@@ -65,7 +65,7 @@ template <int DIR, typename C> struct Butterfly<2, DIR, C> {
 };
 
 template <int DIR, typename C> struct Butterfly<4, DIR, C> {
-    __device__ __forceinline__ static void run(C *u)
+    __host__ __device__ __forceinline__ static void run(C *u)
     {
         C t0 = cadd(u[0], u[2]), t1 = csub(u[0], u[2]);
         C t2 = cadd(u[1], u[3]), t3 = mul_dir_i<DIR>(csub(u[1], u[3]));
@@ -77,7 +77,7 @@ template <int DIR, typename C> struct Butterfly<4, DIR, C> {
 };
 
 template <int DIR, typename C> struct Butterfly<8, DIR, C> {
-    __device__ __forceinline__ static void run(C *u)
+    __host__ __device__ __forceinline__ static void run(C *u)
     {
         using T = decltype(u[0].x);
         const T h = (T)0.70710678118654752440084436210484903928;
@@ -106,9 +106,60 @@ template <int DIR, typename C> struct Butterfly<8, DIR, C> {
     }
 };
 
+// Odd-radix butterflies for line lengths 2^a * 3 (96, 192, 384, 768).  Radix 6 = 2 x 3 and radix 12 = 3 x 4 use the
+// prime-factor (Good-Thomas) index maps, so there are no internal twiddles.
+template <int DIR, typename C> struct Butterfly<3, DIR, C> {
+    __host__ __device__ __forceinline__ static void run(C *u)
+    {
+        using T = decltype(u[0].x);
+        const T s = (T)0.86602540378443864676372317075293618347;      // sin(2 pi / 3)
+        const C t1 = cadd(u[1], u[2]);
+        const C d = mul_dir_i<DIR>(csub(u[1], u[2]));                  // DIR i (x1 - x2)
+        C t2;
+        t2.x = fma((T)-0.5, t1.x, u[0].x);
+        t2.y = fma((T)-0.5, t1.y, u[0].y);
+        u[0] = cadd(u[0], t1);
+        u[1].x = fma(s, d.x, t2.x);  u[1].y = fma(s, d.y, t2.y);
+        u[2].x = fma(-s, d.x, t2.x); u[2].y = fma(-s, d.y, t2.y);
+    }
+};
+
+// n = (3 n1 + 2 n2) mod 6, k = (3 k1 + 4 k2) mod 6
+template <int DIR, typename C> struct Butterfly<6, DIR, C> {
+    __host__ __device__ __forceinline__ static void run(C *u)
+    {
+        C a[3] = { cadd(u[0], u[3]), cadd(u[2], u[5]), cadd(u[4], u[1]) };
+        C b[3] = { csub(u[0], u[3]), csub(u[2], u[5]), csub(u[4], u[1]) };
+        Butterfly<3, DIR, C>::run(a);
+        Butterfly<3, DIR, C>::run(b);
+        u[0] = a[0]; u[4] = a[1]; u[2] = a[2];
+        u[3] = b[0]; u[1] = b[1]; u[5] = b[2];
+    }
+};
+
+// n = (4 n1 + 3 n2) mod 12, k = (4 k1 + 9 k2) mod 12
+template <int DIR, typename C> struct Butterfly<12, DIR, C> {
+    __host__ __device__ __forceinline__ static void run(C *u)
+    {
+        C s0[4] = { u[0], u[3], u[6], u[9] };
+        C s1[4] = { u[4], u[7], u[10], u[1] };
+        C s2[4] = { u[8], u[11], u[2], u[5] };
+        Butterfly<4, DIR, C>::run(s0);
+        Butterfly<4, DIR, C>::run(s1);
+        Butterfly<4, DIR, C>::run(s2);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+            C t[3] = { s0[k2], s1[k2], s2[k2] };
+            Butterfly<3, DIR, C>::run(t);
+#pragma unroll
+            for (int k1 = 0; k1 < 3; ++k1) u[(4 * k1 + 9 * k2) % 12] = t[k1];
+        }
+    }
+};
+
 // plus = a + w' b, minus = a - w' b with w' = w (forward) or conj(w) (backward): 6 FMAs instead of a complex
 // multiply (4) plus an add and a subtract (4).  minus = 2a - plus.
-template <int DIR, typename C> __device__ __forceinline__ void cfma_pm(C a, C w, C b, C &plus, C &minus)
+template <int DIR, typename C> __host__ __device__ __forceinline__ void cfma_pm(C a, C w, C b, C &plus, C &minus)
 {
     using T = decltype(a.x);
     const T wy = DIR < 0 ? w.y : -w.y;
@@ -120,7 +171,7 @@ template <int DIR, typename C> __device__ __forceinline__ void cfma_pm(C a, C w,
 
 // Radix-8 butterfly of the twiddled inputs u[r] * w[r-1] (r = 1..7): the twiddles are folded into the first add /
 // subtract level (36 instead of 44 fp64 instructions for that level).
-template <int DIR, typename C> __device__ __forceinline__ void butterfly8_twiddled(C *u, const C *w)
+template <int DIR, typename C> __host__ __device__ __forceinline__ void butterfly8_twiddled(C *u, const C *w)
 {
     using T = decltype(u[0].x);
     const T h = (T)0.70710678118654752440084436210484903928;
@@ -151,7 +202,7 @@ template <int DIR, typename C> __device__ __forceinline__ void butterfly8_twiddl
 }
 
 template <int DIR, typename C> struct Butterfly<16, DIR, C> {
-    __device__ __forceinline__ static void run(C *u)
+    __host__ __device__ __forceinline__ static void run(C *u)
     {
         using T = decltype(u[0].x);
         const T c1 = (T)0.92387953251128675612818318939678828682;  // cos(pi/8)

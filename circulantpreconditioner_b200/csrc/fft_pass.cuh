@@ -143,6 +143,7 @@ __device__ __forceinline__ void stockham_stage(cplx_t<T> (&v)[E], int j, int l, 
     using C = cplx_t<T>;
     constexpr int TPL = N / E;
     constexpr int NB = E / R;          // butterflies per thread in this stage
+    static_assert(R == 1 || (P & (P - 1)) == 0, "an odd radix must be the last one: k = jb mod P is computed with a mask");
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int jb = j + b * TPL;
@@ -376,7 +377,7 @@ fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, c
         for (int m = 0; m < E; ++m) {
             const int k = j + TPL * m;
             const C a = v[m];
-            const C bq = sm[sm_index<N, TXG, PS, XMAP>((N - k) & (N - 1), lg)];
+            const C bq = sm[sm_index<N, TXG, PS, XMAP>(k == 0 ? 0 : N - k, lg)];
             const C ev = mk<T>((T)0.5 * (a.x + bq.x), (T)0.5 * (a.y - bq.y));
             const C od = mk<T>((T)0.5 * (a.y + bq.y), (T)-0.5 * (a.x - bq.x));       // -i (a - conj b) / 2
             const C wk = sym.rx[k];                                                   // exp(-2 pi i k / (2N))

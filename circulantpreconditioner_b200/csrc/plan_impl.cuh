@@ -45,7 +45,8 @@ enum Variant {
     VAR_SMALL = 4,    // as VAR_WIDE with small CTAs, 4 per SM (256-point y lines)
     VAR_R2X = 5,      // 512 = 2 x (16 x 16): radix-2 level in registers + warp shuffle, one shared-memory exchange
     VAR_XR2X = 6,     // the same for contiguous lines: one warp per line, no block barrier (scalar x pass)
-    VAR_COUNT = 7
+    VAR_SLIM = 7,     // strided lines, TX = 4 and one line group per CTA: 64 KB tiles for 1024-point lines, 2 CTAs per SM
+    VAR_COUNT = 8
 };
 
 template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, variant, mode + 16 * general-addressing)
@@ -158,6 +159,22 @@ template <> struct FastRegistry<double> {
         register_modes<double, VAR_NARROW,  512,  8,  8,  8,  8,  4,  2, 2, 1>(m);
         register_modes<double, VAR_NARROW, 1024, 16,  8,  8, 16,  4,  2, 1>(m);
         register_modes<double, VAR_NARROW, 2048, 16, 16,  8, 16,  4,  1, 1>(m);
+        register_modes<double, VAR_SLIM,   1024, 16,  8,  8, 16,  4,  1, 2>(m);
+        // line lengths 2^a * 3 (radix 6 / 12 last, prime-factor butterflies): 24 points per thread need 96 data registers
+        // in fp64, so these run 3 small CTAs per SM at <= 168 registers; single-rank builds only
+        register_modes_gen<double, VAR_WIDE,     48,  4, 12,  1, 12,  8,  8, 2, 2, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,     96,  4,  4,  6, 12,  8,  4, 2, 2, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,    192,  8,  4,  6, 24,  8,  2, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,    384,  8,  8,  6, 24,  8,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,    768,  8,  8, 12, 24,  4,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_NARROW,   96,  4,  4,  6, 12,  4,  8, 2, 2, false, 1>(m);
+        register_modes_gen<double, VAR_NARROW,  192,  8,  4,  6, 24,  4,  4, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_NARROW,  384,  8,  8,  6, 24,  4,  2, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,     48,  4, 12,  1, 12, 64,  1, 2, 2, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,     96,  4,  4,  6, 12, 32,  1, 2, 2, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    192,  8,  4,  6, 24, 16,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    384,  8,  8,  6, 24,  8,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    768,  8,  8, 12, 24,  4,  1, 3, 3, false, 1>(m);
         register_modes<double, VAR_XMAP,     16, 16,  1,  1, 16, 64,  1, 2>(m);
         register_modes<double, VAR_XMAP,     32,  8,  4,  1,  8, 64,  1, 2>(m);
         register_modes<double, VAR_XMAP,     64,  8,  8,  1,  8, 32,  1, 2>(m);
@@ -193,6 +210,19 @@ template <> struct FastRegistry<float> {
         register_modes<float, VAR_NARROW,  512,  8,  8,  8,  8,  4,  2, 2>(m);
         register_modes<float, VAR_NARROW, 1024, 16,  8,  8, 16,  4,  2, 1>(m);
         register_modes<float, VAR_NARROW, 2048, 16, 16,  8, 16,  4,  1, 1>(m);
+        register_modes_gen<float, VAR_WIDE,     48,  4, 12,  1, 12, 16,  4, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,     96,  4,  4,  6, 12, 16,  2, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    192,  8,  4,  6, 24, 16,  2, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    384,  8,  8,  6, 24, 16,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    768,  8,  8, 12, 24,  8,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_NARROW,   96,  4,  4,  6, 12,  4,  8, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_NARROW,  192,  8,  4,  6, 24,  4,  8, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_NARROW,  384,  8,  8,  6, 24,  4,  4, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,     48,  4, 12,  1, 12, 64,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,     96,  4,  4,  6, 12, 32,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    192,  8,  4,  6, 24, 32,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    384,  8,  8,  6, 24, 16,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    768,  8,  8, 12, 24,  8,  1, 2, 2, false, 1>(m);
         register_modes<float, VAR_XMAP,     16, 16,  1,  1, 16, 64,  1, 2>(m);
         register_modes<float, VAR_XMAP,     32,  8,  4,  1,  8, 64,  1, 2>(m);
         register_modes<float, VAR_XMAP,     64,  8,  8,  1,  8, 32,  1, 2>(m);
@@ -461,6 +491,10 @@ template <typename T> struct PlanT : PlanBase {
             // 256-point y lines otherwise: radix 8.8.4 with 8 points per thread and 4 small CTAs per SM (0.090 vs 0.108 ms
             // at 256^3; the 2 x (16 x 8) kernel: 0.086 ms)
             if (a == 1 && n[a] == 256 && reg.find(FastKey<T>(n[a], VAR_SMALL, MODE_FWD)) != reg.end()) var = VAR_SMALL;
+            // 1024-point y lines: 64 KB tiles (4 lanes) so that two CTAs share an SM: 7.1 vs 8.2 ms at 1024^3.  Not for z,
+            // whose 16 MB line stride makes 64-byte segments slower than the one-CTA 128-byte tiles (14.2 vs 13.3 ms)
+            if (a == 1 && n[a] == 1024 && desc.nranks == 1 && reg.find(FastKey<T>(n[a], VAR_SLIM, MODE_FWD)) != reg.end())
+                var = VAR_SLIM;
             if (a == 1 && (n[a] == 512 || n[a] == 256) && desc.nranks == 1 &&
                 reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FWD)) != reg.end()) var = VAR_R2X;
             {
@@ -506,6 +540,19 @@ template <typename T> struct PlanT : PlanBase {
                         ++p;
                         if ((long long)p * p > rem) p = rem;
                     }
+                }
+                // pairs of 2 become radix 4: same O(sum of factors) arithmetic, half the stages and barriers
+                {
+                    int twos = 0, w = 0, rest[CPC_MAX_FACTORS];
+                    for (int i = 0; i < c.fl.nfac; ++i) {
+                        if (c.fl.fac[i] == 2) ++twos;
+                        else rest[w++] = c.fl.fac[i];
+                    }
+                    int k = 0;
+                    for (; twos >= 2; twos -= 2) c.fl.fac[k++] = 4;
+                    if (twos) c.fl.fac[k++] = 2;
+                    for (int i = 0; i < w; ++i) c.fl.fac[k++] = rest[i];
+                    c.fl.nfac = k;
                 }
                 int gtx = (a == 0 && nc == 4) ? 4 : 8;
                 while (gtx > ((nc == 4) ? 4 : 1) && 2ull * n[a] * gtx * sizeof(C) > (size_t)dev_smem) gtx >>= 1;

@@ -103,7 +103,11 @@ SHAPES = [(16, 16, 16), (32, 64, 16), (64, 16, 128), (128, 32, 16), (256, 16, 32
           (64, 3, 5), (128, 5, 3), (512, 3, 1), (12, 64, 5), (3, 5, 256), (256, 7, 32),
           # 512-point y / z lines take the 2 x (16 x 16) kernel (its root table must be the transformed axis' own)
           (16, 512, 32), (8, 512, 512), (24, 512, 6),
-          (16, 1024, 8), (8, 4, 1024)]
+          (16, 1024, 8), (8, 4, 1024),
+          # 2^a * 3 line lengths: radix-6 / radix-12 last stage (prime-factor butterflies), fast kernels on every axis
+          (48, 96, 192), (384, 6, 48), (10, 768, 3), (5, 3, 384), (96, 768, 2), (192, 5, 96), (768, 2, 3),
+          # generic kernel: radix-4 grouping, odd primes (the reference's own 10 x 25 x 40 grid, testFftSolver_3D.py:82)
+          (10, 25, 40), (100, 10, 25), (250, 6, 7), (36, 45, 14)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -160,7 +164,8 @@ def test_general_first_column_and_diag_table():
 
 
 @pytest.mark.parametrize("shape", [(16, 16, 16), (32, 16, 64), (64, 32, 16), (6, 5, 4), (16, 16, 1), (128, 16, 32),
-                                   (32, 3, 16), (5, 16, 64), (256, 2, 3)])
+                                   (32, 3, 16), (5, 16, 64), (256, 2, 3), (96, 48, 6), (192, 3, 48), (384, 2, 3),
+                                   (10, 25, 12)])
 def test_wave_block_matches_oracle(shape):
     nx, ny, nz = shape
     rng = np.random.default_rng(17)
@@ -182,7 +187,8 @@ def test_wave_block_matches_oracle(shape):
     assert rel_l2(got.real, y) < 1e-11
 
 
-@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 128, 16), (512, 8, 16), (20, 12, 9)])
+@pytest.mark.parametrize("shape", [(32, 32, 32), (64, 128, 16), (512, 8, 16), (20, 12, 9), (96, 48, 192),
+                                   (384, 12, 768), (768, 3, 384), (100, 10, 25)])
 def test_fp32_option(shape):
     nx, ny, nz = shape
     rng = np.random.default_rng(23)
@@ -281,7 +287,8 @@ def test_roundtrip_and_linearity_at_baseline_sizes(n):
 # real-scalar plans (CPC_F64 / CPC_F32): r2c / c2r inside, half the bytes
 # ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(64, 32, 16), (512, 8, 16), (128, 64, 32), (256, 16, 1), (1024, 4, 2), (64, 1, 1),
-                                   (20, 12, 9), (30, 1, 17), (16, 16, 16)])
+                                   (20, 12, 9), (30, 1, 17), (16, 16, 16), (768, 6, 48), (384, 12, 5), (96, 4, 4),
+                                   (192, 4, 4), (100, 6, 4)])
 def test_real_scalar_plan_matches_oracle(shape):
     nx, ny, nz = shape
     rng = np.random.default_rng(nx + ny + nz)
