@@ -157,6 +157,59 @@ template <int DIR, typename C> struct Butterfly<12, DIR, C> {
     }
 };
 
+// Odd primes 5 and 7 (generic any-length kernel): with t_j = x_j + x_{R-j}, d_j = DIR i (x_j - x_{R-j}),
+//   X[q] = x_0 + sum_j cos(2 pi j q / R) t_j + sum_j sin(2 pi j q / R) d_j,   X[R-q] = the same with -sin.
+template <int R> struct PrimeRoots;
+template <> struct PrimeRoots<5> {
+    __host__ __device__ static constexpr double c(int m) { return m == 1 ? 0.30901699437494742410 : -0.80901699437494742410; }
+    __host__ __device__ static constexpr double s(int m) { return m == 1 ? 0.95105651629515357212 : 0.58778525229247312917; }
+};
+template <> struct PrimeRoots<7> {
+    __host__ __device__ static constexpr double c(int m)
+    {
+        return m == 1 ? 0.62348980185873353053 : m == 2 ? -0.22252093395631440429 : -0.90096886790241912624;
+    }
+    __host__ __device__ static constexpr double s(int m)
+    {
+        return m == 1 ? 0.78183148246802980871 : m == 2 ? 0.97492791218182360702 : 0.43388373911755812048;
+    }
+};
+template <int R, int DIR, typename C> struct OddPrimeButterfly {
+    __host__ __device__ __forceinline__ static void run(C *u)
+    {
+        using T = decltype(u[0].x);
+        constexpr int H = (R - 1) / 2;
+        C t[H], d[H];
+#pragma unroll
+        for (int j = 1; j <= H; ++j) {
+            t[j - 1] = cadd(u[j], u[R - j]);
+            d[j - 1] = mul_dir_i<DIR>(csub(u[j], u[R - j]));
+        }
+        const C x0 = u[0];
+        C sum = x0;
+#pragma unroll
+        for (int j = 0; j < H; ++j) sum = cadd(sum, t[j]);
+        u[0] = sum;
+#pragma unroll
+        for (int q = 1; q <= H; ++q) {
+            C a = x0, b;
+            b.x = (T)0; b.y = (T)0;
+#pragma unroll
+            for (int j = 1; j <= H; ++j) {
+                const int m = (j * q) % R;
+                const T cm = (T)(m <= H ? PrimeRoots<R>::c(m) : PrimeRoots<R>::c(R - m));
+                const T sm = (T)(m <= H ? PrimeRoots<R>::s(m) : -PrimeRoots<R>::s(R - m));
+                a.x = fma(cm, t[j - 1].x, a.x); a.y = fma(cm, t[j - 1].y, a.y);
+                b.x = fma(sm, d[j - 1].x, b.x); b.y = fma(sm, d[j - 1].y, b.y);
+            }
+            u[q] = cadd(a, b);
+            u[R - q] = csub(a, b);
+        }
+    }
+};
+template <int DIR, typename C> struct Butterfly<5, DIR, C> : OddPrimeButterfly<5, DIR, C> {};
+template <int DIR, typename C> struct Butterfly<7, DIR, C> : OddPrimeButterfly<7, DIR, C> {};
+
 // plus = a + w' b, minus = a - w' b with w' = w (forward) or conj(w) (backward): 6 FMAs instead of a complex
 // multiply (4) plus an add and a subtract (4).  minus = 2a - plus.
 template <int DIR, typename C> __host__ __device__ __forceinline__ void cfma_pm(C a, C w, C b, C &plus, C &minus)

@@ -2,9 +2,10 @@
 //
 // Used for axis lengths the templated Stockham kernels do not cover (non powers of two such as the reference's
 // own 10 x 25 x 40 and 50 x 200 test grids, tests/FFTDirectSolver/testFftSolver_3D.py:82-93, and n < 16).
-// Same Stockham recurrence with a runtime factor list (prime factors, pairs of 2 merged into radix 4); each thread
-// produces one output of one butterfly with an O(R) sum, twiddle exponents stepped mod n in integers, ping-pong in
-// shared memory.  Coverage path: O(n * sum of factors) per line; lengths 2^a and 2^a * 3 up to 1024 never get here.
+// Same Stockham recurrence with a runtime factor list (prime factors, the 2s merged into radix 8 / 4), ping-pong in
+// shared memory.  Stages of radix 2, 3, 4, 5, 7, 8 run the in-register butterflies of fft_core.cuh, one butterfly per
+// thread at a time; a prime factor >= 11 falls back to an O(R) sum per output with the root exponent stepped mod n
+// in integers.  Coverage path: lengths 2^a and 2^a * 3 up to 1024 never get here.
 #pragma once
 #include "fft_pass.cuh"
 
@@ -29,43 +30,137 @@ __device__ __forceinline__ int fdivmod(int a, int d, float invd, int &rem)
     return q;
 }
 
+// Where a stage reads its inputs / writes its outputs: the shared-memory ping-pong buffers [point][lane], or --
+// first stage of a transform that starts from HBM, last stage of one that ends there -- the global array itself
+// (same addressing as fft_pass.cuh: strided lines, the chunked multi-rank layouts, peer pushes).
+template <typename C> struct SmemSrc {
+    const C *p; int txsh;
+    __device__ __forceinline__ C operator()(int i, int l) const { return p[(i << txsh) + l]; }
+};
+template <typename C> struct SmemDst {
+    C *p; int txsh;
+    __device__ __forceinline__ void operator()(int i, int l, C v) const { p[(i << txsh) + l] = v; }
+};
+template <typename C> struct GlobalSrc {
+    const C *in; const PassGeom *g; long long tbase; int lanes_ok;       // lanes l < lanes_ok hold a real line
+    __device__ __forceinline__ C operator()(int i, int l) const
+    {
+        C z; z.x = 0; z.y = 0;
+        return l < lanes_ok ? in[tbase + (long long)l * g->SL + point_off(i, g->SI, g->Di, g->shi, g->SCi)] : z;
+    }
+};
+template <typename C> struct GlobalDst {
+    C *out; const PassGeom *g; long long obase; int lanes_ok;
+    __device__ __forceinline__ void operator()(int i, int l, C v) const
+    {
+        if (l < lanes_ok) *out_ptr<C>(out, *g, obase + (long long)l * g->SLo, i) = v;
+    }
+};
+
+// One Stockham stage with a compile-time radix: each thread does whole butterflies (R loads, R - 1 twiddles,
+// the in-register butterfly of fft_core.cuh, R stores).  Butterfly jb = m p + k reads x[jb + r n/R], multiplies by
+// exp(-/+ 2 pi i r k / (p R)) and writes y[(m R + q) p + k].
+template <typename T, int DIR, int R, typename Src, typename Dst>
+__device__ __forceinline__ void generic_stage_butterfly(const Src &src, const Dst &dst, int n, int p, int txsh,
+                                                        const cplx_t<T> *__restrict__ tw)
+{
+    using C = cplx_t<T>;
+    const int TX = 1 << txsh;
+    const int nR = n / R;
+    const int tws = nR / p;                      // n / (p R): table stride of this stage's roots
+    const float inv_p = 1.0f / (float)p;
+    for (int idx = threadIdx.x; idx < nR * TX; idx += blockDim.x) {
+        const int jb = idx >> txsh, l = idx & (TX - 1);
+        int k;
+        const int m = fdivmod(jb, p, inv_p, k);
+        C u[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) u[r] = src(jb + r * nR, l);
+        if (p > 1) {
+            const int e1 = k * tws;              // < n / R, so r * e1 < n: no reduction mod n
+#pragma unroll
+            for (int r = 1; r < R; ++r) u[r] = twmul<DIR>(u[r], __ldg(&tw[r * e1]));
+        }
+        Butterfly<R, DIR, C>::run(u);
+        const int o0 = (m * R) * p + k;
+#pragma unroll
+        for (int q = 0; q < R; ++q) dst(o0 + q * p, l, u[q]);
+    }
+}
+
+// Any other radix (primes >= 11, and the radix-1 "copy" of an axis of length 1): each thread produces one output
+// with an O(R) sum.
+template <typename T, int DIR, typename Src, typename Dst>
+__device__ __forceinline__ void generic_stage_sum(const Src &src, const Dst &dst, int n, int p, int R, int txsh,
+                                                  const cplx_t<T> *__restrict__ tw)
+{
+    using C = cplx_t<T>;
+    const int TX = 1 << txsh;
+    const int nR = n / R;
+    const int tws = nR / p;
+    const float inv_p = 1.0f / (float)p, inv_R = 1.0f / (float)R;
+    for (int idx = threadIdx.x; idx < n * TX; idx += blockDim.x) {
+        // output o = (m R + q) p + k of butterfly jb = m p + k
+        const int o = idx >> txsh, l = idx & (TX - 1);
+        int k, q;
+        const int t = fdivmod(o, p, inv_p, k);
+        const int m = fdivmod(t, R, inv_R, q);
+        const int jb = m * p + k;
+        // root exponent of term r is r (k tws + q nR) mod n: one add and a conditional subtract per term
+        int estep = k * tws + q * nR;
+        if (estep >= n) estep -= n;
+        int e = 0;
+        C acc = src(jb, l);
+        for (int r = 1; r < R; ++r) {
+            e += estep;
+            if (e >= n) e -= n;
+            acc = cadd(acc, twmul<DIR>(src(jb + r * nR, l), tw[e]));
+        }
+        dst(o, l, acc);
+    }
+}
+
+template <typename T, int DIR, typename Src, typename Dst>
+__device__ __forceinline__ void generic_stage(int R, const Src &src, const Dst &dst, int n, int p, int txsh,
+                                              const cplx_t<T> *__restrict__ tw)
+{
+    switch (R) {
+    case 2: generic_stage_butterfly<T, DIR, 2>(src, dst, n, p, txsh, tw); break;
+    case 3: generic_stage_butterfly<T, DIR, 3>(src, dst, n, p, txsh, tw); break;
+    case 4: generic_stage_butterfly<T, DIR, 4>(src, dst, n, p, txsh, tw); break;
+    case 5: generic_stage_butterfly<T, DIR, 5>(src, dst, n, p, txsh, tw); break;
+    case 7: generic_stage_butterfly<T, DIR, 7>(src, dst, n, p, txsh, tw); break;
+    case 8: generic_stage_butterfly<T, DIR, 8>(src, dst, n, p, txsh, tw); break;
+    default: generic_stage_sum<T, DIR>(src, dst, n, p, R, txsh, tw); break;
+    }
+}
+
+// Full transform of the tile's lines.  from_global: the first stage reads HBM (through gs) instead of `cur`;
+// to_global: the last stage writes HBM (through gd).  Otherwise the data starts in `cur` / ends in the returned
+// buffer.  The factor list is never empty (an axis of length 1 carries the single factor 1).
 template <typename T, int DIR>
-__device__ __forceinline__ cplx_t<T> *generic_line_fft(cplx_t<T> *src, cplx_t<T> *dst, const FactorList &f, int txsh,
-                                                       const cplx_t<T> *__restrict__ tw)
+__device__ __forceinline__ cplx_t<T> *generic_line_fft(cplx_t<T> *cur, cplx_t<T> *nxt, const FactorList &f, int txsh,
+                                                       const cplx_t<T> *__restrict__ tw, bool from_global,
+                                                       const GlobalSrc<cplx_t<T>> &gs, bool to_global,
+                                                       const GlobalDst<cplx_t<T>> &gd)
 {
     using C = cplx_t<T>;
     const int n = f.n;
-    const int TX = 1 << txsh;
     int p = 1;
     for (int s = 0; s < f.nfac; ++s) {
         const int R = f.fac[s];
-        const int nR = n / R;
-        const int tws = nR / p;                  // n / (p R)
-        const float inv_p = 1.0f / (float)p, inv_R = 1.0f / (float)R;
-        for (int idx = threadIdx.x; idx < n * TX; idx += blockDim.x) {
-            // output o = (m R + q) p + k of butterfly jb = m p + k
-            const int o = idx >> txsh, l = idx & (TX - 1);
-            int k, q;
-            const int t = fdivmod(o, p, inv_p, k);
-            const int m = fdivmod(t, R, inv_R, q);
-            const C *sp = src + (m * p + k) * TX + l;
-            // root exponent of term r is r (k tws + q nR) mod n: one add and a conditional subtract per term
-            int estep = k * tws + q * nR;
-            if (estep >= n) estep -= n;
-            int e = 0;
-            C acc = sp[0];
-            for (int r = 1; r < R; ++r) {
-                e += estep;
-                if (e >= n) e -= n;
-                acc = cadd(acc, twmul<DIR>(sp[(size_t)r * nR * TX], tw[e]));
-            }
-            dst[idx] = acc;
-        }
-        __syncthreads();
-        C *tmp = src; src = dst; dst = tmp;
+        const bool first = from_global && s == 0, last = to_global && s == f.nfac - 1;
+        const SmemSrc<C> ss{ cur, txsh };
+        const SmemDst<C> sd{ first ? cur : nxt, txsh };
+        if (first && last) generic_stage<T, DIR>(R, gs, gd, n, p, txsh, tw);
+        else if (first) generic_stage<T, DIR>(R, gs, sd, n, p, txsh, tw);
+        else if (last) generic_stage<T, DIR>(R, ss, gd, n, p, txsh, tw);
+        else generic_stage<T, DIR>(R, ss, sd, n, p, txsh, tw);
+        if (!last) __syncthreads();
+        if (!first) { C *tmp = cur; cur = nxt; nxt = tmp; }
         p *= R;
     }
-    return src;   // buffer holding the result
+    return cur;   // buffer holding the result (meaningless after a to_global transform)
 }
 
 template <typename T>
@@ -84,21 +179,16 @@ __global__ void generic_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> 
     const int ti = t % g.tiles_inner, to = t / g.tiles_inner;
     const long long tbase = (long long)to * g.B1 + (long long)ti * g.B0;
     const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o;
+    const int lanes_ok = g.lines_inner - ti * TX;            // >= TX for a full tile
+    const GlobalSrc<C> gs{ in, &g, tbase, lanes_ok };
+    const GlobalDst<C> gd{ out, &g, obase, lanes_ok };
 
-    for (int idx = threadIdx.x; idx < n * TX; idx += blockDim.x) {
-        const int i = idx >> txsh, l = idx & (TX - 1);
-        const bool ok = (ti * TX + l) < g.lines_inner;
-        A[idx] = ok ? in[tbase + (long long)l * g.SL + point_off(i, g.SI, g.Di, g.shi, g.SCi)] : mk<T>((T)0, (T)0);
-    }
-    __syncthreads();
-
-    C *res;
     if (mode == MODE_FWD) {
-        res = generic_line_fft<T, -1>(A, B, f, txsh, tw);
+        generic_line_fft<T, -1>(A, B, f, txsh, tw, true, gs, true, gd);
     } else if (mode == MODE_INV) {
-        res = generic_line_fft<T, +1>(A, B, f, txsh, tw);
+        generic_line_fft<T, +1>(A, B, f, txsh, tw, true, gs, true, gd);
     } else {
-        res = generic_line_fft<T, -1>(A, B, f, txsh, tw);
+        C *res = generic_line_fft<T, -1>(A, B, f, txsh, tw, true, gs, false, gd);
         C *oth = (res == A) ? B : A;
         for (int idx = threadIdx.x; idx < n * TX; idx += blockDim.x) {
             const int k = idx >> txsh, l = idx & (TX - 1);
@@ -141,13 +231,7 @@ __global__ void generic_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> 
             oth[idx] = v;
         }
         __syncthreads();
-        res = generic_line_fft<T, +1>(oth, res, f, txsh, tw);
-    }
-
-    for (int idx = threadIdx.x; idx < n * TX; idx += blockDim.x) {
-        const int i = idx >> txsh, l = idx & (TX - 1);
-        if ((ti * TX + l) < g.lines_inner)
-            *out_ptr<C>(out, g, obase + (long long)l * g.SLo, i) = res[idx];
+        generic_line_fft<T, +1>(oth, res, f, txsh, tw, false, gs, true, gd);
     }
 }
 

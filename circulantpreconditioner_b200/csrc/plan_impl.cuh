@@ -541,7 +541,9 @@ template <typename T> struct PlanT : PlanBase {
                         if ((long long)p * p > rem) p = rem;
                     }
                 }
-                // pairs of 2 become radix 4: same O(sum of factors) arithmetic, half the stages and barriers
+                if (c.fl.nfac == 0) c.fl.fac[c.fl.nfac++] = 1;      // length-1 axis: a radix-1 "copy" stage
+                // the 2s become radix 8 / 4 (fewer stages and barriers), largest radix first so that the cheap
+                // twiddle-free first stage (p = 1) is the widest one
                 {
                     int twos = 0, w = 0, rest[CPC_MAX_FACTORS];
                     for (int i = 0; i < c.fl.nfac; ++i) {
@@ -549,12 +551,24 @@ template <typename T> struct PlanT : PlanBase {
                         else rest[w++] = c.fl.fac[i];
                     }
                     int k = 0;
+                    for (; twos >= 3 && twos != 4; twos -= 3) c.fl.fac[k++] = 8;
                     for (; twos >= 2; twos -= 2) c.fl.fac[k++] = 4;
                     if (twos) c.fl.fac[k++] = 2;
                     for (int i = 0; i < w; ++i) c.fl.fac[k++] = rest[i];
                     c.fl.nfac = k;
+                    // a first stage that is an O(R) sum would read every input R times from HBM: stage the tile
+                    // through a radix-1 copy instead
+                    const int r0 = c.fl.fac[0];
+                    if (!(r0 == 1 || r0 == 2 || r0 == 3 || r0 == 4 || r0 == 5 || r0 == 7 || r0 == 8)) {
+                        if (c.fl.nfac >= CPC_MAX_FACTORS) { set_error("too many factors"); return CPC_ERR_UNSUPPORTED; }
+                        for (int i = c.fl.nfac; i > 0; --i) c.fl.fac[i] = c.fl.fac[i - 1];
+                        c.fl.fac[0] = 1;
+                        ++c.fl.nfac;
+                    }
                 }
                 int gtx = (a == 0 && nc == 4) ? 4 : 8;
+                // two CTAs per SM when 4 lanes (64-byte segments) allow it; below that only to fit at all
+                if (gtx == 8 && 2ull * n[a] * 8 * sizeof(C) > (size_t)dev_smem / 2 - 1024) gtx = 4;
                 while (gtx > ((nc == 4) ? 4 : 1) && 2ull * n[a] * gtx * sizeof(C) > (size_t)dev_smem) gtx >>= 1;
                 if (2ull * n[a] * gtx * sizeof(C) > (size_t)dev_smem) {
                     set_error("axis length %d too long for the generic kernel", n[a]);
@@ -562,8 +576,26 @@ template <typename T> struct PlanT : PlanBase {
                 }
                 c.tx = gtx;
                 c.smem_generic = 2ull * n[a] * gtx * sizeof(C);
-                long long work = (long long)n[a] * gtx;
-                c.threads = work >= 256 ? 256 : (int)((work + 31) / 32 * 32);
+                // CTA size: the stage of radix R has (n / R) * lanes butterflies, one per thread per round.  Pick the
+                // size whose rounds waste the fewest thread slots (320-point lines: 320 threads do the radix-8 stages
+                // in one full round, 256 would need two rounds with the second one a quarter full).  <= 320 threads
+                // keeps two CTAs of this 96-register kernel on an SM.
+                {
+                    long long best = -1;
+                    int best_t = 256;
+                    for (int t = 128; t <= 320; t += 32) {
+                        long long cost = 2 * (((long long)n[a] * gtx + t - 1) / t) * t;        // load + store sweeps
+                        for (int i = 0; i < c.fl.nfac; ++i) {
+                            const int R = c.fl.fac[i];
+                            const bool bf = (R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8);
+                            const long long items = bf ? (long long)(n[a] / R) * gtx : (long long)n[a] * gtx;
+                            cost += ((items + t - 1) / t) * t * R;
+                        }
+                        if (best < 0 || cost < best || (cost == best && t > best_t)) { best = cost; best_t = t; }
+                    }
+                    const long long work = (long long)n[a] * gtx;
+                    c.threads = work >= 128 ? best_t : (int)((work + 31) / 32 * 32);
+                }
             }
         }
         CPC_TRACE("axes configured");

@@ -56,7 +56,7 @@ int main()
 {
     int fail = 0;
     srand(7);
-    RUN(2); RUN(3); RUN(4); RUN(6); RUN(8); RUN(12); RUN(16);
+    RUN(2); RUN(3); RUN(4); RUN(5); RUN(6); RUN(7); RUN(8); RUN(12); RUN(16);
     const double t1 = check_twiddled8<-1, double>(), t2 = check_twiddled8<+1, double>();
     printf("twiddled radix 8: %.1e %.1e\n", t1, t2);
     if (t1 > 1e-14 || t2 > 1e-14) fail = 1;

@@ -107,7 +107,9 @@ SHAPES = [(16, 16, 16), (32, 64, 16), (64, 16, 128), (128, 32, 16), (256, 16, 32
           # 2^a * 3 line lengths: radix-6 / radix-12 last stage (prime-factor butterflies), fast kernels on every axis
           (48, 96, 192), (384, 6, 48), (10, 768, 3), (5, 3, 384), (96, 768, 2), (192, 5, 96), (768, 2, 3),
           # generic kernel: radix-4 grouping, odd primes (the reference's own 10 x 25 x 40 grid, testFftSolver_3D.py:82)
-          (10, 25, 40), (100, 10, 25), (250, 6, 7), (36, 45, 14)]
+          (10, 25, 40), (100, 10, 25), (250, 6, 7), (36, 45, 14),
+          # prime factors >= 11 (O(R) sum stages, first / last / only stage) and long generic lines (4 lanes per tile)
+          (22, 39, 34), (101, 2, 3), (3, 640, 2), (2, 3, 1000), (1536, 2, 2)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
