@@ -210,6 +210,42 @@ template <int R, int DIR, typename C> struct OddPrimeButterfly {
 template <int DIR, typename C> struct Butterfly<5, DIR, C> : OddPrimeButterfly<5, DIR, C> {};
 template <int DIR, typename C> struct Butterfly<7, DIR, C> : OddPrimeButterfly<7, DIR, C> {};
 
+// Prime-factor (Good-Thomas) butterfly for R = A * B with gcd(A, B) = 1: no internal twiddles.
+//   inputs  n = (B n1 + A n2) mod R,   outputs k = (cb k1 + ca k2) mod R,   cb = B (B^-1 mod A), ca = A (A^-1 mod B)
+__host__ __device__ constexpr int mod_inverse(int a, int m)
+{
+    int r = 1;
+    for (int i = 1; i < m; ++i)
+        if ((a * i) % m == 1) r = i;
+    return r;
+}
+template <int A, int B, int DIR, typename C> struct PfaButterfly {
+    __host__ __device__ __forceinline__ static void run(C *u)
+    {
+        constexpr int R = A * B;
+        constexpr int cb = B * mod_inverse(B % A, A), ca = A * mod_inverse(A % B, B);
+        C s[A][B];
+#pragma unroll
+        for (int n1 = 0; n1 < A; ++n1) {
+#pragma unroll
+            for (int n2 = 0; n2 < B; ++n2) s[n1][n2] = u[(B * n1 + A * n2) % R];
+            Butterfly<B, DIR, C>::run(s[n1]);
+        }
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2) {
+            C t[A];
+#pragma unroll
+            for (int n1 = 0; n1 < A; ++n1) t[n1] = s[n1][k2];
+            Butterfly<A, DIR, C>::run(t);
+#pragma unroll
+            for (int k1 = 0; k1 < A; ++k1) u[(cb * k1 + ca * k2) % R] = t[k1];
+        }
+    }
+};
+// line lengths 2^a * 5^b (100, 160, 200, 250, 320, 400, 500, 800, 1000)
+template <int DIR, typename C> struct Butterfly<10, DIR, C> : PfaButterfly<2, 5, DIR, C> {};
+template <int DIR, typename C> struct Butterfly<20, DIR, C> : PfaButterfly<4, 5, DIR, C> {};
+
 // plus = a + w' b, minus = a - w' b with w' = w (forward) or conj(w) (backward): 6 FMAs instead of a complex
 // multiply (4) plus an add and a subtract (4).  minus = 2a - plus.
 template <int DIR, typename C> __host__ __device__ __forceinline__ void cfma_pm(C a, C w, C b, C &plus, C &minus)

@@ -143,14 +143,15 @@ __device__ __forceinline__ void stockham_stage(cplx_t<T> (&v)[E], int j, int l, 
     using C = cplx_t<T>;
     constexpr int TPL = N / E;
     constexpr int NB = E / R;          // butterflies per thread in this stage
-    static_assert(R == 1 || (P & (P - 1)) == 0, "an odd radix must be the last one: k = jb mod P is computed with a mask");
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         const int jb = j + b * TPL;
         C u[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) u[r] = v[b + r * NB];
-        const int k = (P > 1) ? (jb & (P - 1)) : 0;
+        // butterfly index within the previous stages' period: a mask for the power-of-two kernels, a constant
+        // modulo (multiply-high) when an earlier radix was 5, 10 or 20
+        const int k = (P > 1) ? (((P & (P - 1)) == 0) ? (jb & (P - 1)) : (jb % P)) : 0;
         if constexpr (P > 1 && R == 8) {
             C w[7];
 #pragma unroll

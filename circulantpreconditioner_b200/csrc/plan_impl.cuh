@@ -175,6 +175,26 @@ template <> struct FastRegistry<double> {
         register_modes_gen<double, VAR_XMAP,    192,  8,  4,  6, 24, 16,  1, 3, 3, false, 1>(m);
         register_modes_gen<double, VAR_XMAP,    384,  8,  8,  6, 24,  8,  1, 3, 3, false, 1>(m);
         register_modes_gen<double, VAR_XMAP,    768,  8,  8, 12, 24,  4,  1, 3, 3, false, 1>(m);
+        // line lengths 2^a * 5^b: radix 5, 10 = 2 x 5 and 20 = 4 x 5 butterflies, 10 or 20 points per thread
+        //                         variant        N   R0  R1  R2   E  TX   G MINB MINBF
+        register_modes_gen<double, VAR_WIDE,    100, 10, 10,  1, 10,  8,  3, 2, 2, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,    160,  4,  4, 10, 20,  8,  2, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,    200, 10, 20,  1, 20,  8,  2, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,    250,  5,  5, 10, 10,  8,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,    320,  4,  4, 20, 20,  8,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,    400, 20, 20,  1, 20,  8,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,    500,  5, 10, 10, 10,  8,  1, 2, 2, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,    800,  4, 10, 20, 20,  4,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_WIDE,   1000, 10, 10, 10, 10,  4,  1, 2, 2, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    100, 10, 10,  1, 10, 24,  1, 2, 2, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    160,  4,  4, 10, 20, 16,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    200, 10, 20,  1, 20, 16,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    250,  5,  5, 10, 10,  8,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    320,  4,  4, 20, 20,  8,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    400, 20, 20,  1, 20,  8,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    500,  5, 10, 10, 10,  8,  1, 2, 2, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,    800,  4, 10, 20, 20,  4,  1, 3, 3, false, 1>(m);
+        register_modes_gen<double, VAR_XMAP,   1000, 10, 10, 10, 10,  4,  1, 2, 2, false, 1>(m);
         register_modes<double, VAR_XMAP,     16, 16,  1,  1, 16, 64,  1, 2>(m);
         register_modes<double, VAR_XMAP,     32,  8,  4,  1,  8, 64,  1, 2>(m);
         register_modes<double, VAR_XMAP,     64,  8,  8,  1,  8, 32,  1, 2>(m);
@@ -223,6 +243,24 @@ template <> struct FastRegistry<float> {
         register_modes_gen<float, VAR_XMAP,    192,  8,  4,  6, 24, 32,  1, 2, 2, false, 1>(m);
         register_modes_gen<float, VAR_XMAP,    384,  8,  8,  6, 24, 16,  1, 2, 2, false, 1>(m);
         register_modes_gen<float, VAR_XMAP,    768,  8,  8, 12, 24,  8,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    100, 10, 10,  1, 10, 16,  2, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    160,  4,  4, 10, 20, 16,  2, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    200, 10, 20,  1, 20, 16,  1, 3, 3, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    250,  5,  5, 10, 10, 16,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    320,  4,  4, 20, 20, 16,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    400, 20, 20,  1, 20, 16,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    500,  5, 10, 10, 10,  8,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,    800,  4, 10, 20, 20,  8,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_WIDE,   1000, 10, 10, 10, 10,  8,  1, 1, 1, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    100, 10, 10,  1, 10, 32,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    160,  4,  4, 10, 20, 32,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    200, 10, 20,  1, 20, 32,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    250,  5,  5, 10, 10, 16,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    320,  4,  4, 20, 20, 16,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    400, 20, 20,  1, 20, 16,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    500,  5, 10, 10, 10,  8,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,    800,  4, 10, 20, 20,  8,  1, 2, 2, false, 1>(m);
+        register_modes_gen<float, VAR_XMAP,   1000, 10, 10, 10, 10,  8,  1, 1, 1, false, 1>(m);
         register_modes<float, VAR_XMAP,     16, 16,  1,  1, 16, 64,  1, 2>(m);
         register_modes<float, VAR_XMAP,     32,  8,  4,  1,  8, 64,  1, 2>(m);
         register_modes<float, VAR_XMAP,     64,  8,  8,  1,  8, 32,  1, 2>(m);

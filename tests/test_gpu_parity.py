@@ -109,7 +109,10 @@ SHAPES = [(16, 16, 16), (32, 64, 16), (64, 16, 128), (128, 32, 16), (256, 16, 32
           # generic kernel: radix-4 grouping, odd primes (the reference's own 10 x 25 x 40 grid, testFftSolver_3D.py:82)
           (10, 25, 40), (100, 10, 25), (250, 6, 7), (36, 45, 14),
           # prime factors >= 11 (O(R) sum stages, first / last / only stage) and long generic lines (4 lanes per tile)
-          (22, 39, 34), (101, 2, 3), (3, 640, 2), (2, 3, 1000), (1536, 2, 2)]
+          (22, 39, 34), (101, 2, 3), (3, 640, 2), (1536, 2, 2),
+          # 2^a * 5^b line lengths: radix 5 / 10 / 20 butterflies, non-power-of-two stage periods (k = jb mod P)
+          (100, 200, 160), (250, 8, 400), (320, 3, 500), (500, 100, 2), (800, 2, 250), (2, 3, 1000), (1000, 2, 800),
+          (6, 800, 5), (400, 320, 3)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -190,7 +193,8 @@ def test_wave_block_matches_oracle(shape):
 
 
 @pytest.mark.parametrize("shape", [(32, 32, 32), (64, 128, 16), (512, 8, 16), (20, 12, 9), (96, 48, 192),
-                                   (384, 12, 768), (768, 3, 384), (100, 10, 25)])
+                                   (384, 12, 768), (768, 3, 384), (100, 10, 25), (100, 200, 160), (250, 400, 3),
+                                   (320, 3, 500), (1000, 2, 800), (800, 1000, 2)])
 def test_fp32_option(shape):
     nx, ny, nz = shape
     rng = np.random.default_rng(23)
@@ -290,7 +294,8 @@ def test_roundtrip_and_linearity_at_baseline_sizes(n):
 # ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(64, 32, 16), (512, 8, 16), (128, 64, 32), (256, 16, 1), (1024, 4, 2), (64, 1, 1),
                                    (20, 12, 9), (30, 1, 17), (16, 16, 16), (768, 6, 48), (384, 12, 5), (96, 4, 4),
-                                   (192, 4, 4), (100, 6, 4)])
+                                   (192, 4, 4), (100, 6, 4), (200, 100, 3), (400, 3, 160), (1000, 4, 3), (500, 2, 2),
+                                   (320, 5, 2), (800, 2, 2)])
 def test_real_scalar_plan_matches_oracle(shape):
     nx, ny, nz = shape
     rng = np.random.default_rng(nx + ny + nz)
