@@ -1,5 +1,4 @@
 // plan_f32.cu -- complex64 instantiation (the fp32 option of BASELINE.json's north_star).
-#define CPC_INSTANTIATE_F32
 #include "plan_impl.cuh"
 
 namespace cpc {

@@ -1,5 +1,4 @@
 // plan_f64.cu -- complex128 instantiation of the plan and its kernels (PetscScalar of a complex PETSc build).
-#define CPC_INSTANTIATE_F64
 #include "plan_impl.cuh"
 
 namespace cpc {

@@ -17,261 +17,31 @@
 #include <tuple>
 
 #include "dist.h"
-#include "fft_pass.cuh"
-#include "fft_r2x.cuh"
 #include "generic_pass.cuh"
 #include "plan.h"
+#include "registry.cuh"
 
 namespace cpc {
 
-// ------------------------------------------------------------------------------------------------
-// Fast-kernel registry
-// ------------------------------------------------------------------------------------------------
-template <typename T> struct FastEntry {
-    void (*kern)(const cplx_t<T> *, cplx_t<T> *, const PassGeom, const cplx_t<T> *, const SymbolArgs<T>);
-    int threads;
-    size_t smem;
-    int g;          // tiles per CTA
-    int tx;         // lines per tile
-    int radix[3];
-};
-
-// Kernel variants of one axis length.
-enum Variant {
-    VAR_WIDE = 0,     // strided lines, TX lanes = one 128-byte row (y, z passes)
-    VAR_NARROW = 1,   // strided lines, TX = 4 (wave x pass: the 4 components of a cell; long lines)
-    VAR_XMAP = 2,     // contiguous lines (scalar x pass)
-    VAR_WIDE2 = 3,    // as VAR_WIDE with a different points-per-thread / radix split (512: two butterflies per thread)
-    VAR_SMALL = 4,    // as VAR_WIDE with small CTAs, 4 per SM (256-point y lines)
-    VAR_R2X = 5,      // 512 = 2 x (16 x 16): radix-2 level in registers + warp shuffle, one shared-memory exchange
-    VAR_XR2X = 6,     // the same for contiguous lines: one warp per line, no block barrier (scalar x pass)
-    VAR_SLIM = 7,     // strided lines, TX = 4 and one line group per CTA: 64 KB tiles for 1024-point lines, 2 CTAs per SM
-    VAR_COUNT = 8
-};
-
-template <typename T> using FastKey = std::tuple<int, int, int>;   // (n, variant, mode + 16 * general-addressing)
-
-constexpr int GEN_BIT = 16;   // key offset of the kernels compiled with chunked-layout / peer-push addressing
-
-template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF, bool GEN, int NG>
-static void register_modes_gen(std::map<FastKey<T>, FastEntry<T>> &m)
-{
-    constexpr int NST = (R1 > 1) + (R2 > 1) + 1;
-    constexpr bool XM = (VAR == VAR_XMAP);
-    constexpr int threads = (N / E) * TX * G;
-    constexpr size_t smem = NST > 1 ? (size_t)G * NG * SmemTile<N, TX / NG, Log2<R0>::v, XM>::elems * sizeof(cplx_t<T>) : 0;
-    constexpr int KB = GEN ? GEN_BIT : 0;
-    FastEntry<T> e{ nullptr, threads, smem, G, TX, { R0, R1, R2 } };
-    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FWD, MINB, XM, GEN, NG>;
-    m[FastKey<T>(N, VAR, MODE_FWD + KB)] = e;
-    e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_INV, MINB, XM, GEN, NG>;
-    m[FastKey<T>(N, VAR, MODE_INV + KB)] = e;
-    if constexpr (XM && NST > 1 && !GEN) {
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_R2C, MINB, XM, false, NG>;
-        m[FastKey<T>(N, VAR, MODE_R2C)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_C2R, MINB, XM, false, NG>;
-        m[FastKey<T>(N, VAR, MODE_C2R)] = e;
-    }
-    if constexpr (!XM) {
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_SEP, MINBF, XM, GEN, NG>;
-        m[FastKey<T>(N, VAR, MODE_FUSED_SEP + KB)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_TABLE, MINBF, XM, GEN, NG>;
-        m[FastKey<T>(N, VAR, MODE_FUSED_TABLE + KB)] = e;
-        e.kern = fft_pass_kernel<T, N, R0, R1, R2, E, TX, G, MODE_FUSED_WAVE, MINBF, XM, GEN, NG>;
-        m[FastKey<T>(N, VAR, MODE_FUSED_WAVE + KB)] = e;
-    }
-}
-
-// Every variant is compiled with plain strided addressing; the variants used for the y and z passes of power-of-two
-// grids (VAR_WIDE and the tuned 512 / 256 ones) also get the general-addressing build needed by multi-rank plans.
-template <typename T, int VAR, int N, int R0, int R1, int R2, int E, int TX, int G, int MINB, int MINBF = MINB, int NG = 1>
-static void register_modes(std::map<FastKey<T>, FastEntry<T>> &m)
-{
-    register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, false, NG>(m);
-    if constexpr (VAR == VAR_WIDE || VAR == VAR_WIDE2 || VAR == VAR_SMALL)
-        register_modes_gen<T, VAR, N, R0, R1, R2, E, TX, G, MINB, MINBF, true, NG>(m);
-}
-
-// strided lines of 2 H points as 2 x (R0 x R1) (fft_r2x.cuh)
-template <typename T, int H, int R0, int R1> static void register_r2x(std::map<FastKey<T>, FastEntry<T>> &m)
-{
-    constexpr int TX = 128 / (int)sizeof(cplx_t<T>);      // 8 lanes (complex128) or 16 (complex64) = one 128-byte row
-    FastEntry<T> e{ nullptr, H * TX / 8, (size_t)H * 2 * TX * sizeof(cplx_t<T>), 1, TX, { R0, R1, 1 } };
-#define CPC_R2X(MODE)                                                                            \
-    e.kern = fft_r2x_kernel<T, H, R0, R1, MODE, false>; m[FastKey<T>(2 * H, VAR_R2X, MODE)] = e;           \
-    e.kern = fft_r2x_kernel<T, H, R0, R1, MODE, true>;  m[FastKey<T>(2 * H, VAR_R2X, MODE + GEN_BIT)] = e;
-    CPC_R2X(MODE_FWD)
-    CPC_R2X(MODE_INV)
-    CPC_R2X(MODE_FUSED_SEP)
-    CPC_R2X(MODE_FUSED_TABLE)
-    CPC_R2X(MODE_FUSED_WAVE)
-#undef CPC_R2X
-}
-
-// contiguous 512-point lines, one warp per line (fft_r2x.cuh); plain transforms only
-template <typename T> static void register_r2x512_line(std::map<FastKey<T>, FastEntry<T>> &m)
-{
-    constexpr int LINES = 8;
-    FastEntry<T> e{ nullptr, 32 * LINES, (size_t)LINES * 512 * sizeof(cplx_t<T>), 1, LINES, { 16, 16, 1 } };
-    e.kern = fft_r2x512_line_kernel<T, MODE_FWD, LINES>; m[FastKey<T>(512, VAR_XR2X, MODE_FWD)] = e;
-    e.kern = fft_r2x512_line_kernel<T, MODE_INV, LINES>; m[FastKey<T>(512, VAR_XR2X, MODE_INV)] = e;
-}
-
-// contiguous 256-point lines, half a warp per line (fft_r2x.cuh): plain transforms and the r2c / c2r pair
-template <typename T> static void register_line256(std::map<FastKey<T>, FastEntry<T>> &m)
-{
-    constexpr int LINES = 16;
-    FastEntry<T> e{ nullptr, 16 * LINES, (size_t)LINES * 256 * sizeof(cplx_t<T>), 1, LINES, { 16, 16, 1 } };
-    e.kern = fft_line256_kernel<T, MODE_FWD, LINES>; m[FastKey<T>(256, VAR_XR2X, MODE_FWD)] = e;
-    e.kern = fft_line256_kernel<T, MODE_INV, LINES>; m[FastKey<T>(256, VAR_XR2X, MODE_INV)] = e;
-    e.kern = fft_line256_kernel<T, MODE_R2C, LINES>; m[FastKey<T>(256, VAR_XR2X, MODE_R2C)] = e;
-    e.kern = fft_line256_kernel<T, MODE_C2R, LINES>; m[FastKey<T>(256, VAR_XR2X, MODE_C2R)] = e;
-}
-
 template <typename T> struct FastRegistry;
-
-#ifdef CPC_INSTANTIATE_F64
-// fp64: a quarter warp (8 lanes x 16 B) covers one 128-byte row of the [N][8] tile.
 template <> struct FastRegistry<double> {
     static void fill(std::map<FastKey<double>, FastEntry<double>> &m)
     {
-        //                     variant        N   R0  R1  R2   E  TX   G MINB [MINB fused]
-        register_modes<double, VAR_WIDE,     16, 16,  1,  1, 16,  8, 16, 2>(m);
-        register_modes<double, VAR_WIDE,     32,  8,  4,  1,  8,  8,  8, 2>(m);
-        register_modes<double, VAR_WIDE,     64,  8,  8,  1,  8,  8,  4, 2>(m);
-        register_modes<double, VAR_WIDE,    128, 16,  8,  1, 16,  8,  4, 2>(m);
-        register_modes<double, VAR_WIDE,    256, 16, 16,  1, 16,  8,  2, 2>(m);
-        register_modes<double, VAR_WIDE,    512,  8,  8,  8,  8,  8,  1, 2, 1>(m);
-        register_modes<double, VAR_WIDE,   1024, 16,  8,  8, 16,  8,  1, 1>(m);
-        register_modes<double, VAR_WIDE2,   512,  8,  8,  8, 16,  8,  1, 2>(m);
-        register_r2x<double, 256, 16, 16>(m);
-        register_r2x<double, 128, 16, 8>(m);
-        register_r2x512_line<double>(m);
-        register_line256<double>(m);
-        register_modes<double, VAR_WIDE2,   256,  8,  8,  4,  8,  8,  2, 2>(m);      // 512 thr, 64 regs
-        register_modes<double, VAR_WIDE2,   128,  8,  4,  4,  8,  8,  4, 2>(m);      // 512 thr, 64 regs
-        register_modes<double, VAR_SMALL,    256,  8,  8,  4,  8,  8,  1, 4>(m);      // 256 thr, 64 regs, 4 CTAs/SM
-        register_modes<double, VAR_NARROW,   16, 16,  1,  1, 16,  4, 32, 2>(m);
-        register_modes<double, VAR_NARROW,   32,  8,  4,  1,  8,  4, 16, 2>(m);
-        register_modes<double, VAR_NARROW,   64,  8,  8,  1,  8,  4,  8, 2>(m);
-        register_modes<double, VAR_NARROW,  128, 16,  8,  1, 16,  4,  8, 2>(m);
-        register_modes<double, VAR_NARROW,  256, 16, 16,  1, 16,  4,  4, 2>(m);
-        register_modes<double, VAR_NARROW,  512,  8,  8,  8,  8,  4,  2, 2, 1>(m);
-        register_modes<double, VAR_NARROW, 1024, 16,  8,  8, 16,  4,  2, 1>(m);
-        register_modes<double, VAR_NARROW, 2048, 16, 16,  8, 16,  4,  1, 1>(m);
-        register_modes<double, VAR_SLIM,   1024, 16,  8,  8, 16,  4,  1, 2>(m);
-        // line lengths 2^a * 3 (radix 6 / 12 last, prime-factor butterflies): 24 points per thread need 96 data registers
-        // in fp64, so these run 3 small CTAs per SM at <= 168 registers; single-rank builds only
-        register_modes_gen<double, VAR_WIDE,     48,  4, 12,  1, 12,  8,  8, 2, 2, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,     96,  4,  4,  6, 12,  8,  4, 2, 2, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,    192,  8,  4,  6, 24,  8,  2, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,    384,  8,  8,  6, 24,  8,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,    768,  8,  8, 12, 24,  4,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_NARROW,   96,  4,  4,  6, 12,  4,  8, 2, 2, false, 1>(m);
-        register_modes_gen<double, VAR_NARROW,  192,  8,  4,  6, 24,  4,  4, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_NARROW,  384,  8,  8,  6, 24,  4,  2, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,     48,  4, 12,  1, 12, 64,  1, 2, 2, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,     96,  4,  4,  6, 12, 32,  1, 2, 2, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    192,  8,  4,  6, 24, 16,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    384,  8,  8,  6, 24,  8,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    768,  8,  8, 12, 24,  4,  1, 3, 3, false, 1>(m);
-        // line lengths 2^a * 5^b: radix 5, 10 = 2 x 5 and 20 = 4 x 5 butterflies, 10 or 20 points per thread
-        //                         variant        N   R0  R1  R2   E  TX   G MINB MINBF
-        register_modes_gen<double, VAR_WIDE,    100, 10, 10,  1, 10,  8,  3, 2, 2, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,    160,  4,  4, 10, 20,  8,  2, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,    200, 10, 20,  1, 20,  8,  2, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,    250,  5,  5, 10, 10,  8,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,    320,  4,  4, 20, 20,  8,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,    400, 20, 20,  1, 20,  8,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,    500,  5, 10, 10, 10,  8,  1, 2, 2, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,    800,  4, 10, 20, 20,  4,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_WIDE,   1000, 10, 10, 10, 10,  4,  1, 2, 2, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    100, 10, 10,  1, 10, 24,  1, 2, 2, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    160,  4,  4, 10, 20, 16,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    200, 10, 20,  1, 20, 16,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    250,  5,  5, 10, 10,  8,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    320,  4,  4, 20, 20,  8,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    400, 20, 20,  1, 20,  8,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    500,  5, 10, 10, 10,  8,  1, 2, 2, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,    800,  4, 10, 20, 20,  4,  1, 3, 3, false, 1>(m);
-        register_modes_gen<double, VAR_XMAP,   1000, 10, 10, 10, 10,  4,  1, 2, 2, false, 1>(m);
-        register_modes<double, VAR_XMAP,     16, 16,  1,  1, 16, 64,  1, 2>(m);
-        register_modes<double, VAR_XMAP,     32,  8,  4,  1,  8, 64,  1, 2>(m);
-        register_modes<double, VAR_XMAP,     64,  8,  8,  1,  8, 32,  1, 2>(m);
-        register_modes<double, VAR_XMAP,    128, 16,  8,  1, 16, 32,  1, 2>(m);
-        register_modes<double, VAR_XMAP,    256, 16, 16,  1, 16, 16,  1, 2>(m);
-        register_modes<double, VAR_XMAP,    512,  8,  8,  8,  8,  8,  1, 2>(m);
-        register_modes<double, VAR_XMAP,   1024, 16,  8,  8, 16,  4,  1, 2>(m);
-        register_modes<double, VAR_XMAP,   2048, 16, 16,  8, 16,  2,  1, 2>(m);
+        fill_fast_f64_odd(m);
+        fill_fast_f64_pow2a(m);
+        fill_fast_f64_pow2b(m);
+        fill_fast_f64_r2x(m);
     }
 };
-#endif
-#ifdef CPC_INSTANTIATE_F32
-// fp32: 16 lanes x 8 B = one 128-byte row.
 template <> struct FastRegistry<float> {
     static void fill(std::map<FastKey<float>, FastEntry<float>> &m)
     {
-        register_modes<float, VAR_WIDE,     16, 16,  1,  1, 16, 16,  8, 2>(m);
-        register_modes<float, VAR_WIDE,     32,  8,  4,  1,  8, 16,  4, 2>(m);
-        register_modes<float, VAR_WIDE,     64,  8,  8,  1,  8, 16,  2, 2>(m);
-        register_modes<float, VAR_WIDE,    128, 16,  8,  1, 16, 16,  2, 2>(m);
-        register_modes<float, VAR_WIDE,    256, 16, 16,  1, 16, 16,  1, 2>(m);
-        register_modes<float, VAR_WIDE,    512, 16,  8,  4, 16, 16,  1, 2>(m);
-        register_modes<float, VAR_WIDE,   1024, 16,  8,  8, 16, 16,  1, 1>(m);
-        register_r2x512_line<float>(m);
-        register_r2x<float, 256, 16, 16>(m);
-        register_r2x<float, 128, 16, 8>(m);
-        register_line256<float>(m);
-        register_modes<float, VAR_NARROW,   16, 16,  1,  1, 16,  4, 32, 2>(m);
-        register_modes<float, VAR_NARROW,   32,  8,  4,  1,  8,  4, 16, 2>(m);
-        register_modes<float, VAR_NARROW,   64,  8,  8,  1,  8,  4,  8, 2>(m);
-        register_modes<float, VAR_NARROW,  128, 16,  8,  1, 16,  4,  8, 2>(m);
-        register_modes<float, VAR_NARROW,  256, 16, 16,  1, 16,  4,  4, 2>(m);
-        register_modes<float, VAR_NARROW,  512,  8,  8,  8,  8,  4,  2, 2>(m);
-        register_modes<float, VAR_NARROW, 1024, 16,  8,  8, 16,  4,  2, 1>(m);
-        register_modes<float, VAR_NARROW, 2048, 16, 16,  8, 16,  4,  1, 1>(m);
-        register_modes_gen<float, VAR_WIDE,     48,  4, 12,  1, 12, 16,  4, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,     96,  4,  4,  6, 12, 16,  2, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    192,  8,  4,  6, 24, 16,  2, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    384,  8,  8,  6, 24, 16,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    768,  8,  8, 12, 24,  8,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_NARROW,   96,  4,  4,  6, 12,  4,  8, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_NARROW,  192,  8,  4,  6, 24,  4,  8, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_NARROW,  384,  8,  8,  6, 24,  4,  4, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,     48,  4, 12,  1, 12, 64,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,     96,  4,  4,  6, 12, 32,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    192,  8,  4,  6, 24, 32,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    384,  8,  8,  6, 24, 16,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    768,  8,  8, 12, 24,  8,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    100, 10, 10,  1, 10, 16,  2, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    160,  4,  4, 10, 20, 16,  2, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    200, 10, 20,  1, 20, 16,  1, 3, 3, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    250,  5,  5, 10, 10, 16,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    320,  4,  4, 20, 20, 16,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    400, 20, 20,  1, 20, 16,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    500,  5, 10, 10, 10,  8,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,    800,  4, 10, 20, 20,  8,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_WIDE,   1000, 10, 10, 10, 10,  8,  1, 1, 1, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    100, 10, 10,  1, 10, 32,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    160,  4,  4, 10, 20, 32,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    200, 10, 20,  1, 20, 32,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    250,  5,  5, 10, 10, 16,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    320,  4,  4, 20, 20, 16,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    400, 20, 20,  1, 20, 16,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    500,  5, 10, 10, 10,  8,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,    800,  4, 10, 20, 20,  8,  1, 2, 2, false, 1>(m);
-        register_modes_gen<float, VAR_XMAP,   1000, 10, 10, 10, 10,  8,  1, 1, 1, false, 1>(m);
-        register_modes<float, VAR_XMAP,     16, 16,  1,  1, 16, 64,  1, 2>(m);
-        register_modes<float, VAR_XMAP,     32,  8,  4,  1,  8, 64,  1, 2>(m);
-        register_modes<float, VAR_XMAP,     64,  8,  8,  1,  8, 32,  1, 2>(m);
-        register_modes<float, VAR_XMAP,    128, 16,  8,  1, 16, 32,  1, 2>(m);
-        register_modes<float, VAR_XMAP,    256, 16, 16,  1, 16, 16,  1, 2>(m);
-        register_modes<float, VAR_XMAP,    512,  8,  8,  8,  8,  8,  1, 2>(m);
-        register_modes<float, VAR_XMAP,   1024, 16,  8,  8, 16,  8,  1, 2>(m);
-        register_modes<float, VAR_XMAP,   2048, 16, 16,  8, 16,  4,  1, 2>(m);
+        fill_fast_f32_odd(m);
+        fill_fast_f32_pow2a(m);
+        fill_fast_f32_pow2b(m);
+        fill_fast_f32_r2x(m);
     }
 };
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // Small set-up kernels
