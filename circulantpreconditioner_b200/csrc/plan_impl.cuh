@@ -20,6 +20,7 @@
 #include "generic_pass.cuh"
 #include "plan.h"
 #include "registry.cuh"
+#include "zsolve.cuh"
 
 namespace cpc {
 
@@ -152,6 +153,11 @@ template <typename T> struct PlanT : PlanBase {
     C *work = nullptr;            // half spectrum (real plans) or the promoted complex copy
     int num_sms = 148;
     int pf_waves = 0;             // L2 prefetch distance in units of (SM count) CTAs; 0 = off
+    // transport symbol with the upwind z column: the middle pass is a cyclic first-order recurrence (zsolve.cuh)
+    bool zrec = false;            // the symbol allows it
+    bool zrec_off = false;        // CPC_ZSOLVE=0: keep the FFT-based fused pass (comparison / tuning hook)
+    double zrec_lz = 0.0;
+    int zrec_e = 0;               // points per thread (0: nz does not fit any compiled form)
     int stagger = 0;              // start offset (cycles) of every SM's second resident CTA (tuning hook)
     int nzl = 1, z0 = 0;          // local z slab
     int nyl = 1, y0 = 0;          // local y range in the transposed distribution
@@ -265,6 +271,8 @@ template <typename T> struct PlanT : PlanBase {
         CPC_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
         if (const char *pf = getenv("CPC_PREFETCH_WAVES")) pf_waves = atoi(pf);   // tuning hook
+        if (const char *zs = getenv("CPC_ZSOLVE")) zrec_off = (atoi(zs) == 0);     // tuning hook
+        zrec_e = zsolve_points_per_thread(n[2]);
         if (const char *sg = getenv("CPC_STAGGER")) stagger = atoi(sg);           // tuning hook
         CPC_TRACE("got smem attribute");
 
@@ -556,7 +564,11 @@ template <typename T> struct PlanT : PlanBase {
     {
         const AxisCfg &c = cfg[axis];
         long long off = 0;
-        PassGeom g = make_geom(axis, c.tx, zb, zc, layout, &off);
+        // middle pass of a transport symbol: cyclic recurrence along z (zsolve.cuh), 128-byte rows as lanes.
+        // Multi-rank pushes need power-of-two chunks (shift / mask addressing), as for the FFT kernels.
+        const bool zs = axis == 2 && mode == MODE_FUSED_SEP && zrec && !zrec_off && zrec_e > 0 && nc == 1 &&
+                        (split == 0 || (nzl & (nzl - 1)) == 0);
+        PassGeom g = make_geom(axis, zs ? 128 / (int)sizeof(C) : c.tx, zb, zc, layout, &off);
         if (split == 1 || split == 2) make_split(g, split == 1);
         if (split == 3 || split == 4) {
             const long long W = (long long)n[0] * nc;
@@ -580,7 +592,22 @@ template <typename T> struct PlanT : PlanBase {
         if (g.ntiles <= 0) return CPC_OK;
         SymbolArgs<T> s = symbol_args();
         s.rz = tw[axis];          // roots of the transformed axis (fft_r2x.cuh); the fused pass is always axis 2
-        if (c.fast) {
+        if (zs) {
+            if (split != 0) {
+                if (g.Di == 0) { g.shi = 31; g.maski = 0x7fffffff; g.SCi = 0; }
+                if (g.Do == 0) { g.sho = 31; g.masko = 0x7fffffff; g.SCo = 0; }
+                if (g.npeer == 0)
+                    for (int q = 0; q < CPC_MAX_PEERS; ++q) g.peer[q] = (void *)(out + off);
+            }
+            const bool gen = split != 0;
+            switch (zrec_e) {
+            case 16: launch_zsolve<16>(gen, g.ntiles, st, in + off, out + off, g); break;
+            case 8: launch_zsolve<8>(gen, g.ntiles, st, in + off, out + off, g); break;
+            case 10: launch_zsolve<10>(gen, g.ntiles, st, in + off, out + off, g); break;
+            case 5: launch_zsolve<5>(gen, g.ntiles, st, in + off, out + off, g); break;
+            default: launch_zsolve<4>(gen, g.ntiles, st, in + off, out + off, g); break;
+            }
+        } else if (c.fast) {
             // multi-rank y / z passes need the general-addressing build (init() made sure it exists)
             if (split != 0) {
                 // branch-free general addressing: a side without a split behaves as one chunk of 2^31 points, and
@@ -679,7 +706,53 @@ template <typename T> struct PlanT : PlanBase {
         int rc = upload_tables(h);
         if (rc) return rc;
         symbol_kind = CPC_SYMBOL_SEPARABLE;
+        // Is the z column the upwind [1, -1, 0, ...] (c_z_hat[k] = 1 - exp(-2 pi i k / nz)) with 0 <= lambda_z <= 4096,
+        // and Re(lambda_x c_x_hat), Re(lambda_y c_y_hat) >= 0 so that |lambda_z / (alpha + lambda_z)| < 1?  Then the
+        // middle pass is solved as a cyclic recurrence (zsolve.cuh) instead of forward FFT, division, backward FFT.
+        zrec = (lz >= 0.0 && lz <= 4096.0);
+        for (int m = 0; zrec && m < n[2]; ++m) {
+            double re = 1.0, im = 0.0;
+            if (n[2] > 1) exact_root(m, n[2], &re, &im);
+            const double wr = n[2] > 1 ? 1.0 - re : 0.0, wi = n[2] > 1 ? -im : 0.0;
+            if (std::fabs(cz[2 * m] - wr) > 1e-13 || std::fabs(cz[2 * m + 1] - wi) > 1e-13) zrec = false;
+        }
+        for (int a = 0; zrec && a < 2; ++a)
+            for (int m = 0; m < n[a]; ++m)
+                if (lam[a] * c[a][2 * m] < -1e-12) { zrec = false; break; }
+        zrec_lz = lz;
         return CPC_OK;
+    }
+
+    // Points per thread of the recurrence kernel for nz-point lines: nz / E segments, a multiple of the 32 / TX
+    // segments a warp holds, at most 32 warps and within the CTA size the kernel is compiled for.  0 = no fit.
+    static int zsolve_points_per_thread(int nz)
+    {
+        constexpr int TX = 128 / (int)sizeof(C), QW = 32 / TX;
+        const int cand[5] = { 16, 8, 10, 5, 4 };
+        for (int i = 0; i < 5; ++i) {
+            const int E = cand[i];
+            if (nz % E) continue;
+            const int S = nz / E;
+            if (S % QW) continue;
+            const int threads = S * TX;
+            const int maxt = (sizeof(T) == 8 && E >= 16) ? 512 : 1024;
+            if (threads > maxt) continue;
+            return E;
+        }
+        return 0;
+    }
+
+    template <int E> void launch_zsolve(bool gen, int grid, cudaStream_t st, const C *in, C *out, const PassGeom &g)
+    {
+        constexpr int TX = 128 / (int)sizeof(C);
+        ZSolveArgs<T> a;
+        a.ax = sym_tab[0]; a.ay = sym_tab[1];
+        a.lz = (T)zrec_lz;
+        a.scale = (T)((double)n[2] / (double)ntot);
+        a.n = n[2];
+        const int threads = n[2] / E * TX;
+        if (gen) zsolve_kernel<T, E, true><<<grid, threads, 0, st>>>(in, out, g, a);
+        else zsolve_kernel<T, E, false><<<grid, threads, 0, st>>>(in, out, g, a);
     }
 
     int set_symbol_transport(double lx, double ly, double lz) override
@@ -726,7 +799,7 @@ template <typename T> struct PlanT : PlanBase {
         CPC_CUDA(cudaGetLastError());
         CPC_CUDA(cudaStreamSynchronize(stream));
         if (tmp) cudaFree(tmp);
-        symbol_kind = CPC_SYMBOL_TABLE;
+        symbol_kind = CPC_SYMBOL_TABLE; zrec = false;
         return CPC_OK;
     }
 
@@ -744,7 +817,7 @@ template <typename T> struct PlanT : PlanBase {
         ++launches;
         CPC_CUDA(cudaGetLastError());
         CPC_CUDA(cudaStreamSynchronize(stream));
-        symbol_kind = CPC_SYMBOL_TABLE;
+        symbol_kind = CPC_SYMBOL_TABLE; zrec = false;
         return CPC_OK;
     }
 
@@ -754,7 +827,7 @@ template <typename T> struct PlanT : PlanBase {
         wave_c0 = c0;
         // degenerate axes contribute nothing (their root table is [1]: sin = 0, 1 - cos = 0)
         wave_mu[0] = mx; wave_mu[1] = my; wave_mu[2] = mz;
-        symbol_kind = CPC_SYMBOL_WAVE;
+        symbol_kind = CPC_SYMBOL_WAVE; zrec = false;
         return CPC_OK;
     }
 

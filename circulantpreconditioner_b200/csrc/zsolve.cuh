@@ -1,0 +1,157 @@
+// zsolve.cuh -- the middle pass for the transport symbol without any FFT along z.
+//
+// After the x and y transforms every z line (fixed kx, ky) is an independent 1-D circulant system.  With the
+// reference's upwind column c_z = [1, -1, 0, ...] (build_transport_col, src/FftLinearSolver_3D.c:80-90) and
+//   alpha = 1 + lambda_x c_x_hat[kx] + lambda_y c_y_hat[ky]            (build_diag_mat_vec_3D, :146-157)
+// the z part of  F^H (F b ./ Diag)  (solve_3D, :170-184) is exactly the solution of the cyclic bidiagonal system
+//   (alpha + lambda_z) x_k - lambda_z x_{k-1} = b_k ,   k = 0 .. nz-1,   x_{-1} = x_{nz-1},
+// because Diag[k] = alpha + lambda_z (1 - exp(-2 pi i k / nz)) is that circulant's spectrum.  With
+// r = 1 / (alpha + lambda_z) and c = lambda_z r (|c| < 1 since Re alpha >= 1 and lambda_z >= 0):
+//   y_k = c y_{k-1} + b_k ,  x_k = r y_k ,  and the cyclic closure  y_k = sum_{m < nz} c^m b_{k-m} / (1 - c^nz).
+// That is a first-order linear recurrence: ~20 flops per point instead of two 512-point FFTs plus a division
+// (~70 fp64 instructions per point in fft_r2x_kernel's fused mode), so the pass becomes purely HBM-bound.
+// It is the same linear operator as forward-z FFT, divide, backward-z FFT; the results agree to rounding
+// (7e-15 relative at lambda = 55.56, nz = 512; the plan only takes this path for 0 <= lambda_z <= 4096).
+//
+// Parallel form: a tile is TX neighbouring z lines (TX lanes x 16 B = one 128-byte row, as in fft_pass.cuh).
+// Thread (l, s) owns E consecutive points [sE, (s+1)E) of line l:
+//   1. local recurrence from a zero carry-in                                 (E complex FMAs)
+//   2. carries between segments: an inclusive scan over the QW = 32/TX segments of a warp with two
+//      shuffles, the warp aggregates through shared memory, and a Horner sum over the NW warps that also closes
+//      the cycle (factor 1 / (1 - c^nz))                                       (one block barrier)
+//   3. x_k = r (y_k + c^(k - sE + 1) carry) / (nx ny), stored straight to HBM (or pushed to a peer, GEN builds).
+#pragma once
+#include "fft_pass.cuh"
+
+namespace cpc {
+
+template <typename T> struct ZSolveArgs {
+    const cplx_t<T> *ax, *ay;     // lambda_x c_x_hat[kx]  and  1 + lambda_y c_y_hat[ky]   (the plan's symbol tables)
+    T lz;                         // lambda_z
+    T scale;                      // 1 / (nx ny): the x and y transforms are unnormalised, the z solve is exact
+    int n;                        // nz
+};
+
+// z^P by binary exponentiation, unrolled at compile time
+template <int P, typename C> __device__ __forceinline__ C cpow(C z)
+{
+    if constexpr (P == 1) return z;
+    else if constexpr (P % 2 == 0) { const C h = cpow<P / 2>(z); return cmul(h, h); }
+    else return cmul(z, cpow<P - 1>(z));
+}
+
+// largest CTA the kernel is compiled for: E = 16 complex128 points are 64 registers of data, so <= 128 registers
+template <typename T, int E> struct ZSolveMaxThreads { static constexpr int v = (sizeof(T) == 8 && E >= 16) ? 512 : 1024; };
+
+template <typename T, int E, bool GEN>
+__global__ void __launch_bounds__((ZSolveMaxThreads<T, E>::v), 1)
+zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g, const ZSolveArgs<T> a)
+{
+    using C = cplx_t<T>;
+    constexpr int TX = 128 / (int)sizeof(C);        // lanes = lines per tile
+    constexpr int QW = 32 / TX;                     // segments per warp
+    __shared__ C agg[32 * TX];                      // warp aggregates [warp][lane]
+
+    const int tid = threadIdx.x;
+    const int l = tid % TX;
+    const int seg = tid / TX;
+    const int q = seg % QW;                         // segment within the warp
+    const int wrp = tid >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const int k0 = seg * E;
+
+    const int t = blockIdx.x;
+    const int ti = t % g.tiles_inner, to = t / g.tiles_inner;
+    const int w = ti * TX + l;
+    const bool active = w < g.lines_inner;
+    const long long gbase = (long long)to * g.B1 + (long long)ti * g.B0 + (long long)l * g.SL;
+    const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)l * g.SLo;
+
+    C v[E];
+    if (active) {
+        if (!GEN) {
+            const C *p = in + gbase + (long long)k0 * g.SI;
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = p[m * g.SI];
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; ++m) v[m] = in[gbase + gen_in_off(g, k0 + m)];
+        }
+    } else {
+#pragma unroll
+        for (int m = 0; m < E; ++m) v[m] = mk<T>((T)0, (T)0);
+    }
+
+    // r = 1 / (alpha + lambda_z), c = lambda_z r
+    const int wc = active ? w : 0;
+    const int x = wc % g.nx, y = wc / g.nx + g.y0;
+    const C alpha = cadd(a.ax[x], a.ay[y]);
+    const C r = crecip_scaled<T>(mk<T>(alpha.x + a.lz, alpha.y), (T)1);
+    const C c = mk<T>(a.lz * r.x, a.lz * r.y);
+
+    // 1. local recurrence, zero carry-in
+#pragma unroll
+    for (int m = 1; m < E; ++m) {
+        v[m].x = fma(c.x, v[m - 1].x, fma(-c.y, v[m - 1].y, v[m].x));
+        v[m].y = fma(c.x, v[m - 1].y, fma(c.y, v[m - 1].x, v[m].y));
+    }
+    const C cE = cpow<E>(c);                        // c^E: the carry factor across one segment
+
+    // 2a. inclusive scan over the warp's QW segments: P_q = sum_{i <= q} cE^(q-i) e_i
+    C P = v[E - 1];
+    C cp = cE;
+#pragma unroll
+    for (int d = 1; d < QW; d <<= 1) {
+        C up;
+        up.x = __shfl_up_sync(0xffffffffu, P.x, d * TX);
+        up.y = __shfl_up_sync(0xffffffffu, P.y, d * TX);
+        if (q >= d) P = cadd(P, cmul(cp, up));
+        cp = cmul(cp, cp);
+    }
+    const C D = cp;                                 // cE^QW: the carry factor across one warp
+    C Pex;                                          // exclusive prefix: the carry from the segments before q in this warp
+    Pex.x = __shfl_up_sync(0xffffffffu, P.x, TX);
+    Pex.y = __shfl_up_sync(0xffffffffu, P.y, TX);
+    if (q == 0) Pex = mk<T>((T)0, (T)0);
+    if (q == QW - 1) agg[wrp * TX + l] = P;
+    __syncthreads();
+
+    // 2b. value at the end of the previous warp, cycle closed:
+    //     Z_{w-1} = sum_{m < NW} D^m A_{w-1-m} / (1 - D^NW)   (Horner over A_w, A_{w+1}, ..., A_{w-1})
+    C acc = mk<T>((T)0, (T)0), Dn = mk<T>((T)1, (T)0);
+    int idx = wrp;
+    for (int i = 0; i < nwarps; ++i) {
+        acc = cadd(cmul(D, acc), agg[idx * TX + l]);
+        Dn = cmul(Dn, D);
+        idx = (idx + 1 == nwarps) ? 0 : idx + 1;
+    }
+    const C Z = cmul(acc, crecip_scaled<T>(mk<T>((T)1 - Dn.x, -Dn.y), (T)1));
+    // carry into this segment: cE^q Z + Pex
+    C cq = mk<T>((T)1, (T)0);
+#pragma unroll
+    for (int i = 1; i < QW; ++i)
+        if (i <= q) cq = cmul(cq, cE);
+    const C carry = cadd(cmul(cq, Z), Pex);
+
+    // 3. x_k = r scale (y_k + c^(m+1) carry)
+    const C rs = mk<T>(r.x * a.scale, r.y * a.scale);
+    C cc = cmul(c, carry);
+#pragma unroll
+    for (int m = 0; m < E; ++m) {
+        v[m] = cmul(cadd(v[m], cc), rs);
+        cc = cmul(cc, c);
+    }
+
+    if (active) {
+        if (!GEN) {
+            C *p = out + obase + (long long)k0 * g.SIo;
+#pragma unroll
+            for (int m = 0; m < E; ++m) p[m * g.SIo] = v[m];
+        } else {
+#pragma unroll
+            for (int m = 0; m < E; ++m) *gen_out_ptr<C>(g, obase, k0 + m) = v[m];
+        }
+    }
+}
+
+}  // namespace cpc
