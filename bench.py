@@ -247,6 +247,7 @@ def run_gpu(args):
         acc = ms if acc is None else [a + m for a, m in zip(acc, ms)]
     pass_ms = [a / nprof for a in acc]
     dist_mode = plan.info()["dist_mode"]
+    middle = "cyclic first-order recurrence along z (zsolve.cuh)" if plan.info()["fast_path"][2] == 2 else "forward-z FFT, division, backward-z FFT fused"
     if world == 1:
         names = ["Fx", "Fy", "Fz*Lambda^-1*Bz", "By", "Bx"]
     elif dist_mode == 2:      # transposes fused into the passes (NVLink peer stores), stream-ordered barriers between
@@ -289,7 +290,7 @@ def run_gpu(args):
         apply_alg = 5 * bytes_pass
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "alg_bytes_per_launch": bytes_pass,
+                    "alg_bytes_per_launch": bytes_pass, "middle_pass": middle,
                     "passes": [{"name": nm, "ms": m, "GB/s": (bytes_pass / m / 1e6) if nm not in ("all-to-all", "barrier") else None}
                                for nm, m in zip(names, pass_ms)],
                     "apply": {"alg_bytes": apply_alg, "achieved": apply_alg / ms_step / 1e6,

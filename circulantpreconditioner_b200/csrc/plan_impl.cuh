@@ -273,6 +273,13 @@ template <typename T> struct PlanT : PlanBase {
         if (const char *pf = getenv("CPC_PREFETCH_WAVES")) pf_waves = atoi(pf);   // tuning hook
         if (const char *zs = getenv("CPC_ZSOLVE")) zrec_off = (atoi(zs) == 0);     // tuning hook
         zrec_e = zsolve_points_per_thread(n[2]);
+        if (const char *ze = getenv("CPC_ZSOLVE_E")) {                             // tuning hook: force E if it fits
+            constexpr int ZTX = 128 / (int)sizeof(C), ZQW = 32 / ZTX;
+            const int E = atoi(ze);
+            if ((E == 4 || E == 5 || E == 8 || E == 10 || E == 16) && n[2] % E == 0 && (n[2] / E) % ZQW == 0 &&
+                n[2] / E * ZTX <= ((sizeof(T) == 8 && E >= 16) ? 512 : 1024))
+                zrec_e = E;
+        }
         if (const char *sg = getenv("CPC_STAGGER")) stagger = atoi(sg);           // tuning hook
         CPC_TRACE("got smem attribute");
 
@@ -1256,6 +1263,9 @@ template <typename T> struct PlanT : PlanBase {
         info->passes_per_apply = 1 + 2 * ((n[0] > 1) + (n[1] > 1));
         info->dist_mode = desc.nranks == 1 ? 0 : (p2p ? 2 : 1);
         for (int a = 0; a < 3; ++a) info->fast_path[a] = cfg[a].fast ? 1 : 0;
+        if (symbol_kind == CPC_SYMBOL_SEPARABLE && zrec && !zrec_off && zrec_e > 0 && nc == 1 &&
+            (desc.nranks == 1 || (nzl & (nzl - 1)) == 0))
+            info->fast_path[2] = 2;
         info->local_elems = nloc;
         info->bytes_per_apply_alg = 5ll * 2 * nloc * (long long)(real ? sizeof(T) : sizeof(C));
         info->kernel_launches = launches;

@@ -15,7 +15,7 @@
 //
 // Parallel form: a tile is TX neighbouring z lines (TX lanes x 16 B = one 128-byte row, as in fft_pass.cuh).
 // Thread (l, s) owns E consecutive points [sE, (s+1)E) of line l:
-//   1. local recurrence from a zero carry-in                                 (E complex FMAs)
+//   1. local recurrence from a zero carry-in, in independent blocks of 4 (or 5) points        (E complex FMAs)
 //   2. carries between segments: an inclusive scan over the QW = 32/TX segments of a warp with two
 //      shuffles, the warp aggregates through shared memory, and a Horner sum over the NW warps that also closes
 //      the cycle (factor 1 / (1 - c^nz))                                       (one block barrier)
@@ -89,16 +89,29 @@ zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, con
     const C r = crecip_scaled<T>(mk<T>(alpha.x + a.lz, alpha.y), (T)1);
     const C c = mk<T>(a.lz * r.x, a.lz * r.y);
 
-    // 1. local recurrence, zero carry-in
+    // 1. local recurrence from a zero carry-in, in NB independent blocks of B points so that the dependent chain is
+    //    B - 1 + NB - 1 complex FMAs deep instead of E - 1; the blocks' carries t[] are folded into step 3.
+    constexpr int B = (E % 4 == 0) ? 4 : 5, NB = E / B;
+    C pw[B];                                        // c^(j+1)
+    pw[0] = c;
 #pragma unroll
-    for (int m = 1; m < E; ++m) {
-        v[m].x = fma(c.x, v[m - 1].x, fma(-c.y, v[m - 1].y, v[m].x));
-        v[m].y = fma(c.x, v[m - 1].y, fma(c.y, v[m - 1].x, v[m].y));
+    for (int j = 1; j < B; ++j) pw[j] = cmul(pw[(j - 1) / 2], pw[j / 2]);      // c^(j+1) = c^(floor((j+1)/2)) c^(ceil((j+1)/2))
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+        for (int j = 1; j < B; ++j) {
+            v[b * B + j].x = fma(c.x, v[b * B + j - 1].x, fma(-c.y, v[b * B + j - 1].y, v[b * B + j].x));
+            v[b * B + j].y = fma(c.x, v[b * B + j - 1].y, fma(c.y, v[b * B + j - 1].x, v[b * B + j].y));
+        }
     }
-    const C cE = cpow<E>(c);                        // c^E: the carry factor across one segment
+    C tb[NB];                                       // value at the end of block b with a zero carry into the segment
+    tb[0] = v[B - 1];
+#pragma unroll
+    for (int b = 1; b < NB; ++b) tb[b] = cadd(v[b * B + B - 1], cmul(pw[B - 1], tb[b - 1]));
+    const C cE = cpow<NB>(pw[B - 1]);               // c^E: the carry factor across one segment
 
     // 2a. inclusive scan over the warp's QW segments: P_q = sum_{i <= q} cE^(q-i) e_i
-    C P = v[E - 1];
+    C P = tb[NB - 1];
     C cp = cE;
 #pragma unroll
     for (int d = 1; d < QW; d <<= 1) {
@@ -133,13 +146,15 @@ zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, con
         if (i <= q) cq = cmul(cq, cE);
     const C carry = cadd(cmul(cq, Z), Pex);
 
-    // 3. x_k = r scale (y_k + c^(m+1) carry)
+    // 3. x_k = r scale (y_k + c^(j+1) H_b),  H_b = carry into block b = t_{b-1} + c^(bB) carry
     const C rs = mk<T>(r.x * a.scale, r.y * a.scale);
-    C cc = cmul(c, carry);
+    C G = carry;
 #pragma unroll
-    for (int m = 0; m < E; ++m) {
-        v[m] = cmul(cadd(v[m], cc), rs);
-        cc = cmul(cc, c);
+    for (int b = 0; b < NB; ++b) {
+        const C H = (b == 0) ? carry : cadd(tb[b - 1], G);
+#pragma unroll
+        for (int j = 0; j < B; ++j) v[b * B + j] = cmul(cadd(v[b * B + j], cmul(pw[j], H)), rs);
+        G = cmul(G, pw[B - 1]);
     }
 
     if (active) {

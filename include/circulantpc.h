@@ -142,7 +142,9 @@ typedef struct {
     int passes_per_apply;          /* HBM passes (kernel launches) of one cpc_apply */
     int dist_mode;                 /* 0 single rank, 1 NCCL all-to-all transposes, 2 transposes fused into the passes
                                       (stores pushed to IPC-mapped peer buffers over NVLink) */
-    int fast_path[3];              /* 1 if axis x/y/z runs the templated Stockham kernel, 0 = generic kernel */
+    int fast_path[3];              /* 1 if axis x/y/z runs the templated Stockham kernel, 0 = generic kernel;
+                                      [2] == 2: the middle pass of the current (transport) symbol is solved as a cyclic
+                                      first-order recurrence along z instead of forward FFT, division, backward FFT */
     int64_t local_elems;           /* elements (of ncomp * cells) held by this rank */
     int64_t bytes_per_apply_alg;   /* 5 passes x 2 x local_elems x sizeof(elem): SURVEY.md 8(d) */
     uint64_t kernel_launches;      /* running count of kernels launched by this plan */

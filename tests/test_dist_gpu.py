@@ -61,7 +61,7 @@ def _run(shape, lam, ncomp=1, wave=False, P=2):
     return dict(errs)
 
 
-@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 32, 16), (32, 16, 256), (20, 12, 10)])
+@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 32, 16), (32, 16, 256), (20, 12, 10), (96, 48, 24), (16, 32, 1024)])
 def test_two_rank_transport(shape):
     errs = _run(shape, (55.5556, 0.3, 2.5))
     for r, (e1, e2, e3) in errs.items():

@@ -150,6 +150,61 @@ def test_apply_transport_matches_oracle(shape):
         assert rel_l2(host(d), want) < TOL64
 
 
+# the middle pass of a transport symbol: cyclic first-order recurrence along z (csrc/zsolve.cuh) against the
+# forward-FFT / divide / backward-FFT form of the reference (solve_3D, src/FftLinearSolver_3D.c:170-184)
+@pytest.mark.parametrize("shape", [(64, 32, 512), (24, 16, 384), (8, 8, 96), (8, 8, 100), (4, 4, 1000), (16, 16, 16),
+                                   (40, 3, 1024), (8, 5, 200), (12, 7, 64)])
+def test_middle_pass_recurrence_matches_fft_form(shape, monkeypatch):
+    nx, ny, nz = shape
+    rng = np.random.default_rng(nx + 3 * ny + 7 * nz)
+    lam = (55.5556, 55.5556, 55.5556)
+    b = rand_c(rng, nx * ny * nz)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b)
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        p.set_symbol_transport(*lam)
+        assert p.info()["fast_path"][2] == 2
+        rec = host(p.apply(dev(b)))
+    monkeypatch.setenv("CPC_ZSOLVE", "0")
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        p.set_symbol_transport(*lam)
+        assert p.info()["fast_path"][2] != 2
+        fft = host(p.apply(dev(b)))
+    assert rel_l2(rec, want) < TOL64
+    assert rel_l2(fft, want) < TOL64
+    assert rel_l2(rec, fft) < TOL64
+
+
+def test_middle_pass_recurrence_gating():
+    nx, ny, nz = 32, 16, 64
+    rng = np.random.default_rng(5)
+    b = rand_c(rng, nx * ny * nz)
+    col_hat = [np.fft.fft(O.build_transport_col(n)) for n in (nx, ny, nz)]
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        # the same tables through the separable entry point (what Fft3DSolver does): recognised
+        p.set_symbol_separable(*col_hat, 2.0, 0.5, 3.0)
+        assert p.info()["fast_path"][2] == 2
+        assert rel_l2(host(p.apply(dev(b))), O.FftTransportSolver(nx, ny, nz, 2.0, 0.5, 3.0, b)) < TOL64
+        # large lambda_z, still inside the gate
+        p.set_symbol_transport(1.0, 1.0, 4000.0)
+        assert p.info()["fast_path"][2] == 2
+        assert rel_l2(host(p.apply(dev(b))), O.FftTransportSolver(nx, ny, nz, 1.0, 1.0, 4000.0, b)) < TOL64
+        # outside: negative or huge lambda_z, a negative lambda_x, a z table that is not the upwind column, other symbols
+        for lam in ((1.0, 1.0, -0.2), (1.0, 1.0, 1e5), (-0.2, 1.0, 1.0)):
+            p.set_symbol_transport(*lam)
+            assert p.info()["fast_path"][2] != 2
+            assert rel_l2(host(p.apply(dev(b))), O.FftTransportSolver(nx, ny, nz, *lam, b)) < 1e-11
+        cz = col_hat[2].copy()
+        cz[3] += 0.25
+        p.set_symbol_separable(col_hat[0], col_hat[1], cz, 2.0, 0.5, 3.0)
+        assert p.info()["fast_path"][2] != 2
+        diag = O.build_diag_mat_vec_3D(col_hat[0], col_hat[1], cz, nx, ny, nz, 2.0, 0.5, 3.0)
+        assert rel_l2(host(p.apply(dev(b))), O.solve_3D(diag, b, nx, ny, nz)) < TOL64
+        p.set_symbol_diag(diag)
+        assert p.info()["fast_path"][2] != 2
+        p.set_symbol_transport(2.0, 0.5, 3.0)
+        assert p.info()["fast_path"][2] == 2
+
+
 def test_general_first_column_and_diag_table():
     nx, ny, nz = 32, 16, 64
     rng = np.random.default_rng(3)
