@@ -42,7 +42,7 @@ def workload_config(n_gpus):
         "workload": f"scalar circulant PC apply, {N_GRID}^3 complex128, lambda=({LAMBDA[0]},)*3 "
                     "(BASELINE.json config 4 at the size the metric is quoted on)",
         "grid": [N_GRID, N_GRID, N_GRID],
-        "decomposition": "single GPU, 5 HBM passes" if n_gpus == 1 else f"z-slabs over {n_gpus} ranks, 2 NCCL all-to-all per apply",
+        "decomposition": "single GPU, 5 HBM passes" if n_gpus == 1 else f"z-slabs over {n_gpus} ranks, one process per GPU",
         "l2_policy": "inputs larger than L2 (2.1 GB array vs 126 MB L2); no explicit flush",
     }
 
@@ -250,6 +250,8 @@ def run_gpu(args):
     middle = "cyclic first-order recurrence along z (zsolve.cuh)" if plan.info()["fast_path"][2] == 2 else "forward-z FFT, division, backward-z FFT fused"
     if world == 1:
         names = ["Fx", "Fy", "Fz*Lambda^-1*Bz", "By", "Bx"]
+    elif dist_mode == 3:      # no transposes: z recurrence on the local slab, one carry per (kx, ky) line all-gathered
+        names = ["Fx", "Fy", "z end values + carry all-gather", "Fz*Lambda^-1*Bz (z solve with carries)", "By", "Bx"]
     elif dist_mode == 2:      # transposes fused into the passes (NVLink peer stores), stream-ordered barriers between
         names = ["Fx", "Fy+transpose", "barrier", "Fz*Lambda^-1*Bz+transpose", "barrier", "By", "Bx"]
     else:
@@ -277,7 +279,7 @@ def run_gpu(args):
     if rank == 0:
         peak, peak_src = measured_peaks()
         bytes_pass = 2 * nloc * ELEM_BYTES
-        kern = [(nm, m) for nm, m in zip(names, pass_ms) if nm not in ("all-to-all", "barrier")]
+        kern = [(nm, m) for nm, m in zip(names, pass_ms) if nm not in ("all-to-all", "barrier") and "all-gather" not in nm]
         dom_name, dom_ms = max(kern, key=lambda kv: kv[1])
         achieved = bytes_pass / dom_ms / 1e6
         traffic = None
@@ -291,11 +293,16 @@ def run_gpu(args):
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": bytes_pass, "middle_pass": middle,
-                    "passes": [{"name": nm, "ms": m, "GB/s": (bytes_pass / m / 1e6) if nm not in ("all-to-all", "barrier") else None}
+                    "passes": [{"name": nm, "ms": m, "GB/s": (bytes_pass / m / 1e6) if nm not in ("all-to-all", "barrier") and "all-gather" not in nm else None}
                                for nm, m in zip(names, pass_ms)],
                     "apply": {"alg_bytes": apply_alg, "achieved": apply_alg / ms_step / 1e6,
                               "frac": apply_alg / ms_step / 1e6 / peak}}
-        if world > 1:
+        if world > 1 and dist_mode == 3:
+            roofline["carry_exchange"] = {
+                "how": "read-only sweep for the slab's end values + ncclAllGather; replaces both global transposes",
+                "bytes_gathered_per_gpu": N_GRID * N_GRID * ELEM_BYTES * world,
+                "ms": pass_ms[names.index("z end values + carry all-gather")] if "z end values + carry all-gather" in names else None}
+        elif world > 1:
             sent = nloc * ELEM_BYTES * (world - 1) / world
             if dist_mode == 2:
                 # the transpose travels inside the producing kernel; charge kernel + the barrier that follows it

@@ -198,4 +198,15 @@ int dist_barrier(DistState &d, cudaStream_t stream)
     return CPC_OK;
 }
 
+// Every rank contributes `bytes` from send; recv holds the P contributions in rank order.
+int dist_allgather(DistState &d, const void *send, void *recv, size_t bytes, cudaStream_t stream)
+{
+    if (d.nranks == 1) {
+        if (send != recv) CPC_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, stream));
+        return CPC_OK;
+    }
+    CPC_NCCL(g_api.AllGather(send, recv, bytes, NCCL_UINT8, (ncclComm_tt)d.comm, stream));
+    return CPC_OK;
+}
+
 }  // namespace cpc

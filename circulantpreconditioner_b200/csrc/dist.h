@@ -21,6 +21,8 @@ void dist_destroy(DistState &d);
 // Rank r sends bytes [q*chunk_bytes, (q+1)*chunk_bytes) of `send` to rank q and receives rank s's chunk into
 // recv + s*chunk_bytes (grouped ncclSend/ncclRecv: NCCL 2.27 has no all-to-all entry point).
 int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes, cudaStream_t stream);
+// ncclAllGather of `bytes` per rank (the z-slab carry exchange of the recurrence middle pass, zsolve.cuh).
+int dist_allgather(DistState &d, const void *send, void *recv, size_t bytes, cudaStream_t stream);
 // Stream-ordered barrier across ranks (1-element all-reduce).
 int dist_barrier(DistState &d, cudaStream_t stream);
 // Exchange CUDA IPC handles of `local` (a cudaMalloc'ed buffer) through an NCCL all-gather and map every peer's

@@ -135,7 +135,7 @@ template <typename T> struct PlanT : PlanBase {
     struct AxisCfg {
         bool fast = false;
         int variant = 0;          // enum Variant of the fast kernel
-        int variant_fwd = -1;     // >= 0: a different variant for the plain forward pass (same tile width)
+        int variant_local = -1;   // >= 0: multi-rank plans, variant for plain passes on the local slab (same tile width)
         int nfast = 0;            // transform length of the fast kernel (nx/2 for the r2c / c2r pass)
         int tx = 1;               // lanes per tile
         int threads = 0;          // generic kernel block size
@@ -167,7 +167,7 @@ template <typename T> struct PlanT : PlanBase {
     AxisCfg cfg[3];
     C *tw[3] = { nullptr, nullptr, nullptr };    // roots exp(-2 pi i m / n)
     C *stw[3] = { nullptr, nullptr, nullptr };   // per-stage twiddle tables of the fast kernel chosen for the axis
-    C *stw_fwd[3] = { nullptr, nullptr, nullptr };   // same for the separate forward-only variant, if any
+    C *stw_local[3] = { nullptr, nullptr, nullptr };   // stage tables of variant_local, if any
 
     // symbol state
     C *sym_tab[3] = { nullptr, nullptr, nullptr };       // ax, ay(+1), az in T
@@ -192,6 +192,9 @@ template <typename T> struct PlanT : PlanBase {
     // multi-rank
     DistState dist;
     C *sendbuf = nullptr, *tbuf = nullptr;
+    // z-slab recurrence (multi-rank transport symbol): this rank's line-end values and every rank's, [P][nx ny]
+    C *ebuf = nullptr, *ecat = nullptr;
+    int zslab_e = 0;              // points per thread for nz / P point lines (0: no fit, keep the transposing path)
     bool p2p = false;                         // peers' buffers are IPC-mapped: transposes are fused into the passes
     void *peer_t[CPC_MAX_PEERS] = {}, *peer_s[CPC_MAX_PEERS] = {};
 
@@ -201,7 +204,7 @@ template <typename T> struct PlanT : PlanBase {
         for (int a = 0; a < 3; ++a) {
             if (tw[a]) cudaFree(tw[a]);
             if (stw[a]) cudaFree(stw[a]);
-            if (stw_fwd[a]) cudaFree(stw_fwd[a]);
+            if (stw_local[a]) cudaFree(stw_local[a]);
             if (sym_tab[a]) cudaFree(sym_tab[a]);
             if (sym_tab64[a]) cudaFree(sym_tab64[a]);
         }
@@ -218,6 +221,8 @@ template <typename T> struct PlanT : PlanBase {
             cudaStreamSynchronize(stream);
         }
         if (sendbuf) cudaFree(sendbuf);
+        if (ebuf) cudaFree(ebuf);
+        if (ecat) cudaFree(ecat);
         if (tbuf) cudaFree(tbuf);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         for (auto e : chunk_ev) cudaEventDestroy(e);
@@ -349,6 +354,14 @@ template <typename T> struct PlanT : PlanBase {
                 c.tx = it->second.tx;
                 int rc_t = build_stage_table(it->second.radix, &stw[a]);
                 if (rc_t) return rc_t;
+                // multi-rank: the 2 x (R0 x R1) kernel for y passes that run on the local slab (no split)
+                if (a == 1 && desc.nranks > 1 && (n[a] == 512 || n[a] == 256) && var != VAR_R2X) {
+                    auto il = reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FWD));
+                    if (il != reg.end() && il->second.tx == it->second.tx && il->second.smem <= (size_t)dev_smem) {
+                        c.variant_local = VAR_R2X;
+                        if ((rc_t = build_stage_table(il->second.radix, &stw_local[a]))) return rc_t;
+                    }
+                }
             } else {
                 c.fast = false;
                 c.fl.n = n[a];
@@ -435,6 +448,11 @@ template <typename T> struct PlanT : PlanBase {
         if (desc.nranks > 1) {
             int rc = dist_init(dist, desc.nranks, desc.rank, desc.nccl_unique_id, device);
             if (rc) return rc;
+            if (!real && nc == 1) {
+                zslab_e = zsolve_points_per_thread(nzl);
+                CPC_CUDA(cudaMalloc(&ebuf, sizeof(C) * (size_t)n[0] * n[1]));
+                CPC_CUDA(cudaMalloc(&ecat, sizeof(C) * (size_t)n[0] * n[1] * desc.nranks));
+            }
             CPC_CUDA(cudaMalloc(&sendbuf, sizeof(C) * nloc));
             CPC_CUDA(cudaMalloc(&tbuf, sizeof(C) * nloc));
             // Fused transposes need every peer's buffers mapped (CUDA IPC over NVLink); otherwise NCCL all-to-all.
@@ -606,14 +624,7 @@ template <typename T> struct PlanT : PlanBase {
                 if (g.npeer == 0)
                     for (int q = 0; q < CPC_MAX_PEERS; ++q) g.peer[q] = (void *)(out + off);
             }
-            const bool gen = split != 0;
-            switch (zrec_e) {
-            case 16: launch_zsolve<16>(gen, g.ntiles, st, in + off, out + off, g); break;
-            case 8: launch_zsolve<8>(gen, g.ntiles, st, in + off, out + off, g); break;
-            case 10: launch_zsolve<10>(gen, g.ntiles, st, in + off, out + off, g); break;
-            case 5: launch_zsolve<5>(gen, g.ntiles, st, in + off, out + off, g); break;
-            default: launch_zsolve<4>(gen, g.ntiles, st, in + off, out + off, g); break;
-            }
+            launch_zsolve_e(zrec_e, ZS_CYCLIC, split != 0, n[2], g.ntiles, st, in + off, out + off, g);
         } else if (c.fast) {
             // multi-rank y / z passes need the general-addressing build (init() made sure it exists)
             if (split != 0) {
@@ -625,11 +636,12 @@ template <typename T> struct PlanT : PlanBase {
                     for (int q = 0; q < CPC_MAX_PEERS; ++q) g.peer[q] = (void *)(out + off);
                 if (g.shi < 0 || g.sho < 0) { set_error("multi-rank fast path needs power-of-two ny/nranks and nz/nranks"); return CPC_ERR_UNSUPPORTED; }
             }
-            const bool alt = (mode == MODE_FWD && c.variant_fwd >= 0);
-            const FastEntry<T> &e = reg.at(FastKey<T>(c.nfast, alt ? c.variant_fwd : c.variant, mode + (split != 0 ? GEN_BIT : 0)));
+            // y passes that stay on the local z-slab (the z-slab recurrence path) need no chunked addressing
+            const bool alt = c.variant_local >= 0 && split == 0 && layout == 0 && (mode == MODE_FWD || mode == MODE_INV);
+            const FastEntry<T> &e = reg.at(FastKey<T>(c.nfast, alt ? c.variant_local : c.variant, mode + (split != 0 ? GEN_BIT : 0)));
             const int grid = (g.ntiles + e.g - 1) / e.g;
             g.pf_tiles = pf_waves > 0 ? pf_waves * num_sms * e.g : 0;
-            e.kern<<<grid, e.threads, e.smem, st>>>(in + off, out + off, g, alt ? stw_fwd[axis] : stw[axis], s);
+            e.kern<<<grid, e.threads, e.smem, st>>>(in + off, out + off, g, alt ? stw_local[axis] : stw[axis], s);
         } else {
             generic_pass_kernel<T><<<g.ntiles, c.threads, c.smem_generic, st>>>(in + off, out + off, g, tw[axis], s,
                                                                                c.fl, c.tx, mode);
@@ -749,17 +761,46 @@ template <typename T> struct PlanT : PlanBase {
         return 0;
     }
 
-    template <int E> void launch_zsolve(bool gen, int grid, cudaStream_t st, const C *in, C *out, const PassGeom &g)
+    ZSolveArgs<T> zsolve_args() const
     {
-        constexpr int TX = 128 / (int)sizeof(C);
-        ZSolveArgs<T> a;
+        ZSolveArgs<T> a{};
         a.ax = sym_tab[0]; a.ay = sym_tab[1];
         a.lz = (T)zrec_lz;
         a.scale = (T)((double)n[2] / (double)ntot);
         a.n = n[2];
-        const int threads = n[2] / E * TX;
-        if (gen) zsolve_kernel<T, E, true><<<grid, threads, 0, st>>>(in, out, g, a);
+        a.ecat = ecat; a.eout = ebuf;
+        a.nranks = desc.nranks; a.rank = desc.rank;
+        return a;
+    }
+
+    // nline = points of the z line a tile holds (nz, or nz / P for the z-slab sweeps)
+    template <int E> void launch_zsolve(int kind, bool gen, int nline, int grid, cudaStream_t st, const C *in, C *out,
+                                        const PassGeom &g)
+    {
+        constexpr int TX = 128 / (int)sizeof(C);
+        const ZSolveArgs<T> a = zsolve_args();
+        const int threads = nline / E * TX;
+        if (kind == ZS_END) zsolve_kernel<T, E, false, ZS_END><<<grid, threads, 0, st>>>(in, out, g, a);
+        else if (kind == ZS_DIST) zsolve_kernel<T, E, false, ZS_DIST><<<grid, threads, 0, st>>>(in, out, g, a);
+        else if (gen) zsolve_kernel<T, E, true><<<grid, threads, 0, st>>>(in, out, g, a);
         else zsolve_kernel<T, E, false><<<grid, threads, 0, st>>>(in, out, g, a);
+    }
+    void launch_zsolve_e(int e, int kind, bool gen, int nline, int grid, cudaStream_t st, const C *in, C *out,
+                         const PassGeom &g)
+    {
+        switch (e) {
+        case 16: launch_zsolve<16>(kind, gen, nline, grid, st, in, out, g); break;
+        case 8: launch_zsolve<8>(kind, gen, nline, grid, st, in, out, g); break;
+        case 10: launch_zsolve<10>(kind, gen, nline, grid, st, in, out, g); break;
+        case 5: launch_zsolve<5>(kind, gen, nline, grid, st, in, out, g); break;
+        default: launch_zsolve<4>(kind, gen, nline, grid, st, in, out, g); break;
+        }
+    }
+
+    // z-slab plans with a transport symbol: no transpose at all (zsolve.cuh)
+    bool use_zslab() const
+    {
+        return desc.nranks > 1 && symbol_kind == CPC_SYMBOL_SEPARABLE && zrec && !zrec_off && zslab_e > 0 && ebuf && ecat;
     }
 
     int set_symbol_transport(double lx, double ly, double lz) override
@@ -924,8 +965,51 @@ template <typename T> struct PlanT : PlanBase {
         return dist_alltoall(dist, send, recv, chunk, stream);
     }
 
+    // Multi-rank apply for a transport symbol: Fx, Fy on the local z-slab, the z recurrence in two local sweeps with
+    // an all-gather of the slabs' end values in between (nx ny complex numbers per rank), By, Bx.  No transposes.
+    int apply_device_zslab(const C *b, C *x, float *pass_ms, int *npasses)
+    {
+        int np = 0, rc;
+        auto mark = [&](int i) -> int {
+            if (pass_ms) CPC_CUDA(cudaEventRecord(prof_ev[i], stream));
+            return CPC_OK;
+        };
+        if (pass_ms && (rc = ensure_prof_events())) return rc;
+        if ((rc = mark(0))) return rc;
+        const C *cur = b;
+        for (int a = 0; a < 2; ++a) {
+            if (n[a] == 1) continue;
+            if ((rc = run_pass(a, MODE_FWD, cur, x, 0, nzl, 0, stream))) return rc;
+            cur = x;
+            if ((rc = mark(++np))) return rc;
+        }
+        long long off = 0;
+        const PassGeom g = make_geom(2, 128 / (int)sizeof(C), 0, nzl, 0, &off);
+        launch_zsolve_e(zslab_e, ZS_END, false, nzl, g.ntiles, stream, cur, x, g);
+        ++launches;
+        CPC_CUDA(cudaGetLastError());
+        if ((rc = dist_allgather(dist, ebuf, ecat, sizeof(C) * (size_t)n[0] * n[1], stream))) return rc;
+        if ((rc = mark(++np))) return rc;
+        launch_zsolve_e(zslab_e, ZS_DIST, false, nzl, g.ntiles, stream, cur, x, g);
+        ++launches;
+        CPC_CUDA(cudaGetLastError());
+        if ((rc = mark(++np))) return rc;
+        for (int a = 1; a >= 0; --a) {
+            if (n[a] == 1) continue;
+            if ((rc = run_pass(a, MODE_INV, x, x, 0, nzl, 0, stream))) return rc;
+            if ((rc = mark(++np))) return rc;
+        }
+        if (pass_ms) {
+            CPC_CUDA(cudaEventSynchronize(prof_ev[np]));
+            for (int i = 0; i < np; ++i) CPC_CUDA(cudaEventElapsedTime(&pass_ms[i], prof_ev[i], prof_ev[i + 1]));
+            if (npasses) *npasses = np;
+        }
+        return CPC_OK;
+    }
+
     int apply_device_dist(const C *b, C *x, float *pass_ms, int *npasses)
     {
+        if (use_zslab()) return apply_device_zslab(b, x, pass_ms, npasses);
         const int fm = fused_mode();
         int np = 0, rc;
         auto mark = [&](int i) -> int {
@@ -1261,10 +1345,10 @@ template <typename T> struct PlanT : PlanBase {
         info->nranks = desc.nranks; info->rank = desc.rank;
         info->symbol_kind = symbol_kind;
         info->passes_per_apply = 1 + 2 * ((n[0] > 1) + (n[1] > 1));
-        info->dist_mode = desc.nranks == 1 ? 0 : (p2p ? 2 : 1);
+        info->dist_mode = desc.nranks == 1 ? 0 : (use_zslab() ? 3 : (p2p ? 2 : 1));
         for (int a = 0; a < 3; ++a) info->fast_path[a] = cfg[a].fast ? 1 : 0;
         if (symbol_kind == CPC_SYMBOL_SEPARABLE && zrec && !zrec_off && zrec_e > 0 && nc == 1 &&
-            (desc.nranks == 1 || (nzl & (nzl - 1)) == 0))
+            (desc.nranks == 1 || (nzl & (nzl - 1)) == 0 || use_zslab()))
             info->fast_path[2] = 2;
         info->local_elems = nloc;
         info->bytes_per_apply_alg = 5ll * 2 * nloc * (long long)(real ? sizeof(T) : sizeof(C));

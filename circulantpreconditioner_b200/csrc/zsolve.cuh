@@ -20,6 +20,11 @@
 //      shuffles, the warp aggregates through shared memory, and a Horner sum over the NW warps that also closes
 //      the cycle (factor 1 / (1 - c^nz))                                       (one block barrier)
 //   3. x_k = r (y_k + c^(k - sE + 1) carry) / (nx ny), stored straight to HBM (or pushed to a peer, GEN builds).
+//
+// z-slab plans (one process per GPU) need NO transpose for this pass: a recurrence only hands a carry from one slab to
+// the next.  Sweep 1 (ZS_END, read-only) computes the value at the end of every local line from a zero carry-in,
+// the P x nx x ny end values are all-gathered (4 MB per rank at 512^2 instead of two 2 GB all-to-alls per apply), and
+// sweep 2 (ZS_DIST) solves the local lines with the carry that closes the cycle over the ranks.
 #pragma once
 #include "fft_pass.cuh"
 
@@ -30,6 +35,17 @@ template <typename T> struct ZSolveArgs {
     T lz;                         // lambda_z
     T scale;                      // 1 / (nx ny): the x and y transforms are unnormalised, the z solve is exact
     int n;                        // nz
+    // z-slab plans (DIST builds): the line is this rank's nz / P planes; the carry into its first plane comes from the
+    // end values of every rank's slab (zero carry-in), all-gathered into ecat[P][nx ny]
+    const cplx_t<T> *ecat;
+    cplx_t<T> *eout;              // END builds: where this rank's end values go, [nx ny]
+    int nranks, rank;
+};
+
+enum ZSolveKind {
+    ZS_CYCLIC = 0,    // the whole z line is in the tile: close the cycle inside the kernel (single GPU, transposed slabs)
+    ZS_END = 1,       // z-slab plans, first sweep: only the value at the end of the local line, zero carry-in (read-only)
+    ZS_DIST = 2       // z-slab plans, second sweep: the local line with the carry computed from ecat
 };
 
 // z^P by binary exponentiation, unrolled at compile time
@@ -43,7 +59,7 @@ template <int P, typename C> __device__ __forceinline__ C cpow(C z)
 // largest CTA the kernel is compiled for: E = 16 complex128 points are 64 registers of data, so <= 128 registers
 template <typename T, int E> struct ZSolveMaxThreads { static constexpr int v = (sizeof(T) == 8 && E >= 16) ? 512 : 1024; };
 
-template <typename T, int E, bool GEN>
+template <typename T, int E, bool GEN, int KIND = ZS_CYCLIC>
 __global__ void __launch_bounds__((ZSolveMaxThreads<T, E>::v), 1)
 zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g, const ZSolveArgs<T> a)
 {
@@ -129,16 +145,43 @@ zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, con
     if (q == QW - 1) agg[wrp * TX + l] = P;
     __syncthreads();
 
-    // 2b. value at the end of the previous warp, cycle closed:
-    //     Z_{w-1} = sum_{m < NW} D^m A_{w-1-m} / (1 - D^NW)   (Horner over A_w, A_{w+1}, ..., A_{w-1})
-    C acc = mk<T>((T)0, (T)0), Dn = mk<T>((T)1, (T)0);
-    int idx = wrp;
-    for (int i = 0; i < nwarps; ++i) {
-        acc = cadd(cmul(D, acc), agg[idx * TX + l]);
-        Dn = cmul(Dn, D);
-        idx = (idx + 1 == nwarps) ? 0 : idx + 1;
+    // 2b. value carried into this warp
+    C Z;
+    if constexpr (KIND == ZS_CYCLIC) {
+        // cycle closed: Z_{w-1} = sum_{m < NW} D^m A_{w-1-m} / (1 - D^NW)   (Horner over A_w, A_{w+1}, ..., A_{w-1})
+        C acc = mk<T>((T)0, (T)0), Dn = mk<T>((T)1, (T)0);
+        int idx = wrp;
+        for (int i = 0; i < nwarps; ++i) {
+            acc = cadd(cmul(D, acc), agg[idx * TX + l]);
+            Dn = cmul(Dn, D);
+            idx = (idx + 1 == nwarps) ? 0 : idx + 1;
+        }
+        Z = cmul(acc, crecip_scaled<T>(mk<T>((T)1 - Dn.x, -Dn.y), (T)1));
+    } else if constexpr (KIND == ZS_END) {
+        // value at the end of the local line with a zero carry-in: sum_w D^(NW-1-w) A_w; one 128-byte row per tile
+        if (wrp == nwarps - 1 && q == QW - 1) {
+            C acc = mk<T>((T)0, (T)0);
+            for (int i = 0; i < nwarps; ++i) acc = cadd(cmul(D, acc), agg[i * TX + l]);
+            if (active) a.eout[w] = acc;
+        }
+        return;
+    } else {
+        // carry into the local line: the other slabs' end values with the cycle closed over the P ranks,
+        //   Zin = sum_{m < P} cL^m e_{rank-1-m} / (1 - cL^P),  cL = c^(nz / P) = D^NW;
+        // then through the warps before this one: Z = D^wrp Zin + sum_{i < wrp} D^(wrp-1-i) A_i
+        C cL = mk<T>((T)1, (T)0);
+        for (int i = 0; i < nwarps; ++i) cL = cmul(cL, D);
+        C acc = mk<T>((T)0, (T)0), cLp = mk<T>((T)1, (T)0);
+        int idx = a.rank;
+        const long long plane = (long long)g.lines_inner;
+        for (int i = 0; i < a.nranks; ++i) {
+            acc = cadd(cmul(cL, acc), a.ecat[idx * plane + wc]);
+            cLp = cmul(cLp, cL);
+            idx = (idx + 1 == a.nranks) ? 0 : idx + 1;
+        }
+        Z = cmul(acc, crecip_scaled<T>(mk<T>((T)1 - cLp.x, -cLp.y), (T)1));
+        for (int i = 0; i < wrp; ++i) Z = cadd(cmul(D, Z), agg[i * TX + l]);
     }
-    const C Z = cmul(acc, crecip_scaled<T>(mk<T>((T)1 - Dn.x, -Dn.y), (T)1));
     // carry into this segment: cE^q Z + Pex
     C cq = mk<T>((T)1, (T)0);
 #pragma unroll

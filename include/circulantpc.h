@@ -141,7 +141,9 @@ typedef struct {
     int symbol_kind;
     int passes_per_apply;          /* HBM passes (kernel launches) of one cpc_apply */
     int dist_mode;                 /* 0 single rank, 1 NCCL all-to-all transposes, 2 transposes fused into the passes
-                                      (stores pushed to IPC-mapped peer buffers over NVLink) */
+                                      (stores pushed to IPC-mapped peer buffers over NVLink), 3 no transposes: the
+                                      current (transport) symbol's middle pass is a recurrence along z, the z-slabs
+                                      only all-gather one carry per (kx, ky) line */
     int fast_path[3];              /* 1 if axis x/y/z runs the templated Stockham kernel, 0 = generic kernel;
                                       [2] == 2: the middle pass of the current (transport) symbol is solved as a cyclic
                                       first-order recurrence along z instead of forward FFT, division, backward FFT */
