@@ -258,6 +258,34 @@ def run_gpu(args):
         names = ["Fx", "Fy", "all-to-all", "Fz*Lambda^-1*Bz", "all-to-all", "By", "Bx"]
     names = names[:len(pass_ms)]
 
+    # for comparison: the same symbol through the general form of the middle pass (forward-z FFT, division,
+    # backward-z FFT fused), which is what every non-transport symbol runs.  Single GPU, a short run, not the headline.
+    general_form = None
+    if world == 1 and plan.info()["fast_path"][2] == 2:
+        os.environ["CPC_ZSOLVE"] = "0"
+        try:
+            with cpc.CirculantPlan(n, n, n) as p2:
+                p2.set_symbol_transport(*LAMBDA)
+                x2 = torch.empty_like(b)
+                for _ in range(3):
+                    p2.apply(b, x2)
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ng = max(3, min(args.steps, 20))
+                g0.record()
+                for _ in range(ng):
+                    p2.apply(b, x2)
+                g1.record()
+                torch.cuda.synchronize()
+                gms = g0.elapsed_time(g1) / ng
+                gp = p2.apply_profiled(b, x2)
+                diff = (torch.linalg.vector_norm(x2 - x) / torch.linalg.vector_norm(x)).item()
+                general_form = {"middle_pass": "forward-z FFT, division, backward-z FFT fused (CPC_ZSOLVE=0)",
+                                "ms_per_step": gms, "value": 1e3 / gms, "steps": ng, "pass_ms": gp,
+                                "rel_l2_vs_recurrence_form": diff}
+                del x2
+        finally:
+            del os.environ["CPC_ZSOLVE"]
+
     # e2e: host-pointer C-ABI call on pinned buffers (H2D of b + D2H of x inside the timed region)
     hb = torch.empty(nloc, dtype=torch.complex128).pin_memory()
     hb.copy_(b)
@@ -292,7 +320,7 @@ def run_gpu(args):
         apply_alg = 5 * bytes_pass
         roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                    "alg_bytes_per_launch": bytes_pass, "middle_pass": middle,
+                    "alg_bytes_per_launch": bytes_pass, "middle_pass": middle, "general_symbol_form": general_form,
                     "passes": [{"name": nm, "ms": m, "GB/s": (bytes_pass / m / 1e6) if nm not in ("all-to-all", "barrier") and "all-gather" not in nm else None}
                                for nm, m in zip(names, pass_ms)],
                     "apply": {"alg_bytes": apply_alg, "achieved": apply_alg / ms_step / 1e6,

@@ -85,3 +85,66 @@ def test_slab_schedule_world_size_2(shape, P):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(P, port, shape, lam, b, ret), nprocs=P, join=True)
     assert rel_l2(ret["x"], want) < 1e-13
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The transpose-free schedule for the transport symbol (csrc/zsolve.cuh, PlanT::apply_device_zslab): Fx, Fy on the
+# local z-slab, the z recurrence in two local sweeps with an all-gather of every slab's end values in between.
+# ---------------------------------------------------------------------------------------------------------------
+def _worker_zslab(rank, P, port, shape, lam, b_full, ret):
+    import circulantpreconditioner_b200 as cpc
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=P)
+    nx, ny, nz = shape
+    z0, nzl = cpc.slab_range(nz, P, rank)
+    lx, ly, lz = lam
+    slab = b_full.reshape(nz, ny, nx)[z0:z0 + nzl].copy()
+    slab = np.fft.fft(np.fft.fft(slab, axis=2), axis=1)                      # Fx, Fy on the z-slab
+    cx = 1.0 - np.exp(-2j * np.pi * np.arange(nx) / nx) if nx > 1 else np.zeros(1)
+    cy = 1.0 - np.exp(-2j * np.pi * np.arange(ny) / ny) if ny > 1 else np.zeros(1)
+    alpha = 1.0 + lx * cx[None, :] + ly * cy[:, None]                         # [ny][nx]
+    r = 1.0 / (alpha + lz)
+    c = lz * r
+    # sweep 1: value at the end of the local lines from a zero carry-in
+    y0 = np.empty_like(slab)
+    acc = np.zeros((ny, nx), dtype=np.complex128)
+    for k in range(nzl):
+        acc = c * acc + slab[k]
+        y0[k] = acc
+    ends = [torch.empty(ny, nx, dtype=torch.complex128) for _ in range(P)]
+    dist.all_gather(ends, torch.from_numpy(acc.copy()))                       # ncclAllGather on the GPU
+    ends = [e.numpy() for e in ends]
+    # carry into this slab: the other slabs' end values, cycle closed over the ranks (Horner, as in the kernel)
+    cL = c ** nzl
+    z = np.zeros((ny, nx), dtype=np.complex128)
+    idx = rank
+    for _ in range(P):
+        z = cL * z + ends[idx]
+        idx = (idx + 1) % P
+    z = z / (1.0 - cL ** P)
+    # sweep 2: fold the carry in; the z solve is exact, so only Bx By remain to be normalised
+    cp = c.copy()
+    for k in range(nzl):
+        y0[k] = (y0[k] + cp * z) * r
+        cp = cp * c
+    slab2 = np.fft.ifft(np.fft.ifft(y0, axis=1), axis=2)
+    parts = [None] * P
+    dist.all_gather_object(parts, (z0, slab2))
+    if rank == 0:
+        ret["x"] = np.concatenate([p[1] for p in sorted(parts, key=lambda t: t[0])], axis=0).ravel()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("shape,P", [((8, 6, 8), 2), ((5, 3, 12), 2), ((4, 4, 12), 3)])   # only nz % P == 0 is needed
+def test_zslab_recurrence_schedule(shape, P):
+    from oracle import circulant_oracle as O
+    nx, ny, nz = shape
+    rng = np.random.default_rng(2)
+    lam = (0.6, 0.15, 55.5556)
+    b = rng.standard_normal(nx * ny * nz) + 1j * rng.standard_normal(nx * ny * nz)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_worker_zslab, args=(P, port, shape, lam, b, ret), nprocs=P, join=True)
+    assert rel_l2(ret["x"], want) < 1e-12
