@@ -6,7 +6,10 @@ import torch
 import circulantpreconditioner_b200 as cpc
 
 sizes = [int(s) for s in sys.argv[1:]] or [128, 256, 512]
+ONLY = os.environ.get("DTYPES", "c128,c64,f64").split(",")       # e.g. DTYPES=c128
 for dtype, tdt, eb in (("c128", torch.complex128, 16), ("c64", torch.complex64, 8), ("f64", torch.float64, 8)):
+    if dtype not in ONLY:
+        continue
     for n in sizes:
         b = torch.randn(n ** 3, dtype=torch.float64, device="cuda").to(tdt)
         x = torch.empty_like(b)
