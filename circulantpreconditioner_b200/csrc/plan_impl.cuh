@@ -6,6 +6,9 @@
 //   tear-down  PCSHELLFft_3D.cxx:86-99
 // Schedule of one apply on one GPU (5 HBM passes):
 //   Fx : b -> x      Fy : x -> x      [Fz . 1/(N Lambda) . Bz] : x -> x      By : x -> x      Bx : x -> x
+// The bracketed middle pass is one kernel: the fused forward-FFT / division / backward-FFT form (fft_pass.cuh,
+// fft_r2x.cuh), or -- for the transport symbol -- the equivalent cyclic recurrence along z (zsolve.cuh), which also
+// lets multi-rank (z-slab) plans run without any transpose (apply_device_zslab).
 // Every pass is tile-disjoint (a tile is read completely before it is written), so all passes run in place on x
 // and b == x aliasing (tests/TransportEquationFFT_SphericalExplosion_impl_mpi.cxx:111) is safe.
 #pragma once

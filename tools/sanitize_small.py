@@ -9,7 +9,10 @@ from oracle import circulant_oracle as O
 
 rng = np.random.default_rng(0)
 worst = 0.0
-for shape in [(32, 16, 64), (64, 128, 16), (512, 8, 8), (16, 256, 16), (20, 6, 9), (1024, 8, 2)]:
+# the z extents cover the recurrence kernel's forms (16, 8, 10, 5, 4 points per thread), a length that fits none (9)
+# and the 2^a * 3 / 2^a * 5 / generic line kernels
+for shape in [(32, 16, 64), (64, 128, 16), (512, 8, 8), (16, 256, 16), (20, 6, 9), (1024, 8, 2), (48, 12, 96),
+              (100, 8, 200), (8, 14, 100), (24, 10, 40)]:
     nx, ny, nz = shape
     lam = (2.0, 0.5, 1.5)
     b = rng.standard_normal(nx * ny * nz) + 1j * rng.standard_normal(nx * ny * nz)
