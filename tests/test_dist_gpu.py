@@ -68,6 +68,17 @@ def test_two_rank_transport(shape):
         assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
 
 
+@pytest.mark.parametrize("shape", [(64, 64, 64), (32, 16, 256)])
+def test_two_rank_transport_transposing_schedule(shape, monkeypatch):
+    """CPC_ZSOLVE=0 (inherited by the spawned ranks): the FFT form of the middle pass and the transposing schedule that
+    every non-transport symbol uses; test_two_rank_transport runs the same shapes through the transpose-free z-slab
+    recurrence (csrc/zsolve.cuh).  Both must match the oracle."""
+    monkeypatch.setenv("CPC_ZSOLVE", "0")
+    errs = _run(shape, (55.5556, 0.3, 2.5))
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
+
+
 def test_two_rank_wave_block():
     errs = _run((32, 32, 32), (3.0, 0.0793651, 0.0793651, 0.0793651), ncomp=4, wave=True)
     for r, (e1, e2, e3) in errs.items():
