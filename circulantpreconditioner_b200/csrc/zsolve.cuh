@@ -146,7 +146,7 @@ zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, con
     __syncthreads();
 
     // 2b. value carried into this warp
-    C Z;
+    C Z = mk<T>((T)0, (T)0);
     if constexpr (KIND == ZS_CYCLIC) {
         // cycle closed: Z_{w-1} = sum_{m < NW} D^m A_{w-1-m} / (1 - D^NW)   (Horner over A_w, A_{w+1}, ..., A_{w-1})
         C acc = mk<T>((T)0, (T)0), Dn = mk<T>((T)1, (T)0);
