@@ -170,6 +170,39 @@ def FftTransportSolver(n_x, n_y, n_z, lambda_x, lambda_y, lambda_z, b, workers=1
     return solve_3D(Diag, b, n_x, n_y, n_z, workers, naive)
 
 
+def FftTransportSolver_z_recurrence(n_x, n_y, n_z, lambda_x, lambda_y, lambda_z, b):
+    """The same solve with the z part done WITHOUT FFTs -- the form the CUDA middle pass takes for this symbol
+    (circulantpreconditioner_b200/csrc/zsolve.cuh); kept here so that the equivalence is pinned on the CPU.
+
+    After the x and y transforms (FftLinearSolver_3D.c:170, two of the three 1-D factors), every z line is a circulant
+    system with first column ``[alpha + lz, -lz, 0, ...]``, ``alpha = 1 + lx c_x_hat[kx] + ly c_y_hat[ky]``
+    (build_diag_mat_vec_3D :146-157 says its spectrum is ``Diag[k]``), i.e.
+    ``(alpha + lz) x_k - lz x_{k-1} = b_k`` cyclically: a first-order recurrence ``y_k = c y_{k-1} + b_k``,
+    ``c = lz / (alpha + lz)``, closed by ``y_{-1} = y_{n-1}^{(0)} / (1 - c^n)``, then ``x = y / (alpha + lz)``.
+    Requires ``lambda_z >= 0`` and ``Re alpha >= 1`` (then ``|c| < 1``)."""
+    b3 = np.asarray(b, dtype=np.complex128).reshape(n_z, n_y, n_x)
+    cx = np.fft.fft(build_transport_col(n_x))
+    cy = np.fft.fft(build_transport_col(n_y))
+    alpha = 1.0 + lambda_x * cx[None, :] + lambda_y * cy[:, None]
+    if lambda_z < 0 or alpha.real.min() < 1.0 - 1e-12:
+        raise ValueError("the recurrence form needs lambda_z >= 0 and Re(alpha) >= 1")
+    bh = np.fft.fft(np.fft.fft(b3, axis=2), axis=1)
+    r = 1.0 / (alpha + lambda_z)
+    c = lambda_z * r
+    y = np.empty_like(bh)
+    acc = np.zeros((n_y, n_x), dtype=np.complex128)
+    for k in range(n_z):                      # zero carry-in
+        acc = c * acc + bh[k]
+        y[k] = acc
+    carry = acc / (1.0 - c ** n_z)            # cyclic closure
+    cp = c.copy()
+    for k in range(n_z):
+        y[k] = (y[k] + cp * carry) * r
+        cp = cp * c
+    X = np.fft.ifft(np.fft.ifft(y, axis=1), axis=2)
+    return X.reshape(-1)
+
+
 def Fft3DTransportSolver(n_x, n_y, n_z, a_x, a_y, a_z, dt, delta_x, delta_y, delta_z, b, workers=1, naive=False):
     """``lambda_d = a_d * dt / delta_d`` (FftLinearSolver_3D.c:266-281)."""
     return FftTransportSolver(n_x, n_y, n_z, a_x * dt / delta_x, a_y * dt / delta_y, a_z * dt / delta_z,

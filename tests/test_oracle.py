@@ -150,3 +150,22 @@ def test_spherical_step_counts():
     assert set(np.unique(u)) == {600.0, 650.0}
     frac = (u == 650.0).mean()
     assert abs(frac - 4 / 3 * np.pi * 0.3 ** 3) < 0.02
+
+
+@pytest.mark.parametrize("shape,lam", [((8, 6, 16), (0.6, 0.15, 0.02)), ((10, 25, 40), (55.5556, 55.5556, 55.5556)),
+                                       ((4, 3, 512), (55.5556, 0.0, 55.5556)), ((5, 1, 64), (1.0, 1.0, 4096.0)),
+                                       ((3, 2, 1), (2.0, 0.5, 3.0)), ((6, 4, 100), (0.0, 0.0, 1000.0)),
+                                       ((7, 5, 33), (3.0, 2.0, 0.0))])
+def test_z_recurrence_form_equals_fft_form(shape, lam):
+    """The middle pass as a cyclic first-order recurrence (what csrc/zsolve.cuh computes) is the same operator as
+    forward-z FFT, division by Diag, backward-z FFT (solve_3D, FftLinearSolver_3D.c:170-184)."""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(nx * 100 + nz)
+    b = rng.standard_normal(nx * ny * nz) + 1j * rng.standard_normal(nx * ny * nz)
+    a = O.FftTransportSolver(nx, ny, nz, *lam, b)
+    r = O.FftTransportSolver_z_recurrence(nx, ny, nz, *lam, b)
+    assert rel_l2(r, a) < 1e-12
+    # and both invert the circulant matrix itself
+    assert rel_l2(O.apply_transport_matrix(r, nx, ny, nz, *lam), b) < 1e-11
+    with pytest.raises(ValueError):
+        O.FftTransportSolver_z_recurrence(nx, ny, nz, lam[0], lam[1], -1.0, b)
