@@ -781,8 +781,13 @@ template <typename T> struct PlanT : PlanBase {
                                         const PassGeom &g)
     {
         constexpr int TX = 128 / (int)sizeof(C);
-        const ZSolveArgs<T> a = zsolve_args();
-        const int threads = nline / E * TX;
+        ZSolveArgs<T> a = zsolve_args();
+        a.nline = nline;
+        // CTAs of at least 128 threads: several tiles per CTA when the line is short
+        const int tpt = nline / E * TX;
+        const int gpc = tpt >= 128 ? 1 : 128 / tpt;
+        const int threads = tpt * gpc;
+        grid = (grid + gpc - 1) / gpc;
         if (kind == ZS_END) zsolve_kernel<T, E, false, ZS_END><<<grid, threads, 0, st>>>(in, out, g, a);
         else if (kind == ZS_DIST) zsolve_kernel<T, E, false, ZS_DIST><<<grid, threads, 0, st>>>(in, out, g, a);
         else if (gen) zsolve_kernel<T, E, true><<<grid, threads, 0, st>>>(in, out, g, a);

@@ -35,6 +35,7 @@ template <typename T> struct ZSolveArgs {
     T lz;                         // lambda_z
     T scale;                      // 1 / (nx ny): the x and y transforms are unnormalised, the z solve is exact
     int n;                        // nz
+    int nline;                    // points of the line a tile holds: nz, or nz / P in the z-slab sweeps
     // z-slab plans (DIST builds): the line is this rank's nz / P planes; the carry into its first plane comes from the
     // end values of every rank's slab (zero carry-in), all-gathered into ecat[P][nx ny]
     const cplx_t<T> *ecat;
@@ -66,20 +67,26 @@ zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, con
     using C = cplx_t<T>;
     constexpr int TX = 128 / (int)sizeof(C);        // lanes = lines per tile
     constexpr int QW = 32 / TX;                     // segments per warp
-    __shared__ C agg[32 * TX];                      // warp aggregates [warp][lane]
+    __shared__ C agg_all[32 * TX];                  // warp aggregates [warp of the CTA][lane]
 
-    const int tid = threadIdx.x;
+    // A CTA holds blockDim.x / (threads per tile) tiles: short lines (nz / P planes of a z-slab at 8 GPUs are 64
+    // points = one warp per tile) would otherwise make 32-thread CTAs.  Tiles never exchange data with each other.
+    const int tpt = a.nline / E * TX;               // threads per tile, a multiple of 32
+    const int grp = threadIdx.x / tpt;              // tile within the CTA
+    const int tid = threadIdx.x - grp * tpt;
     const int l = tid % TX;
     const int seg = tid / TX;
     const int q = seg % QW;                         // segment within the warp
     const int wrp = tid >> 5;
-    const int nwarps = blockDim.x >> 5;
+    const int nwarps = tpt >> 5;
     const int k0 = seg * E;
+    C *agg = agg_all + grp * nwarps * TX;
 
-    const int t = blockIdx.x;
-    const int ti = t % g.tiles_inner, to = t / g.tiles_inner;
+    const int t = blockIdx.x * (blockDim.x / tpt) + grp;
+    const bool tile_ok = t < g.ntiles;
+    const int ti = tile_ok ? t % g.tiles_inner : 0, to = tile_ok ? t / g.tiles_inner : 0;
     const int w = ti * TX + l;
-    const bool active = w < g.lines_inner;
+    const bool active = tile_ok && w < g.lines_inner;
     const long long gbase = (long long)to * g.B1 + (long long)ti * g.B0 + (long long)l * g.SL;
     const long long obase = (long long)to * g.B1o + (long long)ti * g.B0o + (long long)l * g.SLo;
 
