@@ -112,6 +112,11 @@ int cpc_get_diag(cpc_plan plan, void *diag_c128, int mem_kind);
  *                (tests/TransportEquationFFT_SphericalExplosion_impl_mpi.cxx:111 passes Un, Un).
  *                Asynchronous on the plan's stream for device pointers; host pointers return after the
  *                result has landed in x.
+ *                With the transport symbol (z table = DFT of [1,-1,0..], 0 <= lambda_z <= 4096, lambda_x, lambda_y >= 0)
+ *                the z factor of F^H diag(1/Lambda) F is evaluated as the equivalent cyclic first-order recurrence
+ *                (alpha + lz) x_k - lz x_{k-1} = b_k instead of two z FFTs and a division: the same operator, equal
+ *                to rounding (<= 1e-13 relative); multi-rank plans then exchange one carry per (kx, ky) line instead of
+ *                transposing.  Environment CPC_ZSOLVE=0 keeps the FFT form (cpc_plan_info.fast_path[2], dist_mode).
  * cpc_forward <- MatMult(FFT_MAT, in, out)          (unnormalised, exp(-2 pi i ..), :170)
  * cpc_inverse <- MatMultTranspose(FFT_MAT, in, out) (unnormalised, exp(+2 pi i ..), :180)
  * For multi-rank plans b/x/in are the rank's z-slab [cpc_slab_range over nz]; out of cpc_forward and in of
