@@ -26,6 +26,8 @@ def lib():
                                             ctypes.c_double, ctypes.c_double, ctypes.c_double]
         L.oracle_solve_3D.argtypes = [dp, dp, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
         L.oracle_Fft3DTransportSolver.argtypes = [ctypes.c_int] * 3 + [ctypes.c_double] * 7 + [dp, dp]
+        L.oracle_transport_solve_z_recurrence.argtypes = [dp, dp] + [ctypes.c_int] * 3 + [ctypes.c_double] * 3
+        L.oracle_transport_solve_z_recurrence.restype = ctypes.c_int
         L.oracle_num_threads.restype = ctypes.c_int
         _LIB = L
     return _LIB
@@ -60,3 +62,14 @@ def Fft3DTransportSolver(nx, ny, nz, ax, ay, az, dt, dx, dy, dz, b):
     x = np.empty_like(b)
     lib().oracle_Fft3DTransportSolver(nx, ny, nz, ax, ay, az, dt, dx, dy, dz, _p(x), _p(b))
     return x
+
+
+def transport_solve_z_recurrence(nx, ny, nz, lx, ly, lz, b):
+    """The transport solve with the z factor as a cyclic recurrence (what csrc/zsolve.cuh computes)."""
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    x = np.empty_like(b)
+    rc = lib().oracle_transport_solve_z_recurrence(_p(x), _p(b), nx, ny, nz, lx, ly, lz)
+    if rc != 0:
+        raise ValueError("the recurrence form needs non-negative lambdas")
+    return x
+

@@ -190,6 +190,59 @@ void oracle_Fft3DTransportSolver(int nx, int ny, int nz, double ax, double ay, d
     free(Diag);
 }
 
+/* The same solve with the z factor evaluated WITHOUT FFTs: after the x and y transforms every z line is the cyclic
+ * bidiagonal system (alpha + lz) x_k - lz x_{k-1} = b_k, alpha = 1 + lx c_x_hat[kx] + ly c_y_hat[ky] -- its spectrum is
+ * exactly Diag[k] of FftLinearSolver_3D.c:146-157 -- i.e. the recurrence y_k = c y_{k-1} + b_k, c = lz / (alpha + lz),
+ * closed by y_{-1} = y_{n-1}^{(0)} / (1 - c^n), and x = y / (alpha + lz).  This is the form the CUDA middle pass takes
+ * for the transport symbol (circulantpreconditioner_b200/csrc/zsolve.cuh); restated here so that its equality with
+ * oracle_solve_3D is pinned on the CPU.  Needs lz >= 0 and lx, ly >= 0 (|c| < 1).  Returns 0, or -1 on bad lambdas. */
+int oracle_transport_solve_z_recurrence(double *X, const double *b, int nx, int ny, int nz, double lx, double ly,
+                                        double lz)
+{
+    if (lx < 0 || ly < 0 || lz < 0) return -1;
+    size_t N = (size_t)nx * ny * nz;
+    long sxy = (long)nx * ny;
+    cplx *a = (cplx *)malloc(sizeof(cplx) * N);
+    memcpy(a, b, sizeof(cplx) * N);
+    dft_axis(a, nx, 1, nz, sxy, ny, nx, -1);          /* Fx */
+    dft_axis(a, ny, nx, nz, sxy, nx, 1, -1);          /* Fy */
+#pragma omp parallel for schedule(static)
+    for (long line = 0; line < sxy; ++line) {
+        const int i = (int)(line % nx), j = (int)(line / nx);
+        cplx wx = root(i, nx, -1), wy = root(j, ny, -1);
+        /* alpha + lz, with c_hat[q] = 1 - exp(-2 pi i q / n) (0 on an axis of length 1, :80-90) */
+        double are = 1.0 + (nx > 1 ? lx * (1.0 - wx.re) : 0.0) + (ny > 1 ? ly * (1.0 - wy.re) : 0.0) + lz;
+        double aim = (nx > 1 ? -lx * wx.im : 0.0) + (ny > 1 ? -ly * wy.im : 0.0);
+        if (nz == 1) are -= lz;                        /* c_z_hat = 0: no z coupling at all */
+        double d2 = are * are + aim * aim;
+        cplx r = { are / d2, -aim / d2 };
+        cplx c = { (nz > 1 ? lz : 0.0) * r.re, (nz > 1 ? lz : 0.0) * r.im };
+        cplx acc = { 0.0, 0.0 };
+        for (int k = 0; k < nz; ++k) {                 /* zero carry-in */
+            acc = cadd(cmul(c, acc), a[line + (long)k * sxy]);
+            a[line + (long)k * sxy] = acc;
+        }
+        cplx cn = { 1.0, 0.0 };
+        for (int k = 0; k < nz; ++k) cn = cmul(cn, c);
+        double e2 = (1.0 - cn.re) * (1.0 - cn.re) + cn.im * cn.im;
+        cplx inv = { (1.0 - cn.re) / e2, cn.im / e2 };  /* 1 / (1 - c^n) */
+        cplx carry = cmul(acc, inv);
+        cplx cp = c;
+        for (int k = 0; k < nz; ++k) {
+            cplx y = cadd(a[line + (long)k * sxy], cmul(cp, carry));
+            a[line + (long)k * sxy] = cmul(y, r);
+            cp = cmul(cp, c);
+        }
+    }
+    dft_axis(a, ny, nx, nz, sxy, nx, 1, +1);          /* By */
+    dft_axis(a, nx, 1, nz, sxy, ny, nx, +1);          /* Bx */
+    double s = 1.0 / ((double)nx * ny);
+    cplx *x = (cplx *)X;
+    for (size_t m = 0; m < N; ++m) { x[m].re = a[m].re * s; x[m].im = a[m].im * s; }
+    free(a);
+    return 0;
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -169,3 +169,8 @@ def test_z_recurrence_form_equals_fft_form(shape, lam):
     assert rel_l2(O.apply_transport_matrix(r, nx, ny, nz, *lam), b) < 1e-11
     with pytest.raises(ValueError):
         O.FftTransportSolver_z_recurrence(nx, ny, nz, lam[0], lam[1], -1.0, b)
+    # the independent plain-C restatement of the same form
+    rc = CO.transport_solve_z_recurrence(nx, ny, nz, *lam, b)
+    assert rel_l2(rc, a) < 1e-12
+    with pytest.raises(ValueError):
+        CO.transport_solve_z_recurrence(nx, ny, nz, lam[0], lam[1], -1.0, b)
