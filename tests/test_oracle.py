@@ -174,3 +174,30 @@ def test_z_recurrence_form_equals_fft_form(shape, lam):
     assert rel_l2(rc, a) < 1e-12
     with pytest.raises(ValueError):
         CO.transport_solve_z_recurrence(nx, ny, nz, lam[0], lam[1], -1.0, b)
+
+
+def test_oracle_properties_random_shapes():
+    """Property checks over random small grids (hypothesis): the FFT form inverts the circulant matrix, is linear, and
+    equals the recurrence form of the middle pass -- in both oracle implementations."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=40, deadline=None, derandomize=True)
+    @hyp.given(nx=st.integers(1, 12), ny=st.integers(1, 9), nz=st.integers(1, 17),
+               lx=st.floats(0.0, 60.0), ly=st.floats(0.0, 60.0), lz=st.floats(0.0, 4096.0), seed=st.integers(0, 2 ** 16))
+    def check(nx, ny, nz, lx, ly, lz, seed):
+        rng = np.random.default_rng(seed)
+        n = nx * ny * nz
+        x1 = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        x2 = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        b1 = O.apply_transport_matrix(x1, nx, ny, nz, lx, ly, lz)
+        b2 = O.apply_transport_matrix(x2, nx, ny, nz, lx, ly, lz)
+        s1 = O.FftTransportSolver(nx, ny, nz, lx, ly, lz, b1)
+        tol = 1e-12 * (1.0 + lx + ly + lz)               # the forward error scales with the conditioning ~ 1 + 2 sum lambda
+        assert rel_l2(s1, x1) < tol
+        s12 = O.FftTransportSolver(nx, ny, nz, lx, ly, lz, 2.0 * b1 - 3.0j * b2)
+        assert rel_l2(s12, 2.0 * x1 - 3.0j * x2) < tol
+        assert rel_l2(O.FftTransportSolver_z_recurrence(nx, ny, nz, lx, ly, lz, b1), s1) < tol
+        assert rel_l2(CO.transport_solve_z_recurrence(nx, ny, nz, lx, ly, lz, b1), s1) < tol
+
+    check()
