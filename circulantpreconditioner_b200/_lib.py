@@ -46,6 +46,7 @@ ABI = {
     "cpc_set_symbol_diag": (_i, [_vp, _vp, _i]),
     "cpc_set_symbol_first_column": (_i, [_vp, _vp, _i]),
     "cpc_set_symbol_wave": (_i, [_vp, _d, _d, _d, _d]),
+    "cpc_set_option": (_i, [_vp, _i, ctypes.c_longlong]),
     "cpc_get_diag": (_i, [_vp, _vp, _i]),
     "cpc_apply": (_i, [_vp, _vp, _vp, _i]),
     "cpc_forward": (_i, [_vp, _vp, _vp, _i]),
@@ -67,6 +68,7 @@ CPC_MAX_PASSES = 16
 CPC_NCCL_UNIQUE_ID_BYTES = 128
 DTYPES = {"c128": 0, "c64": 1, "f64": 2, "f32": 3}
 MEM_DEVICE, MEM_HOST = 0, 1
+OPTIONS = {"z_recurrence": 1, "l2_chunk_bytes": 2, "chain_streams": 3}
 
 
 def library_path():

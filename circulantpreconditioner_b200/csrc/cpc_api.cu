@@ -157,6 +157,12 @@ int cpc_set_symbol_wave(cpc_plan plan, double c0, double mx, double my, double m
     return plan->impl->set_symbol_wave(c0, mx, my, mz);
 }
 
+int cpc_set_option(cpc_plan plan, int option, long long value)
+{
+    CHECK_PLAN(plan);
+    return plan->impl->set_option(option, value);
+}
+
 int cpc_get_diag(cpc_plan plan, void *diag, int mem_kind)
 {
     CHECK_PLAN(plan);

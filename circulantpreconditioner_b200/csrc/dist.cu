@@ -124,8 +124,19 @@ int dist_map_peers(DistState &d, void *local, void **peers, int device, cudaStre
     peers[d.rank] = local;
     if (d.nranks == 1) return CPC_OK;
     CPC_CUDA(cudaSetDevice(device));
+    // A local failure before the collectives must not leave the other ranks waiting in them: it is carried as
+    // rc through the all-gather and reported by the agreement flag below.
+    int rc = CPC_OK;
     cudaIpcMemHandle_t mine;
-    CPC_CUDA(cudaIpcGetMemHandle(&mine, local));
+    memset(&mine, 0, sizeof(mine));
+    {
+        cudaError_t e = cudaIpcGetMemHandle(&mine, local);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+            rc = CPC_ERR_UNSUPPORTED;
+        }
+    }
     const size_t hs = sizeof(cudaIpcMemHandle_t);
     char *dev = nullptr;
     CPC_CUDA(cudaMalloc(&dev, hs * (size_t)(d.nranks + 1)));
@@ -135,7 +146,6 @@ int dist_map_peers(DistState &d, void *local, void **peers, int device, cudaStre
     CPC_CUDA(cudaMemcpyAsync(all.data(), dev, hs * d.nranks, cudaMemcpyDeviceToHost, stream));
     CPC_CUDA(cudaStreamSynchronize(stream));
     cudaFree(dev);
-    int rc = CPC_OK;
     for (int q = 0; q < d.nranks && rc == CPC_OK; ++q) {
         if (q == d.rank) continue;
         cudaError_t e = cudaIpcOpenMemHandle(&peers[q], all[q], cudaIpcMemLazyEnablePeerAccess);
@@ -195,6 +205,13 @@ int dist_barrier(DistState &d, cudaStream_t stream)
         CPC_CUDA(cudaMemsetAsync(d.barrier_buf, 0, sizeof(float), stream));
     }
     CPC_NCCL(g_api.AllReduce(d.barrier_buf, d.barrier_buf, 1, NCCL_FLOAT32, NCCL_SUM, (ncclComm_tt)d.comm, stream));
+    return CPC_OK;
+}
+
+int dist_allreduce_sum_f32(DistState &d, float *buf, size_t count, cudaStream_t stream)
+{
+    if (d.nranks == 1) return CPC_OK;
+    CPC_NCCL(g_api.AllReduce(buf, buf, count, NCCL_FLOAT32, NCCL_SUM, (ncclComm_tt)d.comm, stream));
     return CPC_OK;
 }
 

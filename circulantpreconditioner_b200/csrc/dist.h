@@ -23,6 +23,8 @@ void dist_destroy(DistState &d);
 int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes, cudaStream_t stream);
 // ncclAllGather of `bytes` per rank (the z-slab carry exchange of the recurrence middle pass, zsolve.cuh).
 int dist_allgather(DistState &d, const void *send, void *recv, size_t bytes, cudaStream_t stream);
+// In-place sum over ranks of `count` floats (agreement flags of collective set-up steps).
+int dist_allreduce_sum_f32(DistState &d, float *buf, size_t count, cudaStream_t stream);
 // Stream-ordered barrier across ranks (1-element all-reduce).
 int dist_barrier(DistState &d, cudaStream_t stream);
 // Exchange CUDA IPC handles of `local` (a cudaMalloc'ed buffer) through an NCCL all-gather and map every peer's

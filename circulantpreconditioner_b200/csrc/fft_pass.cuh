@@ -290,7 +290,7 @@ __device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int k0, int kste
 template <typename T, int N, int R0, int R1, int R2, int E, int TX, int G, int MODE, int MINB, bool XMAP, bool GEN = true,
           int NG = 1>
 __global__ void __launch_bounds__((N / E) * TX * G, MINB)
-fft_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
+fft_pass_kernel(const cplx_t<T> *in, cplx_t<T> *out, const PassGeom g,
                 const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
 {
     using C = cplx_t<T>;

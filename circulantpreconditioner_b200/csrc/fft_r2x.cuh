@@ -30,7 +30,7 @@ template <typename C> __device__ __forceinline__ C shfl_xor_c(C v, int mask)
 // (s, l): shared memory [point][s][l], so the 8 lanes of a quarter warp still hit one 128-byte row.
 template <typename T, int H, int R0, int R1, int MODE, bool GEN, int TX = 128 / (int)sizeof(cplx_t<T>)>
 __global__ void __launch_bounds__(H * TX / 8, (TX == 16 ? 8192 : 4096) / (H * TX))
-fft_r2x_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
+fft_r2x_kernel(const cplx_t<T> *in, cplx_t<T> *out, const PassGeom g,
                const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
 {
     using C = cplx_t<T>;
@@ -152,7 +152,7 @@ namespace cpc {
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MODE, int LINES>
 __global__ void __launch_bounds__(32 * LINES, 2)
-fft_r2x512_line_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
+fft_r2x512_line_kernel(const cplx_t<T> *in, cplx_t<T> *out, const PassGeom g,
                        const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
 {
     using C = cplx_t<T>;
@@ -225,7 +225,7 @@ namespace cpc {
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int MODE, int LINES>
 __global__ void __launch_bounds__(16 * LINES, 2)
-fft_line256_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
+fft_line256_kernel(const cplx_t<T> *in, cplx_t<T> *out, const PassGeom g,
                    const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> sym)
 {
     using C = cplx_t<T>;

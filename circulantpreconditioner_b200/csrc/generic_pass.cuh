@@ -164,7 +164,7 @@ __device__ __forceinline__ cplx_t<T> *generic_line_fft(cplx_t<T> *cur, cplx_t<T>
 }
 
 template <typename T>
-__global__ void generic_pass_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g,
+__global__ void generic_pass_kernel(const cplx_t<T> *in, cplx_t<T> *out, const PassGeom g,
                                     const cplx_t<T> *__restrict__ tw, const SymbolArgs<T> s, const FactorList f,
                                     const int TX, const int mode)
 {

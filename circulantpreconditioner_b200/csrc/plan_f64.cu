@@ -18,6 +18,74 @@ __global__ void diag_from_separable_kernel(double2 *__restrict__ diag, const dou
     }
 }
 
+__global__ void diag_check_separable_kernel(const double2 *__restrict__ diag, const double2 *__restrict__ ax,
+                                            const double2 *__restrict__ ay, const double2 *__restrict__ az, int nx, int ny,
+                                            long long n, unsigned long long *out)
+{
+    double md = 0.0, ma = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % nx);
+        const long long r = i / nx;
+        const int y = (int)(r % ny);
+        const long long z = r / ny;
+        const double2 d = diag[i];
+        const double er = fabs(d.x - (ax[x].x + ay[y].x + az[z].x)), ei = fabs(d.y - (ax[x].y + ay[y].y + az[z].y));
+        md = fmax(md, fmax(er, ei));
+        ma = fmax(ma, fmax(fabs(d.x), fabs(d.y)));
+        if (!(er == er) || !(ei == ei)) md = 1e300;                   // NaN entries are never "separable"
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+        ma = fmax(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+    }
+    if ((threadIdx.x & 31) == 0) {                                    // non-negative doubles order like their bit patterns
+        atomicMax(out, (unsigned long long)__double_as_longlong(md));
+        atomicMax(out + 1, (unsigned long long)__double_as_longlong(ma));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+zs_carry_push_kernel(const double2 *__restrict__ e, long long lines, long long lsub, int rank, ZCarryPeers gpeer)
+{
+    for (long long line = blockIdx.x * (long long)blockDim.x + threadIdx.x; line < lines;
+         line += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(line / lsub);
+        gpeer.p[q][(long long)rank * lsub + (line - (long long)q * lsub)] = e[line];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+zs_carry_owner_kernel(const double2 *__restrict__ gbuf, long long gstride, long long line0, long long count, int nx,
+                      int nzl, int nranks, int rank, int self_only, ZCarryPeers zpeer, const ZSolveArgs a)
+{
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < count;
+         j += (long long)gridDim.x * blockDim.x) {
+        const long long line = line0 + j;
+        double2 r, c;
+        zs_coeffs(a, (int)(line % nx), (int)(line / nx), r, c);
+        const double2 cL = cpow_rt(c, nzl);
+        double2 e[CPC_MAX_PEERS];
+#pragma unroll
+        for (int s = 0; s < CPC_MAX_PEERS; ++s)
+            e[s] = s < nranks ? gbuf[(long long)s * gstride + j] : make_double2(0.0, 0.0);
+        // Zin_0 = sum_m cL^m e_{P-1-m} / (1 - cL^P): Horner over e_0, e_1, ..., e_{P-1}
+        double2 acc = make_double2(0.0, 0.0), cLp = make_double2(1.0, 0.0);
+#pragma unroll
+        for (int s = 0; s < CPC_MAX_PEERS; ++s)
+            if (s < nranks) {
+                acc = cadd(cmul(cL, acc), e[s]);
+                cLp = cmul(cLp, cL);
+            }
+        double2 Z = cmul(acc, crecip_scaled<double>(make_double2(1.0 - cLp.x, -cLp.y), 1.0));
+#pragma unroll
+        for (int q = 0; q < CPC_MAX_PEERS; ++q)
+            if (q < nranks) {
+                if (!self_only || q == rank) zpeer.p[self_only ? 0 : q][line] = Z;
+                Z = cadd(e[q], cmul(cL, Z));                        // Zin_{q+1} = e_q + cL Zin_q
+            }
+    }
+}
+
 PlanBase *make_plan_f64() { return new PlanT<double>(); }
 
 }  // namespace cpc

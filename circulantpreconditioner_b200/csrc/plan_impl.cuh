@@ -76,6 +76,25 @@ __global__ void invert_inplace_kernel(cplx_t<T> *__restrict__ tab, long long n, 
 __global__ void diag_from_separable_kernel(double2 *__restrict__ diag, const double2 *__restrict__ ax,
                                            const double2 *__restrict__ ay, const double2 *__restrict__ az, int nx,
                                            int ny, long long n);
+// max |Diag - (ax + ay + az)| and max |Diag| over the local slab, as bit patterns of non-negative doubles in out[0], out[1]
+// (az already points at the slab's first plane)
+__global__ void diag_check_separable_kernel(const double2 *__restrict__ diag, const double2 *__restrict__ ax,
+                                            const double2 *__restrict__ ay, const double2 *__restrict__ az, int nx, int ny,
+                                            long long n, unsigned long long *out);
+// z-slab [z_loc][y][x] -> per-destination chunks [q][z_loc][y_loc][x] (the layout the all-to-all transposes)
+template <typename C>
+__global__ void slab_to_chunked_kernel(const C *__restrict__ in, C *__restrict__ out, int nx, int ny, int nyl, int nzl)
+{
+    const long long n = (long long)nx * ny * nzl;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % nx);
+        const long long r = i / nx;
+        const int y = (int)(r % ny), z = (int)(r / ny);
+        const int q = y / nyl, yl = y - q * nyl;
+        out[(((long long)q * nzl + z) * nyl + yl) * nx + x] = in[i];
+    }
+}
+
 template <typename T>
 __global__ void diag_from_invtable_kernel(double2 *__restrict__ diag, const cplx_t<T> *__restrict__ inv, long long n,
                                           double scale)
@@ -156,6 +175,12 @@ template <typename T> struct PlanT : PlanBase {
     C *work = nullptr;            // half spectrum (real plans) or the promoted complex copy
     int num_sms = 148;
     int pf_waves = 0;             // L2 prefetch distance in units of (SM count) CTAs; 0 = off
+    // L2-chained schedule: the x and y passes run z-chunk by z-chunk (Fx then Fy on the same planes, By then Bx), so
+    // that the second pass of a pair finds its input in the 126 MB L2 and the intermediate array never goes to HBM.
+    long long l2_chunk_bytes = 32ll << 20;    // bytes of x per z-chunk; 0 = whole-array passes
+    int chain_streams = 1;        // 2: alternate the chunks' chains between the plan stream and a side stream
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     // transport symbol with the upwind z column: the middle pass is a cyclic first-order recurrence (zsolve.cuh)
     bool zrec = false;            // the symbol allows it
     bool zrec_off = false;        // CPC_ZSOLVE=0: keep the FFT-based fused pass (comparison / tuning hook)
@@ -189,17 +214,28 @@ template <typename T> struct PlanT : PlanBase {
     C *dbuf = nullptr;
     cudaStream_t copy_stream = nullptr;
     std::vector<cudaEvent_t> chunk_ev;
-    cudaEvent_t prof_ev[CPC_MAX_PASSES + 1] = {};
-    bool prof_ev_ok = false;
+    // profiled applies: one event after every launch, durations summed per pass kind
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_kind;
+    size_t prof_n = 0;
+    bool prof_on = false;
 
     // multi-rank
     DistState dist;
-    C *sendbuf = nullptr, *tbuf = nullptr;
-    // z-slab recurrence (multi-rank transport symbol): this rank's line-end values and every rank's, [P][nx ny]
-    C *ebuf = nullptr, *ecat = nullptr;
-    int zslab_e = 0;              // points per thread for nz / P point lines (0: no fit, keep the transposing path)
+    C *sendbuf = nullptr, *tbuf = nullptr;    // transposing schedule only; allocated (and IPC-mapped) on first use
+    bool tbuf_tried = false;
+    bool want_p2p = false;
     bool p2p = false;                         // peers' buffers are IPC-mapped: transposes are fused into the passes
     void *peer_t[CPC_MAX_PEERS] = {}, *peer_s[CPC_MAX_PEERS] = {};
+    // z-slab recurrence (multi-rank transport symbol), all fp64: this rank's line-end values ebuf[nx ny]; the gather
+    // buffer of the lines this rank owns, gbuf[P][lsub] (peers store into it), or every rank's end values [P][nx ny]
+    // when peers cannot be mapped (ncclAllGather); zinbuf[nx ny] = the carry into this rank's first plane.
+    double2 *ebuf = nullptr, *gbuf = nullptr, *zinbuf = nullptr;
+    long long lsub = 0;           // lines owned per rank
+    bool carry_p2p = false;
+    void *peer_g[CPC_MAX_PEERS] = {}, *peer_z[CPC_MAX_PEERS] = {};
+    int zslab_e = 0;              // points per thread for nz / P point lines (0: no tile form fits -> one thread per line)
+    bool zslab_line = false;      // tuning hook: always take the thread-per-line form of the second sweep
 
     ~PlanT() override
     {
@@ -215,22 +251,31 @@ template <typename T> struct PlanT : PlanBase {
         if (work) cudaFree(work);
         free_projection();
         if (dbuf) cudaFree(dbuf);
-        if (p2p) {
+        if (p2p || carry_p2p) {
             dist_barrier(dist, stream);
             cudaStreamSynchronize(stream);
-            dist_unmap_peers(dist, peer_t);
-            dist_unmap_peers(dist, peer_s);
+            if (p2p) {
+                dist_unmap_peers(dist, peer_t);
+                dist_unmap_peers(dist, peer_s);
+            }
+            if (carry_p2p) {
+                dist_unmap_peers(dist, peer_g);
+                dist_unmap_peers(dist, peer_z);
+            }
             dist_barrier(dist, stream);          // nobody frees a buffer a peer still has mapped
             cudaStreamSynchronize(stream);
         }
         if (sendbuf) cudaFree(sendbuf);
         if (ebuf) cudaFree(ebuf);
-        if (ecat) cudaFree(ecat);
+        if (gbuf) cudaFree(gbuf);
+        if (zinbuf) cudaFree(zinbuf);
         if (tbuf) cudaFree(tbuf);
         if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (side_stream) cudaStreamDestroy(side_stream);
+        if (fork_ev) cudaEventDestroy(fork_ev);
+        if (join_ev) cudaEventDestroy(join_ev);
         for (auto e : chunk_ev) cudaEventDestroy(e);
-        if (prof_ev_ok)
-            for (auto e : prof_ev) cudaEventDestroy(e);
+        for (auto e : prof_ev) cudaEventDestroy(e);
         dist_destroy(dist);
     }
 
@@ -255,9 +300,9 @@ template <typename T> struct PlanT : PlanBase {
             if (nc != 1) { set_error("real-scalar plans need ncomp == 1"); return CPC_ERR_ARG; }
             if (desc.nranks != 1) { set_error("real-scalar plans are single-rank in this version"); return CPC_ERR_UNSUPPORTED; }
         }
-        if (desc.nranks > 1 && (n[2] % desc.nranks != 0 || n[1] % desc.nranks != 0)) {
-            set_error("multi-rank plans need ny and nz divisible by nranks (ny=%d nz=%d nranks=%d)", n[1], n[2],
-                      desc.nranks);
+        // z-slabs need nz divisible by the ranks; ny too only for the transposing schedule (checked when it is chosen)
+        if (desc.nranks > 1 && n[2] % desc.nranks != 0) {
+            set_error("multi-rank plans need nz divisible by nranks (nz=%d nranks=%d)", n[2], desc.nranks);
             return CPC_ERR_UNSUPPORTED;
         }
         FastRegistry<T>::fill(reg);
@@ -278,19 +323,29 @@ template <typename T> struct PlanT : PlanBase {
         int dev_smem = 0;
         CPC_CUDA(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
         CPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
-        if (const char *pf = getenv("CPC_PREFETCH_WAVES")) pf_waves = atoi(pf);   // tuning hook
-        if (const char *zs = getenv("CPC_ZSOLVE")) zrec_off = (atoi(zs) == 0);     // tuning hook
+        // Tuning hooks (tools/ only): read only when CPC_TUNING=1 is set, so that a stray variable in a production
+        // environment cannot change which kernels run.  The supported switches are cpc_set_option().
+        const bool tuning = getenv("CPC_TUNING") && atoi(getenv("CPC_TUNING")) != 0;
+        auto tune = [&](const char *name) -> const char * { return tuning ? getenv(name) : nullptr; };
+        if (const char *pf = tune("CPC_PREFETCH_WAVES")) pf_waves = atoi(pf);
+        if (const char *zs = tune("CPC_ZSOLVE")) zrec_off = (atoi(zs) == 0);
+        if (const char *lc = tune("CPC_L2_CHUNK_MB")) l2_chunk_bytes = (long long)(atof(lc) * 1048576.0);
+        if (const char *cs = tune("CPC_CHAIN_STREAMS")) chain_streams = atoi(cs) >= 2 ? 2 : 1;
         zrec_e = zsolve_points_per_thread(n[2]);
-        if (const char *ze = getenv("CPC_ZSOLVE_E")) {                             // tuning hook: force E if it fits
+        if (const char *ze = tune("CPC_ZSOLVE_E")) {                               // force E if it fits
             constexpr int ZTX = 128 / (int)sizeof(C), ZQW = 32 / ZTX;
             const int E = atoi(ze);
             if ((E == 4 || E == 5 || E == 8 || E == 10 || E == 16) && n[2] % E == 0 && (n[2] / E) % ZQW == 0 &&
-                n[2] / E * ZTX <= ((sizeof(T) == 8 && E >= 16) ? 512 : 1024))
+                n[2] / E * ZTX <= (E >= 16 ? 512 : 1024))
                 zrec_e = E;
         }
-        if (const char *sg = getenv("CPC_STAGGER")) stagger = atoi(sg);           // tuning hook
+        if (const char *sg = tune("CPC_STAGGER")) stagger = atoi(sg);
+        if (const char *zl = tune("CPC_ZSLAB_LINE")) zslab_line = atoi(zl) != 0;
         CPC_TRACE("got smem attribute");
 
+        // multi-rank plans whose ny is not divisible by the ranks can only run the transpose-free z-slab schedule:
+        // their y passes are always local, so the kernels are chosen as for a single rank
+        const bool multi_tr = desc.nranks > 1 && n[1] % desc.nranks == 0;
         for (int a = 0; a < 3; ++a) {
             // root table
             std::vector<C> h(n[a]);
@@ -314,7 +369,7 @@ template <typename T> struct PlanT : PlanBase {
                 else if (n[a] == 512 && reg.find(FastKey<T>(n[a], VAR_WIDE2, MODE_FUSED_SEP)) != reg.end()) var = VAR_WIDE2;
             }
             // contiguous 512-point x lines: one warp per line, no block barrier (0.62 vs 0.69 ms at 512^3)
-            if (a == 0 && nc == 1 && !real && n[a] == 512 && !getenv("CPC_VARIANT_X") &&
+            if (a == 0 && nc == 1 && !real && n[a] == 512 && !tune("CPC_VARIANT_X") &&
                 reg.find(FastKey<T>(n[a], VAR_XR2X, MODE_FWD)) != reg.end()) var = VAR_XR2X;
             // the 2 x (16 x 16) kernel also for the plain y passes of 512-point lines: 0.64 ms against 0.70 ms (8.8.8)
             // (single-rank only: in the chunked multi-rank layout its paired loads k / k+256 sit exactly one chunk,
@@ -324,27 +379,27 @@ template <typename T> struct PlanT : PlanBase {
             if (a == 1 && n[a] == 256 && reg.find(FastKey<T>(n[a], VAR_SMALL, MODE_FWD)) != reg.end()) var = VAR_SMALL;
             // 1024-point y lines: 64 KB tiles (4 lanes) so that two CTAs share an SM: 7.1 vs 8.2 ms at 1024^3.  Not for z,
             // whose 16 MB line stride makes 64-byte segments slower than the one-CTA 128-byte tiles (14.2 vs 13.3 ms)
-            if (a == 1 && n[a] == 1024 && desc.nranks == 1 && reg.find(FastKey<T>(n[a], VAR_SLIM, MODE_FWD)) != reg.end())
+            if (a == 1 && n[a] == 1024 && !multi_tr && reg.find(FastKey<T>(n[a], VAR_SLIM, MODE_FWD)) != reg.end())
                 var = VAR_SLIM;
-            if (a == 1 && (n[a] == 512 || n[a] == 256) && desc.nranks == 1 &&
+            if (a == 1 && (n[a] == 512 || n[a] == 256) && !multi_tr &&
                 reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FWD)) != reg.end()) var = VAR_R2X;
             {
                 const char *names[3] = { "CPC_VARIANT_X", "CPC_VARIANT_Y", "CPC_VARIANT_Z" };
-                const char *ov = getenv(names[a]);
+                const char *ov = tune(names[a]);
                 if (ov && *ov) var = atoi(ov);      // tuning hook (tools/), not part of the ABI
             }
             const int nfast = (real && !real_promote && a == 0) ? n2 : n[a];     // r2c: nx real points = nx/2 complex
             if (real && !real_promote && a == 0) var = VAR_XMAP;
             // contiguous 256-point lines (complex nx = 256, or the r2c / c2r pass of real nx = 512): half a warp per line
-            if (a == 0 && nc == 1 && nfast == 256 && !getenv("CPC_VARIANT_X") &&
+            if (a == 0 && nc == 1 && nfast == 256 && !tune("CPC_VARIANT_X") &&
                 reg.find(FastKey<T>(256, VAR_XR2X, real ? MODE_R2C : MODE_FWD)) != reg.end()) var = VAR_XR2X;
             if (reg.find(FastKey<T>(nfast, var, MODE_FWD)) == reg.end() && var != VAR_XMAP) var = VAR_NARROW;
             auto it = reg.find(FastKey<T>(nfast, var, MODE_FWD));
             if (it != reg.end() && a == 2 && reg.find(FastKey<T>(n[a], var, MODE_FUSED_SEP)) == reg.end()) it = reg.end();
             // multi-rank fast kernels address chunks with shifts: ny/nranks and nz/nranks must be powers of two
-            if (it != reg.end() && desc.nranks > 1 && a >= 1 && ((nyl & (nyl - 1)) != 0 || (nzl & (nzl - 1)) != 0)) it = reg.end();
+            if (it != reg.end() && multi_tr && a >= 1 && ((nyl & (nyl - 1)) != 0 || (nzl & (nzl - 1)) != 0)) it = reg.end();
             // multi-rank plans push / chunk their y and z stores: only variants with a general-addressing build
-            if (it != reg.end() && desc.nranks > 1 && a >= 1 &&
+            if (it != reg.end() && multi_tr && a >= 1 &&
                 reg.find(FastKey<T>(nfast, var, MODE_FWD + GEN_BIT)) == reg.end()) {
                 var = VAR_WIDE;
                 it = reg.find(FastKey<T>(nfast, var, MODE_FWD + GEN_BIT)) != reg.end() ? reg.find(FastKey<T>(nfast, var, MODE_FWD))
@@ -358,7 +413,7 @@ template <typename T> struct PlanT : PlanBase {
                 int rc_t = build_stage_table(it->second.radix, &stw[a]);
                 if (rc_t) return rc_t;
                 // multi-rank: the 2 x (R0 x R1) kernel for y passes that run on the local slab (no split)
-                if (a == 1 && desc.nranks > 1 && (n[a] == 512 || n[a] == 256) && var != VAR_R2X) {
+                if (a == 1 && multi_tr && (n[a] == 512 || n[a] == 256) && var != VAR_R2X) {
                     auto il = reg.find(FastKey<T>(n[a], VAR_R2X, MODE_FWD));
                     if (il != reg.end() && il->second.tx == it->second.tx && il->second.smem <= (size_t)dev_smem) {
                         c.variant_local = VAR_R2X;
@@ -448,26 +503,59 @@ template <typename T> struct PlanT : PlanBase {
                                       dev_smem));
         CPC_TRACE("func attributes set");
         CPC_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        CPC_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+        CPC_CUDA(cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming));
+        CPC_CUDA(cudaEventCreateWithFlags(&join_ev, cudaEventDisableTiming));
         if (desc.nranks > 1) {
             int rc = dist_init(dist, desc.nranks, desc.rank, desc.nccl_unique_id, device);
             if (rc) return rc;
+            // Peer mapping (CUDA IPC over NVLink) serves the carry exchange and the fused transposes; without it
+            // (or with the tuning hook CPC_DIST_MODE=nccl) both fall back to NCCL collectives.
+            const char *mode = tune("CPC_DIST_MODE");
+            want_p2p = !(mode && strcmp(mode, "nccl") == 0) && desc.nranks <= CPC_MAX_PEERS;
             if (!real && nc == 1) {
                 zslab_e = zsolve_points_per_thread(nzl);
-                CPC_CUDA(cudaMalloc(&ebuf, sizeof(C) * (size_t)n[0] * n[1]));
-                CPC_CUDA(cudaMalloc(&ecat, sizeof(C) * (size_t)n[0] * n[1] * desc.nranks));
+                const long long L = (long long)n[0] * n[1];
+                lsub = (L + desc.nranks - 1) / desc.nranks;
+                CPC_CUDA(cudaMalloc(&ebuf, sizeof(double2) * (size_t)L));
+                CPC_CUDA(cudaMalloc(&zinbuf, sizeof(double2) * (size_t)L));
+                CPC_CUDA(cudaMalloc(&gbuf, sizeof(double2) * (size_t)lsub * desc.nranks));
+                if (want_p2p) {
+                    int r1 = dist_map_peers(dist, gbuf, peer_g, device, stream);
+                    int r2 = r1 == CPC_OK ? dist_map_peers(dist, zinbuf, peer_z, device, stream) : r1;
+                    if (r1 == CPC_OK && r2 != CPC_OK) dist_unmap_peers(dist, peer_g);
+                    carry_p2p = (r1 == CPC_OK && r2 == CPC_OK);
+                    if (!carry_p2p && r1 != CPC_ERR_UNSUPPORTED && r2 != CPC_ERR_UNSUPPORTED) return r1 ? r1 : r2;
+                }
+                if (!carry_p2p) {                 // all-gather fallback: every rank holds every rank's end values
+                    cudaFree(gbuf);
+                    gbuf = nullptr;
+                    CPC_CUDA(cudaMalloc(&gbuf, sizeof(double2) * (size_t)L * desc.nranks));
+                }
             }
-            CPC_CUDA(cudaMalloc(&sendbuf, sizeof(C) * nloc));
-            CPC_CUDA(cudaMalloc(&tbuf, sizeof(C) * nloc));
-            // Fused transposes need every peer's buffers mapped (CUDA IPC over NVLink); otherwise NCCL all-to-all.
-            const char *mode = getenv("CPC_DIST_MODE");
-            const bool want_p2p = !(mode && strcmp(mode, "nccl") == 0) && desc.nranks <= CPC_MAX_PEERS;
-            if (want_p2p) {
-                int r1 = dist_map_peers(dist, tbuf, peer_t, device, stream);
-                int r2 = r1 == CPC_OK ? dist_map_peers(dist, sendbuf, peer_s, device, stream) : r1;
-                if (r1 == CPC_OK && r2 != CPC_OK) dist_unmap_peers(dist, peer_t);
-                p2p = (r1 == CPC_OK && r2 == CPC_OK);
-                if (!p2p && r1 != CPC_ERR_UNSUPPORTED && r2 != CPC_ERR_UNSUPPORTED) return r1 ? r1 : r2;
-            }
+        }
+        return CPC_OK;
+    }
+
+    // Buffers of the transposing schedule (two slabs, IPC-mapped into every peer when possible): allocated the first
+    // time a symbol needs that schedule.  Collective: every rank reaches it in the same call (the symbol is the same
+    // on all ranks).
+    int ensure_transpose_buffers()
+    {
+        if (tbuf_tried) return (sendbuf && tbuf) ? CPC_OK : CPC_ERR_NOMEM;
+        tbuf_tried = true;
+        if (n[1] % desc.nranks != 0) {
+            set_error("the transposing multi-rank schedule needs ny divisible by nranks (ny=%d nranks=%d)", n[1], desc.nranks);
+            return CPC_ERR_UNSUPPORTED;
+        }
+        CPC_CUDA(cudaMalloc(&sendbuf, sizeof(C) * nloc));
+        CPC_CUDA(cudaMalloc(&tbuf, sizeof(C) * nloc));
+        if (want_p2p) {
+            int r1 = dist_map_peers(dist, tbuf, peer_t, device, stream);
+            int r2 = r1 == CPC_OK ? dist_map_peers(dist, sendbuf, peer_s, device, stream) : r1;
+            if (r1 == CPC_OK && r2 != CPC_OK) dist_unmap_peers(dist, peer_t);
+            p2p = (r1 == CPC_OK && r2 == CPC_OK);
+            if (!p2p && r1 != CPC_ERR_UNSUPPORTED && r2 != CPC_ERR_UNSUPPORTED) return r1 ? r1 : r2;
         }
         return CPC_OK;
     }
@@ -702,11 +790,47 @@ template <typename T> struct PlanT : PlanBase {
             std::vector<C> ht(len, mk<T>((T)1, (T)0));
             for (int m = 0; m < n[a]; ++m) ht[m] = mk<T>((T)h[a][m].x, (T)h[a][m].y);
             if (!sym_tab[a]) CPC_CUDA(cudaMalloc(&sym_tab[a], sizeof(C) * len));
-            if (!sym_tab64[a]) CPC_CUDA(cudaMalloc(&sym_tab64[a], sizeof(double2) * n[a]));
+            std::vector<double2> h64(len, make_double2(1.0, 0.0));
+            for (int m = 0; m < n[a]; ++m) h64[m] = h[a][m];
+            if (!sym_tab64[a]) CPC_CUDA(cudaMalloc(&sym_tab64[a], sizeof(double2) * len));
             CPC_CUDA(cudaMemcpyAsync(sym_tab[a], ht.data(), sizeof(C) * len, cudaMemcpyHostToDevice, stream));
-            CPC_CUDA(cudaMemcpyAsync(sym_tab64[a], h[a].data(), sizeof(double2) * n[a], cudaMemcpyHostToDevice, stream));
+            CPC_CUDA(cudaMemcpyAsync(sym_tab64[a], h64.data(), sizeof(double2) * len, cudaMemcpyHostToDevice, stream));
             CPC_CUDA(cudaStreamSynchronize(stream));
         }
+        return CPC_OK;
+    }
+
+    // Separable symbol from the three 1-D tables h[a][m] (already multiplied by lambda; the "+1" rides on y).
+    // Decides whether the middle pass may run as the cyclic recurrence of zsolve.cuh: the z table must be
+    // lambda_z (1 - exp(-2 pi i k / nz)) -- the DFT of the reference's upwind column [1, -1, 0, ...]
+    // (build_transport_col, FftLinearSolver_3D.c:80-90) -- for some 0 <= lambda_z <= 4096, and
+    // Re(ax[i] + ay[j]) >= 1/2 everywhere, so that |lambda_z / (alpha + lambda_z)| < 1.
+    int set_symbol_tables(const std::vector<double2> (&h)[3])
+    {
+        int rc = upload_tables(h);
+        if (rc) return rc;
+        symbol_kind = CPC_SYMBOL_SEPARABLE;
+        double lz = 0.0;
+        if (n[2] > 1) {
+            double re, im;
+            exact_root(1, n[2], &re, &im);
+            lz = h[2][1].x / (1.0 - re);
+        }
+        zrec = std::isfinite(lz) && lz >= 0.0 && lz <= 4096.0;
+        const double tol = 1e-13 * (lz > 1.0 ? lz : 1.0);
+        for (int m = 0; zrec && m < n[2]; ++m) {
+            double re = 1.0, im = 0.0;
+            if (n[2] > 1) exact_root(m, n[2], &re, &im);
+            const double wr = n[2] > 1 ? lz * (1.0 - re) : 0.0, wi = n[2] > 1 ? -lz * im : 0.0;
+            if (std::fabs(h[2][m].x - wr) > tol || std::fabs(h[2][m].y - wi) > tol) zrec = false;
+        }
+        double mn[2] = { 0.0, 0.0 };
+        for (int a = 0; a < 2; ++a) {
+            mn[a] = h[a][0].x;
+            for (int m = 1; m < n[a]; ++m) mn[a] = h[a][m].x < mn[a] ? h[a][m].x : mn[a];
+        }
+        if (!(mn[0] + mn[1] >= 0.5)) zrec = false;
+        zrec_lz = lz;
         return CPC_OK;
     }
 
@@ -725,24 +849,7 @@ template <typename T> struct PlanT : PlanBase {
                 h[a][m].y = lam[a] * c[a][2 * m + 1];
             }
         }
-        int rc = upload_tables(h);
-        if (rc) return rc;
-        symbol_kind = CPC_SYMBOL_SEPARABLE;
-        // Is the z column the upwind [1, -1, 0, ...] (c_z_hat[k] = 1 - exp(-2 pi i k / nz)) with 0 <= lambda_z <= 4096,
-        // and Re(lambda_x c_x_hat), Re(lambda_y c_y_hat) >= 0 so that |lambda_z / (alpha + lambda_z)| < 1?  Then the
-        // middle pass is solved as a cyclic recurrence (zsolve.cuh) instead of forward FFT, division, backward FFT.
-        zrec = (lz >= 0.0 && lz <= 4096.0);
-        for (int m = 0; zrec && m < n[2]; ++m) {
-            double re = 1.0, im = 0.0;
-            if (n[2] > 1) exact_root(m, n[2], &re, &im);
-            const double wr = n[2] > 1 ? 1.0 - re : 0.0, wi = n[2] > 1 ? -im : 0.0;
-            if (std::fabs(cz[2 * m] - wr) > 1e-13 || std::fabs(cz[2 * m + 1] - wi) > 1e-13) zrec = false;
-        }
-        for (int a = 0; zrec && a < 2; ++a)
-            for (int m = 0; m < n[a]; ++m)
-                if (lam[a] * c[a][2 * m] < -1e-12) { zrec = false; break; }
-        zrec_lz = lz;
-        return CPC_OK;
+        return set_symbol_tables(h);
     }
 
     // Points per thread of the recurrence kernel for nz-point lines: nz / E segments, a multiple of the 32 / TX
@@ -757,22 +864,21 @@ template <typename T> struct PlanT : PlanBase {
             const int S = nz / E;
             if (S % QW) continue;
             const int threads = S * TX;
-            const int maxt = (sizeof(T) == 8 && E >= 16) ? 512 : 1024;
+            const int maxt = E >= 16 ? 512 : 1024;       // fp64 arithmetic whatever the storage type (zsolve.cuh)
             if (threads > maxt) continue;
             return E;
         }
         return 0;
     }
 
-    ZSolveArgs<T> zsolve_args() const
+    ZSolveArgs zsolve_args() const
     {
-        ZSolveArgs<T> a{};
-        a.ax = sym_tab[0]; a.ay = sym_tab[1];
-        a.lz = (T)zrec_lz;
-        a.scale = (T)((double)n[2] / (double)ntot);
+        ZSolveArgs a{};
+        a.ax = sym_tab64[0]; a.ay = sym_tab64[1];
+        a.lz = zrec_lz;
+        a.scale = (double)n[2] / (double)ntot;
         a.n = n[2];
-        a.ecat = ecat; a.eout = ebuf;
-        a.nranks = desc.nranks; a.rank = desc.rank;
+        a.zin = zinbuf;
         return a;
     }
 
@@ -781,15 +887,14 @@ template <typename T> struct PlanT : PlanBase {
                                         const PassGeom &g)
     {
         constexpr int TX = 128 / (int)sizeof(C);
-        ZSolveArgs<T> a = zsolve_args();
+        ZSolveArgs a = zsolve_args();
         a.nline = nline;
         // CTAs of at least 128 threads: several tiles per CTA when the line is short
         const int tpt = nline / E * TX;
         const int gpc = tpt >= 128 ? 1 : 128 / tpt;
         const int threads = tpt * gpc;
         grid = (grid + gpc - 1) / gpc;
-        if (kind == ZS_END) zsolve_kernel<T, E, false, ZS_END><<<grid, threads, 0, st>>>(in, out, g, a);
-        else if (kind == ZS_DIST) zsolve_kernel<T, E, false, ZS_DIST><<<grid, threads, 0, st>>>(in, out, g, a);
+        if (kind == ZS_DIST) zsolve_kernel<T, E, false, ZS_DIST><<<grid, threads, 0, st>>>(in, out, g, a);
         else if (gen) zsolve_kernel<T, E, true><<<grid, threads, 0, st>>>(in, out, g, a);
         else zsolve_kernel<T, E, false><<<grid, threads, 0, st>>>(in, out, g, a);
     }
@@ -808,7 +913,7 @@ template <typename T> struct PlanT : PlanBase {
     // z-slab plans with a transport symbol: no transpose at all (zsolve.cuh)
     bool use_zslab() const
     {
-        return desc.nranks > 1 && symbol_kind == CPC_SYMBOL_SEPARABLE && zrec && !zrec_off && zslab_e > 0 && ebuf && ecat;
+        return desc.nranks > 1 && symbol_kind == CPC_SYMBOL_SEPARABLE && zrec && !zrec_off && ebuf && gbuf && zinbuf;
     }
 
     int set_symbol_transport(double lx, double ly, double lz) override
@@ -834,27 +939,110 @@ template <typename T> struct PlanT : PlanBase {
         return CPC_OK;
     }
 
+    // Explicit eigenvalues (the Diag argument of solve_3D, FftLinearSolver_3D.c:166,174): this rank's z-slab of Diag.
+    // The reference only ever builds separable tables (build_diag_mat_vec_3D, :136-164), so the table is first
+    // tested for that structure -- Diag[k,j,i] = a[i] + b[j] + c[k], with a, b, c read off three of its lines --
+    // over all N entries on the GPU.  If it holds (to 1e-13 relative) the plan keeps three 1-D tables instead of N
+    // eigenvalues and the middle pass can take the recurrence form; otherwise 1 / (N Diag) is stored as a full table.
     int set_symbol_diag(const void *diag, int mem_kind) override
     {
-        if (desc.nranks != 1) { set_error("cpc_set_symbol_diag: single-rank plans only"); return CPC_ERR_UNSUPPORTED; }
         if (real) { set_error("cpc_set_symbol_diag: complex plans only (real plans take the transport / separable symbol)"); return CPC_ERR_UNSUPPORTED; }
         if (!diag) { set_error("null diag"); return CPC_ERR_ARG; }
-        int rc = ensure_inv_table();
-        if (rc) return rc;
-        const long long cells = ntot;          // one eigenvalue per cell; replicated over components if ncomp > 1
         if (nc != 1) { set_error("cpc_set_symbol_diag needs ncomp == 1"); return CPC_ERR_ARG; }
+        const long long cells = (long long)n[0] * n[1] * nzl;   // one eigenvalue per local cell
         const double2 *d = (const double2 *)diag;
         double2 *tmp = nullptr;
+        int rc = CPC_OK;
         if (mem_kind == CPC_MEM_HOST) {
             CPC_CUDA(cudaMalloc(&tmp, sizeof(double2) * cells));
             CPC_CUDA(cudaMemcpyAsync(tmp, diag, sizeof(double2) * cells, cudaMemcpyHostToDevice, stream));
+            h2d_bytes += sizeof(double2) * cells;
             d = tmp;
         }
-        invert_table_kernel<T><<<1184, 256, 0, stream>>>(d, inv_table, cells, 1.0 / (double)ntot);
+        rc = diag_try_separable(d);
+        if (rc == CPC_OK && symbol_kind != CPC_SYMBOL_SEPARABLE) rc = diag_to_table(d, cells);
+        cudaStreamSynchronize(stream);
+        if (tmp) cudaFree(tmp);
+        return rc;
+    }
+
+    // On return symbol_kind == CPC_SYMBOL_SEPARABLE iff the device table d is separable (on every rank).
+    int diag_try_separable(const double2 *d)
+    {
+        const int P = desc.nranks;
+        const size_t plane = (size_t)n[0] * n[1];
+        std::vector<double2> A(n[0]), B(n[1]), Cl(nzl), Call((size_t)n[2]);
+        CPC_CUDA(cudaMemcpyAsync(A.data(), d, sizeof(double2) * n[0], cudaMemcpyDeviceToHost, stream));
+        CPC_CUDA(cudaMemcpy2DAsync(B.data(), sizeof(double2), d, sizeof(double2) * n[0], sizeof(double2), n[1],
+                                   cudaMemcpyDeviceToHost, stream));
+        CPC_CUDA(cudaMemcpy2DAsync(Cl.data(), sizeof(double2), d, sizeof(double2) * plane, sizeof(double2), nzl,
+                                   cudaMemcpyDeviceToHost, stream));
+        CPC_CUDA(cudaStreamSynchronize(stream));
+        if (P > 1) {            // the z line of Diag through (0, 0) from every rank's slab
+            double2 *dz = nullptr;
+            CPC_CUDA(cudaMalloc(&dz, sizeof(double2) * (size_t)n[2]));
+            CPC_CUDA(cudaMemcpyAsync(dz + z0, Cl.data(), sizeof(double2) * nzl, cudaMemcpyHostToDevice, stream));
+            int rc = dist_allgather(dist, dz + z0, dz, sizeof(double2) * nzl, stream);
+            if (rc) { cudaFree(dz); return rc; }
+            CPC_CUDA(cudaMemcpyAsync(Call.data(), dz, sizeof(double2) * n[2], cudaMemcpyDeviceToHost, stream));
+            CPC_CUDA(cudaStreamSynchronize(stream));
+            cudaFree(dz);
+        } else {
+            Call = Cl;
+        }
+        // a[i] - a[0], b[j] - b[0] + Diag[0,0,0], c[k] - c[0]: their sum is Diag wherever Diag is separable
+        const double2 d00 = A[0], D000 = Call[0];
+        std::vector<double2> h[3];
+        h[0].resize(n[0]); h[1].resize(n[1]); h[2].resize(n[2]);
+        for (int i = 0; i < n[0]; ++i) h[0][i] = make_double2(A[i].x - d00.x, A[i].y - d00.y);
+        for (int j = 0; j < n[1]; ++j) h[1][j] = make_double2(B[j].x - d00.x + D000.x, B[j].y - d00.y + D000.y);
+        for (int k = 0; k < n[2]; ++k) h[2][k] = make_double2(Call[k].x - D000.x, Call[k].y - D000.y);
+        int rc = set_symbol_tables(h);
+        if (rc) return rc;
+        unsigned long long *res = nullptr, hres[2] = { 0, 0 };
+        CPC_CUDA(cudaMalloc(&res, 2 * sizeof(unsigned long long) + sizeof(float)));
+        CPC_CUDA(cudaMemsetAsync(res, 0, 2 * sizeof(unsigned long long) + sizeof(float), stream));
+        diag_check_separable_kernel<<<1184, 256, 0, stream>>>(d, sym_tab64[0], sym_tab64[1], sym_tab64[2] + z0, n[0], n[1],
+                                                              (long long)plane * nzl, res);
         ++launches;
         CPC_CUDA(cudaGetLastError());
+        CPC_CUDA(cudaMemcpyAsync(hres, res, sizeof(hres), cudaMemcpyDeviceToHost, stream));
         CPC_CUDA(cudaStreamSynchronize(stream));
-        if (tmp) cudaFree(tmp);
+        double maxdiff, maxabs;
+        memcpy(&maxdiff, &hres[0], 8);
+        memcpy(&maxabs, &hres[1], 8);
+        float bad = (maxdiff <= 1e-13 * (1.0 + maxabs)) ? 0.f : 1.f;
+        if (P > 1) {            // every rank must take the same decision
+            float *flag = (float *)(res + 2);
+            CPC_CUDA(cudaMemcpyAsync(flag, &bad, sizeof(float), cudaMemcpyHostToDevice, stream));
+            rc = dist_allreduce_sum_f32(dist, flag, 1, stream);
+            if (rc) { cudaFree(res); return rc; }
+            CPC_CUDA(cudaMemcpyAsync(&bad, flag, sizeof(float), cudaMemcpyDeviceToHost, stream));
+            CPC_CUDA(cudaStreamSynchronize(stream));
+        }
+        cudaFree(res);
+        if (bad != 0.f) { symbol_kind = CPC_SYMBOL_NONE; zrec = false; }
+        return CPC_OK;
+    }
+
+    // 1 / (N Diag) as a full table in the layout the fused z pass runs in (transposed for multi-rank plans)
+    int diag_to_table(const double2 *d, long long cells)
+    {
+        int rc = ensure_inv_table();
+        if (rc) return rc;
+        if (desc.nranks == 1) {
+            invert_table_kernel<T><<<1184, 256, 0, stream>>>(d, inv_table, cells, 1.0 / (double)ntot);
+            ++launches;
+            CPC_CUDA(cudaGetLastError());
+        } else {
+            if ((rc = ensure_transpose_buffers())) return rc;
+            invert_table_kernel<T><<<1184, 256, 0, stream>>>(d, tbuf, cells, 1.0 / (double)ntot);
+            slab_to_chunked_kernel<C><<<1184, 256, 0, stream>>>(tbuf, sendbuf, n[0], n[1], nyl, nzl);
+            launches += 2;
+            CPC_CUDA(cudaGetLastError());
+            if ((rc = alltoall(sendbuf, inv_table))) return rc;
+        }
+        CPC_CUDA(cudaStreamSynchronize(stream));
         symbol_kind = CPC_SYMBOL_TABLE; zrec = false;
         return CPC_OK;
     }
@@ -869,6 +1057,12 @@ template <typename T> struct PlanT : PlanBase {
         // Lambda = FFT3(col) lands in the layout the fused pass runs in (transposed for multi-rank plans).
         rc = transform_impl((const C *)col, inv_table, mem_kind, -1, /*out_is_device=*/true);
         if (rc) return rc;
+        // a column with entries on the axes only (the transport stencil) has a separable spectrum: keep three 1-D
+        // tables then, and the recurrence form of the middle pass if it applies (fp64 single-rank plans)
+        if (sizeof(T) == 8 && desc.nranks == 1) {
+            if ((rc = diag_try_separable((const double2 *)inv_table))) return rc;
+            if (symbol_kind == CPC_SYMBOL_SEPARABLE) return CPC_OK;
+        }
         invert_inplace_kernel<T><<<1184, 256, 0, stream>>>(inv_table, nloc, 1.0 / (double)ntot);
         ++launches;
         CPC_CUDA(cudaGetLastError());
@@ -885,6 +1079,16 @@ template <typename T> struct PlanT : PlanBase {
         wave_mu[0] = mx; wave_mu[1] = my; wave_mu[2] = mz;
         symbol_kind = CPC_SYMBOL_WAVE; zrec = false;
         return CPC_OK;
+    }
+
+    int set_option(int option, long long value) override
+    {
+        switch (option) {
+        case CPC_OPT_Z_RECURRENCE: zrec_off = (value == 0); return CPC_OK;
+        case CPC_OPT_L2_CHUNK_BYTES: l2_chunk_bytes = value < 0 ? (32ll << 20) : value; return CPC_OK;
+        case CPC_OPT_CHAIN_STREAMS: chain_streams = value >= 2 ? 2 : 1; return CPC_OK;
+        default: set_error("cpc_set_option: unknown option %d", option); return CPC_ERR_ARG;
+        }
     }
 
     int get_diag(void *diag, int mem_kind) override
@@ -923,47 +1127,118 @@ template <typename T> struct PlanT : PlanBase {
         return CPC_OK;
     }
 
-    int ensure_prof_events()
+    // ---- profiled applies: an event after every launch, durations summed per pass kind -------------------------
+    int prof_begin(float *pass_ms)
     {
-        if (!prof_ev_ok) {
-            for (auto &e : prof_ev) CPC_CUDA(cudaEventCreate(&e));
-            prof_ev_ok = true;
+        prof_on = pass_ms != nullptr;
+        prof_n = 0;
+        prof_kind.clear();
+        return prof_on ? prof_mark(-1) : CPC_OK;
+    }
+    int prof_mark(int kind)
+    {
+        if (!prof_on) return CPC_OK;
+        if (prof_n == prof_ev.size()) {
+            cudaEvent_t e;
+            CPC_CUDA(cudaEventCreate(&e));
+            prof_ev.push_back(e);
         }
+        CPC_CUDA(cudaEventRecord(prof_ev[prof_n++], stream));
+        prof_kind.push_back(kind);
+        return CPC_OK;
+    }
+    int prof_end(float *pass_ms, int *npasses, int nkinds)
+    {
+        if (!prof_on) return CPC_OK;
+        prof_on = false;
+        CPC_CUDA(cudaEventSynchronize(prof_ev[prof_n - 1]));
+        for (int i = 0; i < nkinds; ++i) pass_ms[i] = 0.f;
+        for (size_t i = 1; i < prof_n; ++i) {
+            float ms = 0.f;
+            CPC_CUDA(cudaEventElapsedTime(&ms, prof_ev[i - 1], prof_ev[i]));
+            if (prof_kind[i] >= 0 && prof_kind[i] < nkinds) pass_ms[prof_kind[i]] += ms;
+        }
+        if (npasses) *npasses = nkinds;
         return CPC_OK;
     }
 
-    // Single-rank apply on device pointers.  pass_ms != nullptr => record events around each pass.
+    // ---- L2-chained x / y passes -----------------------------------------------------------------------------
+    // planes per z-chunk; 0 = whole-array passes (nothing to chain, or the local array sits in L2 anyway)
+    int chain_planes() const
+    {
+        if (l2_chunk_bytes <= 0 || n[0] == 1 || n[1] == 1) return 0;
+        const long long plane = wx * n[1] * (long long)sizeof(C);
+        if (plane * nzl <= 2 * l2_chunk_bytes) return 0;
+        const long long p = l2_chunk_bytes / plane;
+        return (int)(p < 1 ? 1 : p);
+    }
+
+    // Forward x and y passes (src -> x, then in place), or backward y and x passes (in place on x), over the local
+    // planes.  With a chunk size the two passes of the pair run back to back on each z-chunk so that the second
+    // finds the chunk in L2; `after(zb, zc)` (optional) is queued behind the pair of each chunk.
+    // kinds: profile kinds of the two passes in launch order.
+    template <typename After>
+    int run_xy(bool forward, const C *src, C *x, const int kinds[2], After after)
+    {
+        int rc;
+        const int cp = chain_planes();
+        const int step = cp > 0 ? cp : nzl;
+        const bool two = cp > 0 && chain_streams >= 2 && !prof_on;
+        if (two) {
+            CPC_CUDA(cudaEventRecord(fork_ev, stream));
+            CPC_CUDA(cudaStreamWaitEvent(side_stream, fork_ev, 0));
+        }
+        int ci = 0;
+        for (int zb = 0; zb < nzl; zb += step, ++ci) {
+            const int zc = nzl - zb < step ? nzl - zb : step;
+            cudaStream_t st = (two && (ci & 1)) ? side_stream : stream;
+            if (forward) {
+                const C *cur = src;
+                for (int a = 0; a < 2; ++a) {
+                    if (n[a] == 1) continue;
+                    if ((rc = run_pass(a, MODE_FWD, cur, x, zb, zc, 0, st))) return rc;
+                    cur = x;
+                    if ((rc = prof_mark(kinds[a]))) return rc;
+                }
+                if (cur == src && src != x)        // both axes degenerate: the pair is a copy
+                    CPC_CUDA(cudaMemcpyAsync(x + (long long)zb * n[1] * wx, src + (long long)zb * n[1] * wx,
+                                             sizeof(C) * (size_t)zc * n[1] * wx, cudaMemcpyDeviceToDevice, st));
+            } else {
+                for (int a = 1; a >= 0; --a) {
+                    if (n[a] == 1) continue;
+                    if ((rc = run_pass(a, MODE_INV, x, x, zb, zc, 0, st))) return rc;
+                    if ((rc = prof_mark(kinds[1 - a]))) return rc;
+                }
+            }
+            if ((rc = after(zb, zc, st))) return rc;
+        }
+        if (two) {
+            CPC_CUDA(cudaEventRecord(join_ev, side_stream));
+            CPC_CUDA(cudaStreamWaitEvent(stream, join_ev, 0));
+        }
+        return CPC_OK;
+    }
+    static int no_after(int, int, cudaStream_t) { return CPC_OK; }
+
+    // Single-rank apply on device pointers.  pass_ms != nullptr => per-pass durations (CUDA events).
     int apply_device_single(const C *b, C *x, float *pass_ms, int *npasses)
     {
         const int fm = fused_mode();
-        int np = 0;
-        auto mark = [&](int i) -> int {
-            if (pass_ms) CPC_CUDA(cudaEventRecord(prof_ev[i], stream));
-            return CPC_OK;
-        };
-        if (pass_ms) { int rc = ensure_prof_events(); if (rc) return rc; }
-        int rc = mark(0);
-        if (rc) return rc;
-        const C *cur = b;
-        for (int a = 0; a < 2; ++a) {
-            if (n[a] == 1) continue;
-            if ((rc = run_pass(a, MODE_FWD, cur, x, 0, nzl, 0, stream))) return rc;
-            cur = x;
-            if ((rc = mark(++np))) return rc;
-        }
-        if ((rc = run_pass(2, fm, cur, x, 0, nzl, 0, stream))) return rc;
-        if ((rc = mark(++np))) return rc;
-        for (int a = 1; a >= 0; --a) {
-            if (n[a] == 1) continue;
-            if ((rc = run_pass(a, MODE_INV, x, x, 0, nzl, 0, stream))) return rc;
-            if ((rc = mark(++np))) return rc;
-        }
-        if (pass_ms) {
-            CPC_CUDA(cudaEventSynchronize(prof_ev[np]));
-            for (int i = 0; i < np; ++i) CPC_CUDA(cudaEventElapsedTime(&pass_ms[i], prof_ev[i], prof_ev[i + 1]));
-            if (npasses) *npasses = np;
-        }
-        return CPC_OK;
+        int rc;
+        // pass kinds in the order Fx, Fy, middle, By, Bx (degenerate axes have no pass)
+        int k = 0, kf[2] = { -1, -1 }, kb[2] = { -1, -1 };
+        for (int a = 0; a < 2; ++a)
+            if (n[a] > 1) kf[a] = k++;
+        const int kz = k++;
+        for (int a = 1; a >= 0; --a)
+            if (n[a] > 1) kb[1 - a] = k++;
+        if ((rc = prof_begin(pass_ms))) return rc;
+        const bool copy_first = (n[0] == 1 && n[1] == 1);
+        if (!copy_first && (rc = run_xy(true, b, x, kf, no_after))) return rc;
+        if ((rc = run_pass(2, fm, copy_first ? b : x, x, 0, nzl, 0, stream))) return rc;
+        if ((rc = prof_mark(kz))) return rc;
+        if (!copy_first && (rc = run_xy(false, x, x, kb, no_after))) return rc;
+        return prof_end(pass_ms, npasses, k);
     }
 
     // Multi-rank (z-slab) apply: Fx, Fy(split store) | all-to-all | fused z | all-to-all | By(split load), Bx
@@ -973,46 +1248,68 @@ template <typename T> struct PlanT : PlanBase {
         return dist_alltoall(dist, send, recv, chunk, stream);
     }
 
-    // Multi-rank apply for a transport symbol: Fx, Fy on the local z-slab, the z recurrence in two local sweeps with
-    // an all-gather of the slabs' end values in between (nx ny complex numbers per rank), By, Bx.  No transposes.
+    // Multi-rank apply for a transport symbol: no transposes.  [Fx, Fy, end-value accumulation] z-chunk by z-chunk
+    // (L2-chained), the carry exchange (zsolve.cuh), the z solve on the local slab from the exchanged carry-in,
+    // [By, Bx] z-chunk by z-chunk.  Pass kinds: Fx, Fy, carry (end values + exchange), z solve, By, Bx.
     int apply_device_zslab(const C *b, C *x, float *pass_ms, int *npasses)
     {
-        int np = 0, rc;
-        auto mark = [&](int i) -> int {
-            if (pass_ms) CPC_CUDA(cudaEventRecord(prof_ev[i], stream));
-            return CPC_OK;
+        int rc;
+        if ((rc = prof_begin(pass_ms))) return rc;
+        const long long L = (long long)n[0] * n[1];
+        ZSolveArgs za = zsolve_args();
+        za.nline = nzl;
+        const int kf[2] = { 0, 1 }, kb[2] = { 4, 5 };
+        const int egrid = (int)((L + 255) / 256);
+        auto end_acc = [&](int zb, int zc, cudaStream_t st) -> int {
+            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(x, L, n[0], zb, zc, zb > 0 ? 1 : 0, ebuf, za);
+            ++launches;
+            CPC_CUDA(cudaGetLastError());
+            return prof_mark(2);
         };
-        if (pass_ms && (rc = ensure_prof_events())) return rc;
-        if ((rc = mark(0))) return rc;
-        const C *cur = b;
-        for (int a = 0; a < 2; ++a) {
-            if (n[a] == 1) continue;
-            if ((rc = run_pass(a, MODE_FWD, cur, x, 0, nzl, 0, stream))) return rc;
-            cur = x;
-            if ((rc = mark(++np))) return rc;
+        // the end values chain from chunk to chunk, so the chunks stay on one stream
+        const int cs = chain_streams;
+        chain_streams = 1;
+        rc = run_xy(true, b, x, kf, end_acc);
+        chain_streams = cs;
+        if (rc) return rc;
+        const int cgrid = 148 * 8;
+        if (carry_p2p) {
+            ZCarryPeers gp{}, zp{};
+            for (int q = 0; q < desc.nranks; ++q) { gp.p[q] = (double2 *)peer_g[q]; zp.p[q] = (double2 *)peer_z[q]; }
+            zs_carry_push_kernel<<<cgrid, 256, 0, stream>>>(ebuf, L, lsub, desc.rank, gp);
+            ++launches;
+            CPC_CUDA(cudaGetLastError());
+            if ((rc = dist_barrier(dist, stream))) return rc;            // every rank's end values have landed
+            const long long line0 = lsub * desc.rank;
+            const long long cnt = line0 >= L ? 0 : (L - line0 < lsub ? L - line0 : lsub);
+            if (cnt > 0) {
+                zs_carry_owner_kernel<<<(int)((cnt + 255) / 256), 256, 0, stream>>>(gbuf, lsub, line0, cnt, n[0], nzl, desc.nranks,
+                                                                                 desc.rank, 0, zp, za);
+                ++launches;
+                CPC_CUDA(cudaGetLastError());
+            }
+            if ((rc = dist_barrier(dist, stream))) return rc;            // every line's carry-in has landed
+        } else {
+            if ((rc = dist_allgather(dist, ebuf, gbuf, sizeof(double2) * (size_t)L, stream))) return rc;
+            ZCarryPeers zp{};
+            zp.p[0] = zinbuf;
+            zs_carry_owner_kernel<<<cgrid, 256, 0, stream>>>(gbuf, L, 0, L, n[0], nzl, desc.nranks, desc.rank, 1, zp, za);
+            ++launches;
+            CPC_CUDA(cudaGetLastError());
         }
-        long long off = 0;
-        const PassGeom g = make_geom(2, 128 / (int)sizeof(C), 0, nzl, 0, &off);
-        launch_zsolve_e(zslab_e, ZS_END, false, nzl, g.ntiles, stream, cur, x, g);
+        if ((rc = prof_mark(2))) return rc;
+        if (zslab_e > 0 && !zslab_line) {
+            long long off = 0;
+            const PassGeom g = make_geom(2, 128 / (int)sizeof(C), 0, nzl, 0, &off);
+            launch_zsolve_e(zslab_e, ZS_DIST, false, nzl, g.ntiles, stream, x, x, g);
+        } else {
+            zs_dist_line_kernel<T><<<egrid, 256, 0, stream>>>(x, L, n[0], nzl, za);
+        }
         ++launches;
         CPC_CUDA(cudaGetLastError());
-        if ((rc = dist_allgather(dist, ebuf, ecat, sizeof(C) * (size_t)n[0] * n[1], stream))) return rc;
-        if ((rc = mark(++np))) return rc;
-        launch_zsolve_e(zslab_e, ZS_DIST, false, nzl, g.ntiles, stream, cur, x, g);
-        ++launches;
-        CPC_CUDA(cudaGetLastError());
-        if ((rc = mark(++np))) return rc;
-        for (int a = 1; a >= 0; --a) {
-            if (n[a] == 1) continue;
-            if ((rc = run_pass(a, MODE_INV, x, x, 0, nzl, 0, stream))) return rc;
-            if ((rc = mark(++np))) return rc;
-        }
-        if (pass_ms) {
-            CPC_CUDA(cudaEventSynchronize(prof_ev[np]));
-            for (int i = 0; i < np; ++i) CPC_CUDA(cudaEventElapsedTime(&pass_ms[i], prof_ev[i], prof_ev[i + 1]));
-            if (npasses) *npasses = np;
-        }
-        return CPC_OK;
+        if ((rc = prof_mark(3))) return rc;
+        if ((rc = run_xy(false, x, x, kb, no_after))) return rc;
+        return prof_end(pass_ms, npasses, 6);
     }
 
     int apply_device_dist(const C *b, C *x, float *pass_ms, int *npasses)
@@ -1020,58 +1317,50 @@ template <typename T> struct PlanT : PlanBase {
         if (use_zslab()) return apply_device_zslab(b, x, pass_ms, npasses);
         const int fm = fused_mode();
         int np = 0, rc;
-        auto mark = [&](int i) -> int {
-            if (pass_ms) CPC_CUDA(cudaEventRecord(prof_ev[i], stream));
-            return CPC_OK;
-        };
-        if (pass_ms && (rc = ensure_prof_events())) return rc;
-        if ((rc = mark(0))) return rc;
+        if ((rc = ensure_transpose_buffers())) return rc;
+        if ((rc = prof_begin(pass_ms))) return rc;
         const C *cur = b;
         if (n[0] > 1) {
             if ((rc = run_pass(0, MODE_FWD, cur, x, 0, nzl, 0, stream))) return rc;
             cur = x;
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(np++))) return rc;
         }
         if (p2p) {
             // transposes fused into the producing kernels: stores go straight to the owning rank over NVLink.
             // Leading barrier: no peer may still be reading its buffers from an earlier call when pushes start.
             if ((rc = dist_barrier(dist, stream))) return rc;
             if ((rc = run_pass(1, MODE_FWD, cur, tbuf, 0, nzl, 0, stream, 3))) return rc;    // Fy -> peers' y-slabs
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(np++))) return rc;
             if ((rc = dist_barrier(dist, stream))) return rc;                                // all pushes have landed
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(np++))) return rc;
             if ((rc = run_pass(2, fm, tbuf, sendbuf, 0, n[2], 1, stream, 4))) return rc;     // fused z -> peers' z-slabs
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(np++))) return rc;
             if ((rc = dist_barrier(dist, stream))) return rc;
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(np++))) return rc;
         } else {
             if ((rc = run_pass(1, MODE_FWD, cur, sendbuf, 0, nzl, 0, stream, 1))) return rc; // Fy, chunked store
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(np++))) return rc;
             if ((rc = alltoall(sendbuf, tbuf))) return rc;                                   // z-slab -> y-slab
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(np++))) return rc;
             if ((rc = run_pass(2, fm, tbuf, tbuf, 0, n[2], 1, stream))) return rc;           // Fz . 1/(N Lambda) . Bz
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(np++))) return rc;
             if ((rc = alltoall(tbuf, sendbuf))) return rc;                                   // y-slab -> z-slab
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(np++))) return rc;
         }
         if ((rc = run_pass(1, MODE_INV, sendbuf, x, 0, nzl, 0, stream, 2))) return rc;       // By, chunked load
-        if ((rc = mark(++np))) return rc;
+        if ((rc = prof_mark(np++))) return rc;
         if (n[0] > 1) {
             if ((rc = run_pass(0, MODE_INV, x, x, 0, nzl, 0, stream))) return rc;
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(np++))) return rc;
         }
-        if (pass_ms) {
-            CPC_CUDA(cudaEventSynchronize(prof_ev[np]));
-            for (int i = 0; i < np; ++i) CPC_CUDA(cudaEventElapsedTime(&pass_ms[i], prof_ev[i], prof_ev[i + 1]));
-            if (npasses) *npasses = np;
-        }
-        return CPC_OK;
+        return prof_end(pass_ms, npasses, np);
     }
 
     // forward: in = z-slab, out = transposed (all z, local y range); backward: the reverse
     int transform_device_dist(const C *in, C *out, int dir)
     {
         int rc;
+        if ((rc = ensure_transpose_buffers())) return rc;
         if (dir < 0) {
             const C *cur = in;
             if (n[0] > 1) {
@@ -1132,47 +1421,52 @@ template <typename T> struct PlanT : PlanBase {
         return CPC_OK;
     }
 
-    // Real plan, device pointers: r2c x | Fy | fused z | By | c2r x, the middle three on the half spectrum.
+    // Real plan, device pointers: r2c x | Fy | fused z | By | c2r x, the middle three on the half spectrum; the
+    // (r2c, Fy) and (By, c2r) pairs run z-chunk by z-chunk like the complex plans' (L2-chained).
     int apply_device_real(const T *b, T *x, float *pass_ms, int *npasses)
     {
-        int np = 0, rc;
-        auto mark = [&](int i) -> int {
-            if (pass_ms) CPC_CUDA(cudaEventRecord(prof_ev[i], stream));
-            return CPC_OK;
-        };
-        if (pass_ms && (rc = ensure_prof_events())) return rc;
-        if ((rc = mark(0))) return rc;
+        int rc;
+        if ((rc = prof_begin(pass_ms))) return rc;
         const long long N = (long long)n[0] * n[1] * n[2];
         if (real_promote) {
             real_to_complex_kernel<T><<<1184, 256, 0, stream>>>(b, work, N);
             ++launches;
-            if ((rc = apply_device_single(work, work, nullptr, nullptr))) return rc;
+            const bool on = prof_on;
+            prof_on = false;
+            rc = apply_device_single(work, work, nullptr, nullptr);
+            prof_on = on;
+            if (rc) return rc;
             complex_to_real_kernel<T><<<1184, 256, 0, stream>>>(work, x, N);
             ++launches;
             CPC_CUDA(cudaGetLastError());
-            if ((rc = mark(++np))) return rc;
-        } else {
-            if ((rc = run_real_x(true, b, work, 0, n[2], stream))) return rc;
-            if ((rc = mark(++np))) return rc;
-            if (n[1] > 1) {
-                if ((rc = run_pass(1, MODE_FWD, work, work, 0, n[2], 0, stream))) return rc;
-                if ((rc = mark(++np))) return rc;
-            }
-            if ((rc = run_pass(2, fused_mode(), work, work, 0, n[2], 0, stream))) return rc;
-            if ((rc = mark(++np))) return rc;
-            if (n[1] > 1) {
-                if ((rc = run_pass(1, MODE_INV, work, work, 0, n[2], 0, stream))) return rc;
-                if ((rc = mark(++np))) return rc;
-            }
-            if ((rc = run_real_x(false, work, x, 0, n[2], stream))) return rc;
-            if ((rc = mark(++np))) return rc;
+            if ((rc = prof_mark(0))) return rc;
+            return prof_end(pass_ms, npasses, 1);
         }
-        if (pass_ms) {
-            CPC_CUDA(cudaEventSynchronize(prof_ev[np]));
-            for (int i = 0; i < np; ++i) CPC_CUDA(cudaEventElapsedTime(&pass_ms[i], prof_ev[i], prof_ev[i + 1]));
-            if (npasses) *npasses = np;
+        int k = 0;
+        const int kx0 = k++, ky0 = n[1] > 1 ? k++ : -1, kz = k++, ky1 = n[1] > 1 ? k++ : -1, kx1 = k++;
+        const int cp = chain_planes();
+        const int step = cp > 0 ? cp : n[2];
+        for (int zb = 0; zb < n[2]; zb += step) {
+            const int zc = n[2] - zb < step ? n[2] - zb : step;
+            if ((rc = run_real_x(true, b, work, zb, zc, stream))) return rc;
+            if ((rc = prof_mark(kx0))) return rc;
+            if (n[1] > 1) {
+                if ((rc = run_pass(1, MODE_FWD, work, work, zb, zc, 0, stream))) return rc;
+                if ((rc = prof_mark(ky0))) return rc;
+            }
         }
-        return CPC_OK;
+        if ((rc = run_pass(2, fused_mode(), work, work, 0, n[2], 0, stream))) return rc;
+        if ((rc = prof_mark(kz))) return rc;
+        for (int zb = 0; zb < n[2]; zb += step) {
+            const int zc = n[2] - zb < step ? n[2] - zb : step;
+            if (n[1] > 1) {
+                if ((rc = run_pass(1, MODE_INV, work, work, zb, zc, 0, stream))) return rc;
+                if ((rc = prof_mark(ky1))) return rc;
+            }
+            if ((rc = run_real_x(false, work, x, zb, zc, stream))) return rc;
+            if ((rc = prof_mark(kx1))) return rc;
+        }
+        return prof_end(pass_ms, npasses, k);
     }
 
     int apply_real(const void *b, void *x, int mem_kind, float *pass_ms, int *npasses)
@@ -1355,8 +1649,8 @@ template <typename T> struct PlanT : PlanBase {
         info->passes_per_apply = 1 + 2 * ((n[0] > 1) + (n[1] > 1));
         info->dist_mode = desc.nranks == 1 ? 0 : (use_zslab() ? 3 : (p2p ? 2 : 1));
         for (int a = 0; a < 3; ++a) info->fast_path[a] = cfg[a].fast ? 1 : 0;
-        if (symbol_kind == CPC_SYMBOL_SEPARABLE && zrec && !zrec_off && zrec_e > 0 && nc == 1 &&
-            (desc.nranks == 1 || (nzl & (nzl - 1)) == 0 || use_zslab()))
+        if (desc.nranks > 1 ? use_zslab()
+                            : (symbol_kind == CPC_SYMBOL_SEPARABLE && zrec && !zrec_off && zrec_e > 0 && nc == 1))
             info->fast_path[2] = 2;
         info->local_elems = nloc;
         info->bytes_per_apply_alg = 5ll * 2 * nloc * (long long)(real ? sizeof(T) : sizeof(C));

@@ -22,32 +22,40 @@
 //   3. x_k = r (y_k + c^(k - sE + 1) carry) / (nx ny), stored straight to HBM (or pushed to a peer, GEN builds).
 //
 // z-slab plans (one process per GPU) need NO transpose for this pass: a recurrence only hands a carry from one slab to
-// the next.  Sweep 1 (ZS_END, read-only) computes the value at the end of every local line from a zero carry-in,
-// the P x nx x ny end values are all-gathered (4 MB per rank at 512^2 instead of two 2 GB all-to-alls per apply), and
-// sweep 2 (ZS_DIST) solves the local lines with the carry that closes the cycle over the ranks.
+// the next.  The value at the end of every local line from a zero carry-in is accumulated plane by plane
+// (zs_end_accum_kernel; it rides behind the forward y pass of the same z-chunk while that chunk is still in L2), the
+// carries are exchanged -- each rank owns 1/P of the (kx, ky) lines, gathers their P end values through peer stores,
+// closes the cycle over the ranks and pushes one carry-in per line back to every rank (zs_carry_*_kernel; 2 x 3.5 MB
+// over NVLink per rank at 512^2 and 8 ranks instead of two 235 MB all-to-alls) -- and the second sweep (ZS_DIST)
+// solves the local lines from that carry-in.
+//
+// All arithmetic of this file is fp64 whatever the storage type: the decay 1 - c = 1 / (alpha + lambda_z) carries a
+// relative rounding error of eps (1 + lambda_z), which in fp32 would cost complex64 / float32 plans 2-3 digits
+// against the FFT form at lambda_z = 55 .. 4096.  The pass stays HBM-bound either way.
 #pragma once
 #include "fft_pass.cuh"
 
 namespace cpc {
 
-template <typename T> struct ZSolveArgs {
-    const cplx_t<T> *ax, *ay;     // lambda_x c_x_hat[kx]  and  1 + lambda_y c_y_hat[ky]   (the plan's symbol tables)
-    T lz;                         // lambda_z
-    T scale;                      // 1 / (nx ny): the x and y transforms are unnormalised, the z solve is exact
+struct ZSolveArgs {
+    const double2 *ax, *ay;       // lambda_x c_x_hat[kx]  and  1 + lambda_y c_y_hat[ky]   (the plan's fp64 symbol tables)
+    double lz;                    // lambda_z
+    double scale;                 // 1 / (nx ny): the x and y transforms are unnormalised, the z solve is exact
     int n;                        // nz
-    int nline;                    // points of the line a tile holds: nz, or nz / P in the z-slab sweeps
-    // z-slab plans (DIST builds): the line is this rank's nz / P planes; the carry into its first plane comes from the
-    // end values of every rank's slab (zero carry-in), all-gathered into ecat[P][nx ny]
-    const cplx_t<T> *ecat;
-    cplx_t<T> *eout;              // END builds: where this rank's end values go, [nx ny]
-    int nranks, rank;
+    int nline;                    // points of the line a tile holds: nz, or nz / P in the z-slab sweep
+    const double2 *zin;           // ZS_DIST: carry into the first local plane of every (kx, ky) line, [nx ny]
 };
 
 enum ZSolveKind {
     ZS_CYCLIC = 0,    // the whole z line is in the tile: close the cycle inside the kernel (single GPU, transposed slabs)
-    ZS_END = 1,       // z-slab plans, first sweep: only the value at the end of the local line, zero carry-in (read-only)
-    ZS_DIST = 2       // z-slab plans, second sweep: the local line with the carry computed from ecat
+    ZS_DIST = 2       // z-slab plans: the local part of the line with the carry-in computed by zs_carry_owner_kernel
 };
+
+__device__ __forceinline__ double2 to_d2(double2 v) { return v; }
+__device__ __forceinline__ double2 to_d2(float2 v) { return make_double2((double)v.x, (double)v.y); }
+template <typename C> __device__ __forceinline__ C from_d2(double2 v);
+template <> __device__ __forceinline__ double2 from_d2<double2>(double2 v) { return v; }
+template <> __device__ __forceinline__ float2 from_d2<float2>(double2 v) { return make_float2((float)v.x, (float)v.y); }
 
 // z^P by binary exponentiation, unrolled at compile time
 template <int P, typename C> __device__ __forceinline__ C cpow(C z)
@@ -56,16 +64,36 @@ template <int P, typename C> __device__ __forceinline__ C cpow(C z)
     else if constexpr (P % 2 == 0) { const C h = cpow<P / 2>(z); return cmul(h, h); }
     else return cmul(z, cpow<P - 1>(z));
 }
+// z^p, runtime exponent p >= 1
+__device__ __forceinline__ double2 cpow_rt(double2 z, int p)
+{
+    double2 r = make_double2(1.0, 0.0);
+    while (p > 0) {
+        if (p & 1) r = cmul(r, z);
+        z = cmul(z, z);
+        p >>= 1;
+    }
+    return r;
+}
 
-// largest CTA the kernel is compiled for: E = 16 complex128 points are 64 registers of data, so <= 128 registers
-template <typename T, int E> struct ZSolveMaxThreads { static constexpr int v = (sizeof(T) == 8 && E >= 16) ? 512 : 1024; };
+// c = lambda_z / (alpha + lambda_z) and r = 1 / (alpha + lambda_z) of line (x, y)
+__device__ __forceinline__ void zs_coeffs(const ZSolveArgs &a, int x, int y, double2 &r, double2 &c)
+{
+    const double2 alpha = cadd(a.ax[x], a.ay[y]);
+    r = crecip_scaled<double>(make_double2(alpha.x + a.lz, alpha.y), 1.0);
+    c = make_double2(a.lz * r.x, a.lz * r.y);
+}
+
+// largest CTA the kernel is compiled for: E = 16 points are 64 registers of fp64 data, so <= 128 registers
+template <int E> struct ZSolveMaxThreads { static constexpr int v = (E >= 16) ? 512 : 1024; };
 
 template <typename T, int E, bool GEN, int KIND = ZS_CYCLIC>
-__global__ void __launch_bounds__((ZSolveMaxThreads<T, E>::v), 1)
-zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, const PassGeom g, const ZSolveArgs<T> a)
+__global__ void __launch_bounds__((ZSolveMaxThreads<E>::v), 1)
+zsolve_kernel(const cplx_t<T> *in, cplx_t<T> *out, const PassGeom g, const ZSolveArgs a)
 {
-    using C = cplx_t<T>;
-    constexpr int TX = 128 / (int)sizeof(C);        // lanes = lines per tile
+    using CS = cplx_t<T>;                           // storage type
+    using C = double2;                              // arithmetic type
+    constexpr int TX = 128 / (int)sizeof(CS);       // lanes = lines per tile
     constexpr int QW = 32 / TX;                     // segments per warp
     __shared__ C agg_all[32 * TX];                  // warp aggregates [warp of the CTA][lane]
 
@@ -93,24 +121,22 @@ zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, con
     C v[E];
     if (active) {
         if (!GEN) {
-            const C *p = in + gbase + (long long)k0 * g.SI;
+            const CS *p = in + gbase + (long long)k0 * g.SI;
 #pragma unroll
-            for (int m = 0; m < E; ++m) v[m] = p[m * g.SI];
+            for (int m = 0; m < E; ++m) v[m] = to_d2(p[m * g.SI]);
         } else {
 #pragma unroll
-            for (int m = 0; m < E; ++m) v[m] = in[gbase + gen_in_off(g, k0 + m)];
+            for (int m = 0; m < E; ++m) v[m] = to_d2(in[gbase + gen_in_off(g, k0 + m)]);
         }
     } else {
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = mk<T>((T)0, (T)0);
+        for (int m = 0; m < E; ++m) v[m] = make_double2(0.0, 0.0);
     }
 
     // r = 1 / (alpha + lambda_z), c = lambda_z r
     const int wc = active ? w : 0;
-    const int x = wc % g.nx, y = wc / g.nx + g.y0;
-    const C alpha = cadd(a.ax[x], a.ay[y]);
-    const C r = crecip_scaled<T>(mk<T>(alpha.x + a.lz, alpha.y), (T)1);
-    const C c = mk<T>(a.lz * r.x, a.lz * r.y);
+    C r, c;
+    zs_coeffs(a, wc % g.nx, wc / g.nx + g.y0, r, c);
 
     // 1. local recurrence from a zero carry-in, in NB independent blocks of B points so that the dependent chain is
     //    B - 1 + NB - 1 complex FMAs deep instead of E - 1; the blocks' carries t[] are folded into step 3.
@@ -148,56 +174,37 @@ zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, con
     C Pex;                                          // exclusive prefix: the carry from the segments before q in this warp
     Pex.x = __shfl_up_sync(0xffffffffu, P.x, TX);
     Pex.y = __shfl_up_sync(0xffffffffu, P.y, TX);
-    if (q == 0) Pex = mk<T>((T)0, (T)0);
+    if (q == 0) Pex = make_double2(0.0, 0.0);
     if (q == QW - 1) agg[wrp * TX + l] = P;
     __syncthreads();
 
     // 2b. value carried into this warp
-    C Z = mk<T>((T)0, (T)0);
+    C Z = make_double2(0.0, 0.0);
     if constexpr (KIND == ZS_CYCLIC) {
         // cycle closed: Z_{w-1} = sum_{m < NW} D^m A_{w-1-m} / (1 - D^NW)   (Horner over A_w, A_{w+1}, ..., A_{w-1})
-        C acc = mk<T>((T)0, (T)0), Dn = mk<T>((T)1, (T)0);
+        C acc = make_double2(0.0, 0.0), Dn = make_double2(1.0, 0.0);
         int idx = wrp;
         for (int i = 0; i < nwarps; ++i) {
             acc = cadd(cmul(D, acc), agg[idx * TX + l]);
             Dn = cmul(Dn, D);
             idx = (idx + 1 == nwarps) ? 0 : idx + 1;
         }
-        Z = cmul(acc, crecip_scaled<T>(mk<T>((T)1 - Dn.x, -Dn.y), (T)1));
-    } else if constexpr (KIND == ZS_END) {
-        // value at the end of the local line with a zero carry-in: sum_w D^(NW-1-w) A_w; one 128-byte row per tile
-        if (wrp == nwarps - 1 && q == QW - 1) {
-            C acc = mk<T>((T)0, (T)0);
-            for (int i = 0; i < nwarps; ++i) acc = cadd(cmul(D, acc), agg[i * TX + l]);
-            if (active) a.eout[w] = acc;
-        }
-        return;
+        Z = cmul(acc, crecip_scaled<double>(make_double2(1.0 - Dn.x, -Dn.y), 1.0));
     } else {
-        // carry into the local line: the other slabs' end values with the cycle closed over the P ranks,
-        //   Zin = sum_{m < P} cL^m e_{rank-1-m} / (1 - cL^P),  cL = c^(nz / P) = D^NW;
-        // then through the warps before this one: Z = D^wrp Zin + sum_{i < wrp} D^(wrp-1-i) A_i
-        C cL = mk<T>((T)1, (T)0);
-        for (int i = 0; i < nwarps; ++i) cL = cmul(cL, D);
-        C acc = mk<T>((T)0, (T)0), cLp = mk<T>((T)1, (T)0);
-        int idx = a.rank;
-        const long long plane = (long long)g.lines_inner;
-        for (int i = 0; i < a.nranks; ++i) {
-            acc = cadd(cmul(cL, acc), a.ecat[idx * plane + wc]);
-            cLp = cmul(cLp, cL);
-            idx = (idx + 1 == a.nranks) ? 0 : idx + 1;
-        }
-        Z = cmul(acc, crecip_scaled<T>(mk<T>((T)1 - cLp.x, -cLp.y), (T)1));
+        // the carry into the local line closes the cycle over the ranks (zs_carry_owner_kernel); then through the
+        // warps before this one: Z = D^wrp Zin + sum_{i < wrp} D^(wrp-1-i) A_i
+        Z = a.zin[wc];
         for (int i = 0; i < wrp; ++i) Z = cadd(cmul(D, Z), agg[i * TX + l]);
     }
     // carry into this segment: cE^q Z + Pex
-    C cq = mk<T>((T)1, (T)0);
+    C cq = make_double2(1.0, 0.0);
 #pragma unroll
     for (int i = 1; i < QW; ++i)
         if (i <= q) cq = cmul(cq, cE);
     const C carry = cadd(cmul(cq, Z), Pex);
 
     // 3. x_k = r scale (y_k + c^(j+1) H_b),  H_b = carry into block b = t_{b-1} + c^(bB) carry
-    const C rs = mk<T>(r.x * a.scale, r.y * a.scale);
+    const C rs = make_double2(r.x * a.scale, r.y * a.scale);
     C G = carry;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
@@ -209,14 +216,106 @@ zsolve_kernel(const cplx_t<T> *__restrict__ in, cplx_t<T> *__restrict__ out, con
 
     if (active) {
         if (!GEN) {
-            C *p = out + obase + (long long)k0 * g.SIo;
+            CS *p = out + obase + (long long)k0 * g.SIo;
 #pragma unroll
-            for (int m = 0; m < E; ++m) p[m * g.SIo] = v[m];
+            for (int m = 0; m < E; ++m) p[m * g.SIo] = from_d2<CS>(v[m]);
         } else {
 #pragma unroll
-            for (int m = 0; m < E; ++m) *gen_out_ptr<C>(g, obase, k0 + m) = v[m];
+            for (int m = 0; m < E; ++m) *gen_out_ptr<CS>(g, obase, k0 + m) = from_d2<CS>(v[m]);
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// z-slab plans: end values and the carry exchange
+// ---------------------------------------------------------------------------------------------------------------
+// e[line] = c^zc e[line] (if carry_in) + sum_{k < zc} c^(zc-1-k) v[zb + k][line]: the value at the end of planes
+// [zb, zb + zc) of every local line, continuing the planes before zb.  One thread per (kx, ky) line, coalesced over
+// kx; launched per z-chunk right behind the forward y pass of that chunk, so the reads hit L2.
+template <typename T>
+__global__ void __launch_bounds__(256)
+zs_end_accum_kernel(const cplx_t<T> *__restrict__ x, long long lines, int nx, int zb, int zc, int carry_in,
+                    double2 *__restrict__ e, const ZSolveArgs a)
+{
+    const long long line = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (line >= lines) return;
+    double2 r, c;
+    zs_coeffs(a, (int)(line % nx), (int)(line / nx), r, c);
+    double2 acc = carry_in ? e[line] : make_double2(0.0, 0.0);
+    const cplx_t<T> *p = x + (long long)zb * lines + line;
+    int k = 0;
+    for (; k + 8 <= zc; k += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = to_d2(p[(long long)(k + m) * lines]);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const double2 t = acc;
+            acc.x = fma(c.x, t.x, fma(-c.y, t.y, v[m].x));
+            acc.y = fma(c.x, t.y, fma(c.y, t.x, v[m].y));
+        }
+    }
+    for (; k < zc; ++k) {
+        const double2 v = to_d2(p[(long long)k * lines]), t = acc;
+        acc.x = fma(c.x, t.x, fma(-c.y, t.y, v.x));
+        acc.y = fma(c.x, t.y, fma(c.y, t.x, v.y));
+    }
+    e[line] = acc;
+}
+
+// Second sweep for slabs whose plane count fits no tile form of zsolve_kernel (nz / P = 8 planes at 8 ranks of a 64^3
+// grid, odd counts ...): one thread per (kx, ky) line marches over the local planes from the exchanged carry-in,
+//   y_k = c y_{k-1} + b_k,  x_k = r y_k / (nx ny),   in place, 8 planes in flight per thread.
+template <typename T>
+__global__ void __launch_bounds__(256)
+zs_dist_line_kernel(cplx_t<T> *x, long long lines, int nx, int nzl, const ZSolveArgs a)
+{
+    using CS = cplx_t<T>;
+    const long long line = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (line >= lines) return;
+    double2 r, c;
+    zs_coeffs(a, (int)(line % nx), (int)(line / nx), r, c);
+    const double2 rs = make_double2(r.x * a.scale, r.y * a.scale);
+    double2 acc = a.zin[line];
+    CS *p = x + line;
+    int k = 0;
+    for (; k + 8 <= nzl; k += 8) {
+        double2 v[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) v[m] = to_d2(p[(long long)(k + m) * lines]);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+            const double2 t = acc;
+            acc.x = fma(c.x, t.x, fma(-c.y, t.y, v[m].x));
+            acc.y = fma(c.x, t.y, fma(c.y, t.x, v[m].y));
+            v[m] = cmul(acc, rs);
+        }
+#pragma unroll
+        for (int m = 0; m < 8; ++m) p[(long long)(k + m) * lines] = from_d2<CS>(v[m]);
+    }
+    for (; k < nzl; ++k) {
+        const double2 v = to_d2(p[(long long)k * lines]), t = acc;
+        acc.x = fma(c.x, t.x, fma(-c.y, t.y, v.x));
+        acc.y = fma(c.x, t.y, fma(c.y, t.x, v.y));
+        p[(long long)k * lines] = from_d2<CS>(cmul(acc, rs));
+    }
+}
+
+struct ZCarryPeers {
+    double2 *p[CPC_MAX_PEERS];
+};
+
+// Rank `rank` hands the end values of the lines owned by rank q (lines [q lsub, (q+1) lsub)) to q: peer store into
+// q's gather buffer G_q[rank][line - q lsub].
+__global__ void __launch_bounds__(256)
+zs_carry_push_kernel(const double2 *__restrict__ e, long long lines, long long lsub, int rank, ZCarryPeers gpeer);
+
+// Owner of lines [line0, line0 + count): from the P end values of each line, the carry into every rank's first plane
+//   Zin_r = sum_{m < P} cL^m e_{r-1-m} / (1 - cL^P),  cL = c^(nz / P)       (the cycle closed over the ranks),
+// computed for r = 0 by Horner and then Zin_{r+1} = e_r + cL Zin_r; stored into rank r's zin buffer (peer store), or
+// only into this rank's when self_only (fallback without peer mapping: every rank owns all lines).
+__global__ void __launch_bounds__(256)
+zs_carry_owner_kernel(const double2 *__restrict__ gbuf, long long gstride, long long line0, long long count, int nx,
+                      int nzl, int nranks, int rank, int self_only, ZCarryPeers zpeer, const ZSolveArgs a);
 
 }  // namespace cpc

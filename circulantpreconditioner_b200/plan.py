@@ -30,19 +30,36 @@ def slab_range(n, nranks, rank):
     return s.value, c.value
 
 
-def _ptr_and_kind(a, writable=False):
-    """(address, mem_kind, keepalive) of a torch tensor or numpy array."""
+def _ptr_and_kind(a, writable=False, np_dtype=None, count=None, device=None, what="array"):
+    """(address, mem_kind, keepalive) of a torch tensor or numpy array.
+
+    With np_dtype / count / device given, the array's element type, element count and CUDA device are checked against
+    them first: the C ABI takes raw addresses, so a mismatch would be an out-of-bounds access, not an error."""
     if torch is not None and isinstance(a, torch.Tensor):
         if not a.is_contiguous():
-            raise ValueError("tensor must be contiguous")
+            raise ValueError(f"{what}: tensor must be contiguous")
+        if np_dtype is not None and a.dtype != _TORCH_DTYPES[np.dtype(np_dtype).name]:
+            raise ValueError(f"{what}: dtype {a.dtype} does not match the plan's {np.dtype(np_dtype).name}")
+        if count is not None and a.numel() != count:
+            raise ValueError(f"{what}: {a.numel()} elements, the plan expects {count}")
+        if a.is_cuda and device is not None and device >= 0 and a.device.index != device:
+            raise ValueError(f"{what}: tensor lives on cuda:{a.device.index}, the plan on cuda:{device}")
         return a.data_ptr(), (MEM_DEVICE if a.is_cuda else MEM_HOST), a
     if isinstance(a, np.ndarray):
         if not a.flags.c_contiguous:
-            raise ValueError("array must be C-contiguous")
+            raise ValueError(f"{what}: array must be C-contiguous")
         if writable and not a.flags.writeable:
-            raise ValueError("output array is read-only")
+            raise ValueError(f"{what}: output array is read-only")
+        if np_dtype is not None and a.dtype != np.dtype(np_dtype):
+            raise ValueError(f"{what}: dtype {a.dtype} does not match the plan's {np.dtype(np_dtype).name}")
+        if count is not None and a.size != count:
+            raise ValueError(f"{what}: {a.size} elements, the plan expects {count}")
         return a.ctypes.data, MEM_HOST, a
     raise TypeError(f"unsupported array type {type(a)}")
+
+
+_TORCH_DTYPES = ({"complex128": torch.complex128, "complex64": torch.complex64, "float64": torch.float64,
+                  "float32": torch.float32} if torch is not None else {})
 
 
 class CirculantPlan:
@@ -59,6 +76,13 @@ class CirculantPlan:
                           ctypes.cast(self._id_buf, ctypes.c_void_p) if self._id_buf else None,
                           ctypes.c_void_p(stream or 0), int(device))
         check(lib().cpc_plan_create(ctypes.byref(self._h), ctypes.byref(d)))
+        inf = self.info()
+        self.local_elems = int(inf["local_elems"])        # elements of b / x held by this rank
+        self.local_cells = self.local_elems // self.ncomp
+        self.proj_cols = 0
+        self.device = int(device)
+        if self.device < 0 and torch is not None and torch.cuda.is_available():
+            self.device = torch.cuda.current_device()
 
     # -- life cycle ----------------------------------------------------------------------------
     def destroy(self):
@@ -97,12 +121,20 @@ class CirculantPlan:
         check(lib().cpc_set_symbol_separable(self._h, p[0], p[1], p[2], lambda_x, lambda_y, lambda_z))
 
     def set_symbol_diag(self, diag):
-        ptr, kind, keep = _ptr_and_kind(diag)
+        """Explicit eigenvalues: this rank's z-slab of Diag, complex128 whatever the plan dtype."""
+        ptr, kind, keep = _ptr_and_kind(diag, np_dtype=np.complex128, count=self.local_cells, device=self.device,
+                                        what="diag")
         check(lib().cpc_set_symbol_diag(self._h, ctypes.c_void_p(ptr), kind))
 
     def set_symbol_first_column(self, col):
-        ptr, kind, keep = _ptr_and_kind(col)
+        ptr, kind, keep = _ptr_and_kind(col, np_dtype=self.np_dtype, count=self.local_elems, device=self.device,
+                                        what="column")
         check(lib().cpc_set_symbol_first_column(self._h, ctypes.c_void_p(ptr), kind))
+
+    def set_option(self, name, value):
+        """Schedule switches (include/circulantpc.h, enum cpc_option): 'z_recurrence', 'l2_chunk_bytes',
+        'chain_streams'."""
+        check(lib().cpc_set_option(self._h, _lib.OPTIONS[name], int(value)))
 
     def set_symbol_wave(self, c0, mu_x, mu_y, mu_z):
         check(lib().cpc_set_symbol_wave(self._h, c0, mu_x, mu_y, mu_z))
@@ -113,9 +145,11 @@ class CirculantPlan:
         return out
 
     # -- hot path -----------------------------------------------------------------------------------
-    def _call(self, fn, src, dst):
-        ps, ks, _k1 = _ptr_and_kind(src)
-        pd, kd, _k2 = _ptr_and_kind(dst, writable=True)
+    def _call(self, fn, src, dst, count=None):
+        count = self.local_elems if count is None else count
+        ps, ks, _k1 = _ptr_and_kind(src, np_dtype=self.np_dtype, count=count, device=self.device, what="input")
+        pd, kd, _k2 = _ptr_and_kind(dst, writable=True, np_dtype=self.np_dtype, count=count, device=self.device,
+                                    what="output")
         if ks != kd:
             raise ValueError("input and output must live in the same memory kind")
         check(fn(self._h, ctypes.c_void_p(ps), ctypes.c_void_p(pd), ks))
@@ -147,17 +181,19 @@ class CirculantPlan:
         check(lib().cpc_set_projection(self._h, int(cols), rp.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
                                        ci.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                                        v.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+        self.proj_cols = int(cols)
 
     def apply_projected(self, b, x=None):
         """x = P^T solve_3D(P b)  (reference applyFFT3DPrecTransport, PCSHELLFft_3D.cxx:10-24, plus back-projection)."""
         if x is None:
             x = torch.empty_like(b) if (torch is not None and isinstance(b, torch.Tensor)) else np.empty_like(b)
-        return self._call(lib().cpc_apply_projected, b, x)
+        return self._call(lib().cpc_apply_projected, b, x, count=self.proj_cols)
 
     def apply_profiled(self, b, x):
         """Device-pointer apply that also returns the per-pass durations in ms (CUDA events on the plan stream)."""
-        pb, kb, _ = _ptr_and_kind(b)
-        px, kx, _ = _ptr_and_kind(x, writable=True)
+        pb, kb, _ = _ptr_and_kind(b, np_dtype=self.np_dtype, count=self.local_elems, device=self.device, what="input")
+        px, kx, _ = _ptr_and_kind(x, writable=True, np_dtype=self.np_dtype, count=self.local_elems, device=self.device,
+                                  what="output")
         if kb != MEM_DEVICE or kx != MEM_DEVICE:
             raise ValueError("apply_profiled needs CUDA tensors")
         ms = (ctypes.c_float * _lib.CPC_MAX_PASSES)()

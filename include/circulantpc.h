@@ -91,8 +91,11 @@ int cpc_sync(cpc_plan plan);
  * cpc_set_symbol_separable   <- build_diag_mat_vec_3D with caller-supplied c_x_hat, c_y_hat, c_z_hat
  *                               (FftLinearSolver_3D.c:136-164); tables are HOST complex128 arrays of nx, ny, nz
  * cpc_set_symbol_diag        <- the Diag argument of solve_3D (FftLinearSolver_3D.c:166,174): N eigenvalues,
- *                               complex128 (always, whatever the plan dtype), host or device, local slab for
- *                               multi-rank plans is NOT supported (single rank only)
+ *                               complex128 (always, whatever the plan dtype), host or device; multi-rank plans
+ *                               pass the rank's z-slab (collective).  The table is tested on the GPU for the
+ *                               separable structure a[i] + b[j] + c[k] that build_diag_mat_vec_3D produces; if it
+ *                               has it, three 1-D tables are kept (and the recurrence middle pass applies),
+ *                               otherwise the N reciprocals are held in HBM
  * cpc_set_symbol_first_column<- general circulant: Lambda = FFT3(first column), the 1-D form of which is
  *                               tests/FFTDirectSolver/testFftSolver_1D.c:144-177; column in the plan dtype
  * cpc_set_symbol_wave        <- (absent in the reference) arrow-matrix symbol derived from
@@ -103,6 +106,19 @@ int cpc_set_symbol_separable(cpc_plan plan, const double *cx_hat, const double *
 int cpc_set_symbol_diag(cpc_plan plan, const void *diag_c128, int mem_kind);
 int cpc_set_symbol_first_column(cpc_plan plan, const void *column, int mem_kind);
 int cpc_set_symbol_wave(cpc_plan plan, double c0, double mu_x, double mu_y, double mu_z);
+/* ---- options ------------------------------------------------------------------------------------
+ * Schedule switches of a plan (no counterpart in the reference, whose FFTW plan is FFTW_ESTIMATE with no knobs).
+ * Defaults are what the benchmarks run; the switches exist for comparison runs and tests. */
+enum cpc_option {
+    CPC_OPT_Z_RECURRENCE = 1,   /* 1 (default): a transport symbol's middle pass is the cyclic recurrence along z;
+                                   0: keep the fused forward-FFT / division / backward-FFT form for every symbol */
+    CPC_OPT_L2_CHUNK_BYTES = 2, /* bytes of x per z-chunk of the L2-chained x / y passes (default 32 MiB: Fx and Fy,
+                                   By and Bx run back to back on each chunk so the second pass reads it from L2);
+                                   0 = whole-array passes; < 0 = default */
+    CPC_OPT_CHAIN_STREAMS = 3   /* 1 (default) or 2: alternate the chunks' chains between two streams */
+};
+int cpc_set_option(cpc_plan plan, int option, long long value);
+
 /* Writes the N eigenvalues currently in force (complex128) -- what the reference keeps in ctx->Diag. */
 int cpc_get_diag(cpc_plan plan, void *diag_c128, int mem_kind);
 
@@ -116,7 +132,8 @@ int cpc_get_diag(cpc_plan plan, void *diag_c128, int mem_kind);
  *                the z factor of F^H diag(1/Lambda) F is evaluated as the equivalent cyclic first-order recurrence
  *                (alpha + lz) x_k - lz x_{k-1} = b_k instead of two z FFTs and a division: the same operator, equal
  *                to rounding (<= 1e-13 relative); multi-rank plans then exchange one carry per (kx, ky) line instead of
- *                transposing.  Environment CPC_ZSOLVE=0 keeps the FFT form (cpc_plan_info.fast_path[2], dist_mode).
+ *                transposing.  cpc_set_option(CPC_OPT_Z_RECURRENCE, 0) keeps the FFT form
+ *                (cpc_plan_info.fast_path[2], dist_mode).
  * cpc_forward <- MatMult(FFT_MAT, in, out)          (unnormalised, exp(-2 pi i ..), :170)
  * cpc_inverse <- MatMultTranspose(FFT_MAT, in, out) (unnormalised, exp(+2 pi i ..), :180)
  * For multi-rank plans b/x/in are the rank's z-slab [cpc_slab_range over nz]; out of cpc_forward and in of
@@ -148,7 +165,7 @@ typedef struct {
     int dist_mode;                 /* 0 single rank, 1 NCCL all-to-all transposes, 2 transposes fused into the passes
                                       (stores pushed to IPC-mapped peer buffers over NVLink), 3 no transposes: the
                                       current (transport) symbol's middle pass is a recurrence along z, the z-slabs
-                                      only all-gather one carry per (kx, ky) line */
+                                      only exchange one carry per (kx, ky) line */
     int fast_path[3];              /* 1 if axis x/y/z runs the templated Stockham kernel, 0 = generic kernel;
                                       [2] == 2: the middle pass of the current (transport) symbol is solved as a cyclic
                                       first-order recurrence along z instead of forward FFT, division, backward FFT */

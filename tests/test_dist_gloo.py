@@ -89,7 +89,10 @@ def test_slab_schedule_world_size_2(shape, P):
 
 # ---------------------------------------------------------------------------------------------------------------
 # The transpose-free schedule for the transport symbol (csrc/zsolve.cuh, PlanT::apply_device_zslab): Fx, Fy on the
-# local z-slab, the z recurrence in two local sweeps with an all-gather of every slab's end values in between.
+# local z-slab with the slab's end values accumulated z-chunk by z-chunk (zs_end_accum_kernel), the carry exchange
+# through line owners (zs_carry_push_kernel / zs_carry_owner_kernel: rank q owns lines [q lsub, (q+1) lsub), gathers
+# their P end values, closes the cycle over the ranks and hands every rank its carry-in), the second sweep from that
+# carry-in (ZS_DIST / zs_dist_line_kernel), By, Bx.
 # ---------------------------------------------------------------------------------------------------------------
 def _worker_zslab(rank, P, port, shape, lam, b_full, ret):
     import circulantpreconditioner_b200 as cpc
@@ -99,35 +102,47 @@ def _worker_zslab(rank, P, port, shape, lam, b_full, ret):
     z0, nzl = cpc.slab_range(nz, P, rank)
     lx, ly, lz = lam
     slab = b_full.reshape(nz, ny, nx)[z0:z0 + nzl].copy()
-    slab = np.fft.fft(np.fft.fft(slab, axis=2), axis=1)                      # Fx, Fy on the z-slab
     cx = 1.0 - np.exp(-2j * np.pi * np.arange(nx) / nx) if nx > 1 else np.zeros(1)
     cy = 1.0 - np.exp(-2j * np.pi * np.arange(ny) / ny) if ny > 1 else np.zeros(1)
-    alpha = 1.0 + lx * cx[None, :] + ly * cy[:, None]                         # [ny][nx]
+    alpha = (1.0 + lx * cx[None, :] + ly * cy[:, None]).ravel()               # [ny nx] lines
     r = 1.0 / (alpha + lz)
     c = lz * r
-    # sweep 1: value at the end of the local lines from a zero carry-in
-    y0 = np.empty_like(slab)
-    acc = np.zeros((ny, nx), dtype=np.complex128)
+    L = nx * ny
+    # [Fx, Fy, end-value accumulation] z-chunk by z-chunk: e = c^len e + (end value of the chunk from a zero carry)
+    chunk = 3
+    e = np.zeros(L, dtype=np.complex128)
+    for zb in range(0, nzl, chunk):
+        ze = min(nzl, zb + chunk)
+        slab[zb:ze] = np.fft.fft(np.fft.fft(slab[zb:ze], axis=2), axis=1)
+        for k in range(zb, ze):
+            e = c * e + slab[k].ravel()
+    # push: the end values of the lines owned by q go to q (all_gather stands in for the peer stores)
+    lsub = (L + P - 1) // P
+    allv = [torch.empty(L, dtype=torch.complex128) for _ in range(P)]
+    dist.all_gather(allv, torch.from_numpy(e.copy()))
+    lo, hi = min(L, rank * lsub), min(L, (rank + 1) * lsub)
+    G = np.stack([v.numpy()[lo:hi] for v in allv])                            # gbuf[P][lsub] of this owner
+    # owner: Zin_0 by Horner over e_0 .. e_{P-1}, closed cyclically, then Zin_{q+1} = e_q + cL Zin_q
+    cL = c[lo:hi] ** nzl
+    acc = np.zeros(hi - lo, dtype=np.complex128)
+    for s_ in range(P):
+        acc = cL * acc + G[s_]
+    Z = acc / (1.0 - cL ** P)
+    zin_owned = np.zeros((P, lsub), dtype=np.complex128)                     # what this owner pushes to every rank
+    for q in range(P):
+        zin_owned[q, :hi - lo] = Z
+        Z = G[q] + cL * Z
+    # push back: rank q receives its row from every owner
+    back = [torch.empty(P, lsub, dtype=torch.complex128) for _ in range(P)]
+    dist.all_gather(back, torch.from_numpy(zin_owned))
+    zin = np.concatenate([bk.numpy()[rank] for bk in back])[:L]
+    # second sweep from the carry-in (thread-per-line form): y_k = c y_{k-1} + b_k, x_k = r y_k
+    acc = zin.copy()
+    out = np.empty_like(slab)
     for k in range(nzl):
-        acc = c * acc + slab[k]
-        y0[k] = acc
-    ends = [torch.empty(ny, nx, dtype=torch.complex128) for _ in range(P)]
-    dist.all_gather(ends, torch.from_numpy(acc.copy()))                       # ncclAllGather on the GPU
-    ends = [e.numpy() for e in ends]
-    # carry into this slab: the other slabs' end values, cycle closed over the ranks (Horner, as in the kernel)
-    cL = c ** nzl
-    z = np.zeros((ny, nx), dtype=np.complex128)
-    idx = rank
-    for _ in range(P):
-        z = cL * z + ends[idx]
-        idx = (idx + 1) % P
-    z = z / (1.0 - cL ** P)
-    # sweep 2: fold the carry in; the z solve is exact, so only Bx By remain to be normalised
-    cp = c.copy()
-    for k in range(nzl):
-        y0[k] = (y0[k] + cp * z) * r
-        cp = cp * c
-    slab2 = np.fft.ifft(np.fft.ifft(y0, axis=1), axis=2)
+        acc = c * acc + slab[k].ravel()
+        out[k] = (acc * r).reshape(ny, nx)
+    slab2 = np.fft.ifft(np.fft.ifft(out, axis=1), axis=2)
     parts = [None] * P
     dist.all_gather_object(parts, (z0, slab2))
     if rank == 0:
@@ -135,7 +150,7 @@ def _worker_zslab(rank, P, port, shape, lam, b_full, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("shape,P", [((8, 6, 8), 2), ((5, 3, 12), 2), ((4, 4, 12), 3)])   # only nz % P == 0 is needed
+@pytest.mark.parametrize("shape,P", [((8, 6, 8), 2), ((5, 3, 12), 2), ((4, 4, 12), 3), ((5, 3, 8), 4)])   # only nz % P == 0 is needed
 def test_zslab_recurrence_schedule(shape, P):
     from oracle import circulant_oracle as O
     nx, ny, nz = shape

@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, P, port, shape, lam, b_full, want, ncomp, wave, errs):
+def _worker(rank, P, port, shape, lam, b_full, want, ncomp, wave, opts, errs):
     import circulantpreconditioner_b200 as cpc
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     torch.cuda.set_device(rank)
@@ -26,26 +26,40 @@ def _worker(rank, P, port, shape, lam, b_full, want, ncomp, wave, errs):
     plane = nx * ny * ncomp
     loc = torch.from_numpy(b_full[z0 * plane:(z0 + nzl) * plane].copy()).cuda()
     with cpc.CirculantPlan(nx, ny, nz, ncomp=ncomp, nranks=P, rank=rank, nccl_id=idt.cpu().numpy().tobytes()) as p:
+        for k, v in opts.items():
+            if k not in ("diag", "diag_perturb", "expect_dist_mode", "skip_transforms"):
+                p.set_option(k, v)
         if wave:
             p.set_symbol_wave(*lam)
+        elif opts.get("diag"):
+            # the reference's own set-up product: this rank's z-slab of Diag (solve_3D's argument)
+            from oracle import circulant_oracle as O
+            Diag = O.transport_diag(nx, ny, nz, *lam)
+            if opts.get("diag_perturb"):
+                Diag[5] += 0.25                 # no longer a[i] + b[j] + c[k]: must be held as a full table
+            p.set_symbol_diag(torch.from_numpy(Diag[z0 * plane:(z0 + nzl) * plane].copy()).cuda())
         else:
             p.set_symbol_transport(*lam)
+        if "expect_dist_mode" in opts:
+            assert p.info()["dist_mode"] == opts["expect_dist_mode"], p.info()
         out = torch.empty_like(loc)
         p.apply(loc, out)
         e1 = np.linalg.norm(out.cpu().numpy() - want[z0 * plane:(z0 + nzl) * plane]) / np.linalg.norm(want)
         p.apply(loc, loc)                      # in place
         e2 = np.linalg.norm(loc.cpu().numpy() - want[z0 * plane:(z0 + nzl) * plane]) / np.linalg.norm(want)
         # forward then inverse returns N * input
-        src = torch.from_numpy(b_full[z0 * plane:(z0 + nzl) * plane].copy()).cuda()
-        f = p.forward(src)
-        bk = p.inverse(f)
-        e3 = (torch.linalg.vector_norm(bk / (nx * ny * nz) - src) / torch.linalg.vector_norm(src)).item()
+        e3 = 0.0
+        if not opts.get("skip_transforms"):
+            src = torch.from_numpy(b_full[z0 * plane:(z0 + nzl) * plane].copy()).cuda()
+            f = p.forward(src)
+            bk = p.inverse(f)
+            e3 = (torch.linalg.vector_norm(bk / (nx * ny * nz) - src) / torch.linalg.vector_norm(src)).item()
     errs[rank] = (float(e1), float(e2), float(e3))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def _run(shape, lam, ncomp=1, wave=False, P=2):
+def _run(shape, lam, ncomp=1, wave=False, P=2, opts=None):
     from oracle import circulant_oracle as O
     if torch.cuda.device_count() < P:
         pytest.skip(f"needs {P} GPUs")
@@ -53,11 +67,18 @@ def _run(shape, lam, ncomp=1, wave=False, P=2):
     rng = np.random.default_rng(5)
     n = nx * ny * nz * ncomp
     b = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex128)
-    want = O.solve_wave_block(b, nx, ny, nz, *lam) if wave else O.FftTransportSolver(nx, ny, nz, *lam, b)
+    if wave:
+        want = O.solve_wave_block(b, nx, ny, nz, *lam)
+    elif opts and opts.get("diag_perturb"):
+        Diag = O.transport_diag(nx, ny, nz, *lam)
+        Diag[5] += 0.25
+        want = O.solve_3D(Diag, b, nx, ny, nz)
+    else:
+        want = O.FftTransportSolver(nx, ny, nz, *lam, b)
     mgr = mp.Manager()
     errs = mgr.dict()
     port = 29600 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(P, port, shape, lam, b, want, ncomp, wave, errs), nprocs=P, join=True)
+    mp.spawn(_worker, args=(P, port, shape, lam, b, want, ncomp, wave, dict(opts or {}), errs), nprocs=P, join=True)
     return dict(errs)
 
 
@@ -69,12 +90,11 @@ def test_two_rank_transport(shape):
 
 
 @pytest.mark.parametrize("shape", [(64, 64, 64), (32, 16, 256)])
-def test_two_rank_transport_transposing_schedule(shape, monkeypatch):
-    """CPC_ZSOLVE=0 (inherited by the spawned ranks): the FFT form of the middle pass and the transposing schedule that
-    every non-transport symbol uses; test_two_rank_transport runs the same shapes through the transpose-free z-slab
-    recurrence (csrc/zsolve.cuh).  Both must match the oracle."""
-    monkeypatch.setenv("CPC_ZSOLVE", "0")
-    errs = _run(shape, (55.5556, 0.3, 2.5))
+def test_two_rank_transport_transposing_schedule(shape):
+    """z_recurrence = 0: the FFT form of the middle pass and the transposing schedule that every non-transport symbol
+    uses; test_two_rank_transport runs the same shapes through the transpose-free z-slab recurrence
+    (csrc/zsolve.cuh).  Both must match the oracle."""
+    errs = _run(shape, (55.5556, 0.3, 2.5), opts={"z_recurrence": 0, "expect_dist_mode": 2})
     for r, (e1, e2, e3) in errs.items():
         assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
 
@@ -128,3 +148,57 @@ def test_four_rank_transport():
     errs = _run((64, 64, 64), (1.0, 2.0, 3.0), P=4)
     for r, (e1, e2, e3) in errs.items():
         assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
+
+
+# ---- 8 ranks (one 8 x B200 node: `gpurun --gpus 8 -- python -m pytest tests/test_dist_gpu.py -m gpu -k eight`) ----
+@pytest.mark.parametrize("shape", [(64, 64, 64), (128, 64, 512), (40, 24, 128)])
+def test_eight_rank_transport(shape):
+    """The transpose-free z-slab schedule at 8 ranks (64 / 16 planes per rank; the (40, 24, 128) grid has generic x / y
+    lengths): every rank's slab against the single-process oracle."""
+    errs = _run(shape, (55.5556, 55.5556, 55.5556), P=8, opts={"expect_dist_mode": 3})
+    assert len(errs) == 8
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
+
+
+def test_eight_rank_transport_transposing_schedule():
+    errs = _run((64, 64, 64), (55.5556, 0.3, 2.5), P=8, opts={"z_recurrence": 0, "expect_dist_mode": 2})
+    assert len(errs) == 8
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
+
+
+def test_eight_rank_wave_block():
+    errs = _run((32, 32, 32), (700.0, 0.0793651, 0.0793651, 0.0793651), ncomp=4, wave=True, P=8)
+    assert len(errs) == 8
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
+
+
+# ---- explicit Diag on z-slabs (the Diag Vec of solve_3D, src/FftLinearSolver_3D.c:166, distributed like b and X) ----
+@pytest.mark.parametrize("P", [2, 4])
+def test_multi_rank_explicit_diag_is_recognised_as_separable(P):
+    errs = _run((32, 16, 64), (2.0, 0.5, 3.0), P=P, opts={"diag": 1, "expect_dist_mode": 3})
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
+
+
+def test_two_rank_explicit_diag_without_recurrence():
+    """A Diag whose lambda_z is negative is still separable but not recurrence-capable: transposing schedule."""
+    errs = _run((32, 16, 64), (2.0, 0.5, -0.2), P=2, opts={"diag": 1, "expect_dist_mode": 2})
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-11 and e2 < 1e-11 and e3 < 1e-12, (r, e1, e2, e3)
+
+
+def test_two_rank_explicit_diag_full_table():
+    """A Diag that is not separable goes to HBM as N reciprocals, transposed to the layout the fused z pass runs in."""
+    errs = _run((32, 16, 64), (2.0, 0.5, 3.0), P=2, opts={"diag": 1, "diag_perturb": 1, "expect_dist_mode": 2})
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-12 and e2 < 1e-12 and e3 < 1e-12, (r, e1, e2, e3)
+
+
+def test_two_rank_ny_not_divisible_takes_the_zslab_schedule():
+    """ny = 15 cannot be split over 2 ranks for a transpose; the transport symbol needs none."""
+    errs = _run((32, 15, 64), (55.5556, 0.3, 2.5), P=2, opts={"expect_dist_mode": 3, "skip_transforms": 1})
+    for r, (e1, e2, e3) in errs.items():
+        assert e1 < 1e-12 and e2 < 1e-12, (r, e1, e2, e3)

@@ -154,7 +154,7 @@ def test_apply_transport_matches_oracle(shape):
 # forward-FFT / divide / backward-FFT form of the reference (solve_3D, src/FftLinearSolver_3D.c:170-184)
 @pytest.mark.parametrize("shape", [(64, 32, 512), (24, 16, 384), (8, 8, 96), (8, 8, 100), (4, 4, 1000), (16, 16, 16),
                                    (40, 3, 1024), (8, 5, 200), (12, 7, 64)])
-def test_middle_pass_recurrence_matches_fft_form(shape, monkeypatch):
+def test_middle_pass_recurrence_matches_fft_form(shape):
     nx, ny, nz = shape
     rng = np.random.default_rng(nx + 3 * ny + 7 * nz)
     lam = (55.5556, 55.5556, 55.5556)
@@ -164,8 +164,8 @@ def test_middle_pass_recurrence_matches_fft_form(shape, monkeypatch):
         p.set_symbol_transport(*lam)
         assert p.info()["fast_path"][2] == 2
         rec = host(p.apply(dev(b)))
-    monkeypatch.setenv("CPC_ZSOLVE", "0")
     with cpc.CirculantPlan(nx, ny, nz) as p:
+        p.set_option("z_recurrence", 0)
         p.set_symbol_transport(*lam)
         assert p.info()["fast_path"][2] != 2
         fft = host(p.apply(dev(b)))
