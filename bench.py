@@ -61,7 +61,7 @@ def workload_config(n_gpus):
         "workload": f"scalar circulant PC apply, {N_GRID}^3 complex128, lambda=({LAMBDA[0]},)*3 "
                     "(BASELINE.json config 4 at the size the metric is quoted on)",
         "grid": [N_GRID, N_GRID, N_GRID],
-        "decomposition": "single GPU, 5 passes (x/y pairs L2-chained per z-chunk)" if n_gpus == 1
+        "decomposition": "single GPU, 5 HBM passes" if n_gpus == 1
                          else f"z-slabs over {n_gpus} ranks, one process per GPU",
         "l2_policy": "inputs larger than L2 (2.1 GB array vs 126 MB L2); no explicit flush",
     }
@@ -91,7 +91,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -103,10 +103,20 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append((time.time(), line.strip()))
 
+    def wait_ready(self, timeout=3.0):
+        """nvidia-smi needs a moment to start: do not open a (65 ms) timed region before the first sample exists."""
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.samples and time.time() < t_end:
+            time.sleep(0.02)
+
     def window(self, t0, t1):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        rows = [s for (t, s) in self.samples if t0 <= t <= t1 + 0.05] or [s for (_, s) in self.samples]
+        time.sleep(0.05)              # let the sample that covers the end of the window arrive
+        rows = [s for (t, s) in self.samples if t0 <= t <= t1 + 0.05]
+        if not rows and self.samples:  # window shorter than the sampling period: the sample nearest to it
+            mid = 0.5 * (t0 + t1)
+            rows = [min(self.samples, key=lambda ts: abs(ts[0] - mid))[1]]
         sm, mx, reasons, pw = [], [], set(), []
         for r in rows:
             f = [x.strip() for x in r.split(",")]
@@ -283,6 +293,8 @@ def run_gpu(args):
         sampler.start()
     for _ in range(args.warmup):
         plan.apply(b, x)
+    if sampler:
+        sampler.wait_ready()
     l0 = plan.info()["kernel_launches"]
     ms_step, t0, t1 = timed_loop(plan, args.steps, x)
     launches = plan.info()["kernel_launches"] - l0
@@ -398,9 +410,7 @@ def run_gpu(args):
                                 "GB/s": (bytes_pass / m / 1e6) if nm not in not_kernel and "exchange" not in nm and m > 0 else None}
                                for nm, m in zip(names, pass_ms)],
                     "apply": {"alg_bytes": apply_alg, "achieved": apply_alg / ms_step / 1e6,
-                              "frac": apply_alg / ms_step / 1e6 / peak},
-                    "note": "Fx+Fy and By+Bx run z-chunk by z-chunk so the second pass of a pair reads the chunk from "
-                            "L2: per-pass GB/s are algorithmic bytes / time and can exceed the HBM peak"}
+                              "frac": apply_alg / ms_step / 1e6 / peak}}
         if world > 1 and dist_mode == 3:
             ci = names.index("z end values + carry exchange") if "z end values + carry exchange" in names else None
             roofline["carry_exchange"] = {

@@ -48,6 +48,7 @@ ABI = {
     "cpc_set_symbol_wave": (_i, [_vp, _d, _d, _d, _d]),
     "cpc_set_option": (_i, [_vp, _i, ctypes.c_longlong]),
     "cpc_get_diag": (_i, [_vp, _vp, _i]),
+    "cpc_build_diag_separable": (_i, [_i, _i, _i, _dp, _dp, _dp, _d, _d, _d, _i, _i, _vp, _i]),
     "cpc_apply": (_i, [_vp, _vp, _vp, _i]),
     "cpc_forward": (_i, [_vp, _vp, _vp, _i]),
     "cpc_inverse": (_i, [_vp, _vp, _vp, _i]),

@@ -171,6 +171,18 @@ int cpc_get_diag(cpc_plan plan, void *diag, int mem_kind)
     return plan->impl->get_diag(diag, mem_kind);
 }
 
+int cpc_build_diag_separable(int nx, int ny, int nz, const double *cx, const double *cy, const double *cz, double lx, double ly,
+                             double lz, int z0, int nzl, void *diag, int mem_kind)
+{
+    if (nx < 1 || ny < 1 || nz < 1 || !cx || !cy || !cz || !diag || z0 < 0 || nzl < 0 || z0 + nzl > nz) {
+        set_error("cpc_build_diag_separable: bad argument");
+        return CPC_ERR_ARG;
+    }
+    if (mem_kind != CPC_MEM_DEVICE && mem_kind != CPC_MEM_HOST) { set_error("bad mem_kind %d", mem_kind); return CPC_ERR_ARG; }
+    if (cpc_device_count() <= 0) { set_error("cpc_build_diag_separable: no CUDA device (this library has no CPU fallback)"); return CPC_ERR_CUDA; }
+    return build_diag_separable(nx, ny, nz, cx, cy, cz, lx, ly, lz, z0, nzl, diag, mem_kind);
+}
+
 // device arrays are accessed with 16-byte vector loads / stores (complex128; two complex64, two float64, four float32)
 static int check_alignment(const void *a, const void *b, int mem_kind, const char *who)
 {

@@ -49,6 +49,8 @@ struct PlanBase {
     virtual int apply_projected(const void *b, void *x, int mem_kind) = 0;
 };
 
+int build_diag_separable(int nx, int ny, int nz, const double *cx, const double *cy, const double *cz, double lx, double ly,
+                         double lz, int z0, int nzl, void *diag, int mem_kind);
 PlanBase *make_plan_f64();
 PlanBase *make_plan_f32();
 

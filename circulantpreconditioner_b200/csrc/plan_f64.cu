@@ -1,6 +1,8 @@
 // plan_f64.cu -- complex128 instantiation of the plan and its kernels (PetscScalar of a complex PETSc build).
 #include "plan_impl.cuh"
 
+#include <vector>
+
 namespace cpc {
 
 __global__ void diag_from_separable_kernel(double2 *__restrict__ diag, const double2 *__restrict__ ax,
@@ -84,6 +86,38 @@ zs_carry_owner_kernel(const double2 *__restrict__ gbuf, long long gstride, long 
                 Z = cadd(e[q], cmul(cL, Z));                        // Zin_{q+1} = e_q + cL Zin_q
             }
     }
+}
+
+int build_diag_separable(int nx, int ny, int nz, const double *cx, const double *cy, const double *cz, double lx, double ly,
+                         double lz, int z0, int nzl, void *diag, int mem_kind)
+{
+    const int n[3] = { nx, ny, nz };
+    const double *c[3] = { cx, cy, cz };
+    const double lam[3] = { lx, ly, lz };
+    const long long cells = (long long)nx * ny * nzl;
+    double2 *tab = nullptr, *out = (double2 *)diag, *tmp = nullptr;
+    std::vector<double2> h((size_t)nx + ny + nz);
+    size_t o = 0;
+    for (int a = 0; a < 3; ++a)
+        for (int m = 0; m < n[a]; ++m, ++o)     // the "+1" (VecShift, :155) rides on y, as in the plan's tables
+            h[o] = make_double2(lam[a] * c[a][2 * m] + (a == 1 ? 1.0 : 0.0), lam[a] * c[a][2 * m + 1]);
+    CPC_CUDA(cudaMalloc(&tab, sizeof(double2) * h.size()));
+    int rc = CPC_OK;
+    auto fail = [&](cudaError_t e, const char *what) { if (e != cudaSuccess && rc == CPC_OK) rc = cuda_fail(e, what); };
+    fail(cudaMemcpy(tab, h.data(), sizeof(double2) * h.size(), cudaMemcpyHostToDevice), "cudaMemcpy(tables)");
+    if (rc == CPC_OK && mem_kind == CPC_MEM_HOST) {
+        fail(cudaMalloc(&tmp, sizeof(double2) * (size_t)(cells > 0 ? cells : 1)), "cudaMalloc(diag)");
+        out = tmp;
+    }
+    if (rc == CPC_OK && cells > 0) {
+        diag_from_separable_kernel<<<1184, 256>>>(out, tab, tab + nx, tab + nx + ny + z0, nx, ny, cells);
+        fail(cudaGetLastError(), "diag_from_separable_kernel");
+        if (tmp) fail(cudaMemcpy(diag, tmp, sizeof(double2) * (size_t)cells, cudaMemcpyDeviceToHost), "cudaMemcpy(diag)");
+        fail(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+    }
+    if (tmp) cudaFree(tmp);
+    cudaFree(tab);
+    return rc;
 }
 
 PlanBase *make_plan_f64() { return new PlanT<double>(); }

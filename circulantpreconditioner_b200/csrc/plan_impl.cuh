@@ -175,9 +175,11 @@ template <typename T> struct PlanT : PlanBase {
     C *work = nullptr;            // half spectrum (real plans) or the promoted complex copy
     int num_sms = 148;
     int pf_waves = 0;             // L2 prefetch distance in units of (SM count) CTAs; 0 = off
-    // L2-chained schedule: the x and y passes run z-chunk by z-chunk (Fx then Fy on the same planes, By then Bx), so
-    // that the second pass of a pair finds its input in the 126 MB L2 and the intermediate array never goes to HBM.
-    long long l2_chunk_bytes = 32ll << 20;    // bytes of x per z-chunk; 0 = whole-array passes
+    // L2-chained schedule (off by default): the x and y passes run z-chunk by z-chunk (Fx then Fy on the same planes,
+    // By then Bx), so that the second pass of a pair finds its input in the 126 MB L2.  Measured at 512^3
+    // (profiles/r02_notes.md): with separate launches per chunk the kernel boundaries cost as much as the L2 hits
+    // save -- 3.28 ms at best (28 MiB chunks on two streams) against 3.27 ms for whole-array passes.
+    long long l2_chunk_bytes = 0;             // bytes of x per z-chunk; 0 = whole-array passes
     int chain_streams = 1;        // 2: alternate the chunks' chains between the plan stream and a side stream
     cudaStream_t side_stream = nullptr;
     cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
@@ -1085,7 +1087,7 @@ template <typename T> struct PlanT : PlanBase {
     {
         switch (option) {
         case CPC_OPT_Z_RECURRENCE: zrec_off = (value == 0); return CPC_OK;
-        case CPC_OPT_L2_CHUNK_BYTES: l2_chunk_bytes = value < 0 ? (32ll << 20) : value; return CPC_OK;
+        case CPC_OPT_L2_CHUNK_BYTES: l2_chunk_bytes = value < 0 ? 0 : value; return CPC_OK;
         case CPC_OPT_CHAIN_STREAMS: chain_streams = value >= 2 ? 2 : 1; return CPC_OK;
         default: set_error("cpc_set_option: unknown option %d", option); return CPC_ERR_ARG;
         }

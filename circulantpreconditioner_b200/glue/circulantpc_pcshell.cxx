@@ -1,9 +1,20 @@
 // circulantpc_pcshell.cxx -- the PCShell adapter of the reference (src/PCSHELLFft_3D.cxx) over libcirculantpc.
+// Public PETSc API only (see circulantpc_petsc.cxx).
 #include <cmath>
 #include <cstdlib>
-#include <vector>
 
 #include "circulantpc_petsc.h"
+
+// MatCreateFFT(comm, ndim, dims, MATFFTW, &A) of the reference (PCSHELLFft_3D.cxx:34-35): with a real PETSc the FFT Mat
+// is this library's MATSHELL (no FFTW involved); the shim's MatCreateFFT does the same thing under the reference's name.
+static PetscErrorCode create_fft_mat(MPI_Comm comm, PetscInt ndim, const PetscInt dims[], Mat *A)
+{
+#ifdef CPC_WITH_PETSC
+    return MatCreateFFT_CPC(comm, ndim, dims, A);
+#else
+    return MatCreateFFT(comm, ndim, dims, MATFFTW, A);
+#endif
+}
 
 // reference PCSHELLFft_3D.cxx:10-24: project b onto the Cartesian grid (when a projection exists), then solve_3D.
 PetscErrorCode applyFFT3DPrecTransport(PC pc, Vec b, Vec x)
@@ -11,31 +22,12 @@ PetscErrorCode applyFFT3DPrecTransport(PC pc, Vec b, Vec x)
     PetscFunctionBeginUser;
     FFTPrecTransportContext *ctx = nullptr;
     PetscCall(PCShellGetContext(pc, &ctx));
-    PetscCheck(ctx && ctx->FFT_MAT, PETSC_COMM_WORLD, PETSC_ERR_ORDER, "applyFFT3DPrecTransport: PC not set up");
+    PetscCheck(ctx && ctx->FFT_MAT, PETSC_COMM_SELF, PETSC_ERR_ORDER, "applyFFT3DPrecTransport: PC not set up");
     const PetscInt N = ctx->n_x * ctx->n_y * ctx->n_z;
     if (ctx->intersectionMatrix) {
         // unstructured -> Cartesian, solve, Cartesian -> unstructured (the transpose; the reference stops half way):
-        // both SpMVs and the five FFT passes run on the GPU in one cpc_apply_projected call
-        Mat P = ctx->intersectionMatrix, F = ctx->FFT_MAT;
-        PetscCheck(P->kind == SHIM_MAT_CSR && P->rows == N, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
-                   "intersectionMatrix must have %d rows", N);
-        PetscCheck(b->n == P->cols && x->n == P->cols, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
-                   "b and x must have %d entries", P->cols);
-        if (F->proj_seen != (const void *)P) {
-            std::vector<int64_t> rp(P->rowptr, P->rowptr + P->rows + 1);
-            std::vector<double> val((size_t)P->rowptr[P->rows]);
-            for (size_t q = 0; q < val.size(); ++q) val[q] = P->val[q].real();
-            PetscCallCPC(cpc_set_projection(F->plan, P->cols, rp.data(), P->colidx, val.data()));
-            F->proj_seen = P;
-        }
-        // eigenvalues: upload ctx->Diag once (same caching as solve_3D)
-        if (F->diag_seen != (const void *)ctx->Diag->array || F->diag_state != ctx->Diag->state) {
-            PetscCallCPC(cpc_set_symbol_diag(F->plan, ctx->Diag->array, CPC_MEM_HOST));
-            F->diag_seen = ctx->Diag->array;
-            F->diag_state = ctx->Diag->state;
-        }
-        PetscCallCPC(cpc_apply_projected(F->plan, b->array, x->array, CPC_MEM_HOST));
-        ++x->state;
+        // both SpMVs and the five passes run on the GPU in one cpc_apply_projected call
+        PetscCall(CPCApplyProjected(ctx->FFT_MAT, ctx->intersectionMatrix, ctx->Diag, b, x, N));
     } else {
         PetscCall(solve_3D(ctx->FFT_MAT, x, ctx->Diag, b, ctx->b_hat, N));
     }
@@ -48,27 +40,29 @@ PetscErrorCode setupFFTPrec3D(PC pc)
     PetscFunctionBeginUser;
     FFTPrecTransportContext *ctx = nullptr;
     PetscCall(PCShellGetContext(pc, &ctx));
-    PetscCheck(ctx, PETSC_COMM_WORLD, PETSC_ERR_ORDER, "setupFFTPrec3D: no context (PCShellSetContext / PCShellFFT3DAttach)");
-    PetscCheck(ctx->spaceDim >= 1 && ctx->spaceDim <= 3, PETSC_COMM_WORLD, PETSC_ERR_ARG_OUTOFRANGE,
+    PetscCheck(ctx, PETSC_COMM_SELF, PETSC_ERR_ORDER, "setupFFTPrec3D: no context (PCShellSetContext / PCShellFFT3DAttach)");
+    PetscCheck(ctx->spaceDim >= 1 && ctx->spaceDim <= 3, PETSC_COMM_SELF, PETSC_ERR_ARG_OUTOFRANGE,
                "Dimension should be 1, 2 or 3");
     // always three extents, 1 on unused axes (the reference passes ndim = spaceDim with a 3-entry dims array, :34-35)
     PetscInt dims[3] = { ctx->spaceDim > 2 ? ctx->n_z : 1, ctx->spaceDim > 1 ? ctx->n_y : 1, ctx->n_x };
-    PetscCall(MatCreateFFT(PETSC_COMM_WORLD, 3, dims, MATFFTW, &ctx->FFT_MAT));
-    PetscCall(MatCreateVecsFFTW(ctx->FFT_MAT, NULL, &ctx->Diag, NULL));
-    PetscCall(MatCreateVecsFFTW(ctx->FFT_MAT, &ctx->b_cartesien, &ctx->b_hat, NULL));
+    PetscCall(create_fft_mat(PETSC_COMM_WORLD, 3, dims, &ctx->FFT_MAT));
+    PetscCall(MatCreateVecs(ctx->FFT_MAT, &ctx->Diag, NULL));                    // reference :36 (MatCreateVecsFFTW)
+    PetscCall(MatCreateVecs(ctx->FFT_MAT, &ctx->b_cartesien, &ctx->b_hat));      // reference :37
 
-    // 1-D columns and their DFTs (reference :51-66), through the same library (1-D plans)
+    // 1-D columns and their DFTs (reference :51-66), through the same library (1-D plans on this rank alone)
     Vec c[3], ch[3];
     const PetscInt n[3] = { dims[2], dims[1], dims[0] };
     for (int a = 0; a < 3; ++a) {
         Mat F1;
         PetscInt d1[1] = { n[a] };
-        PetscCall(MatCreateFFT(PETSC_COMM_WORLD, 1, d1, MATFFTW, &F1));
-        PetscCall(MatCreateVecsFFTW(F1, &c[a], &ch[a], NULL));
+        PetscCall(create_fft_mat(PETSC_COMM_SELF, 1, d1, &F1));
+        PetscCall(MatCreateVecs(F1, &c[a], &ch[a]));
         PetscCall(build_transport_col(c[a], n[a]));
         PetscCall(MatMult(F1, c[a], ch[a]));
         PetscCall(MatDestroy(&F1));
     }
+    // Diag, distributed like b and X (this rank's z planes); solve_3D hands it to the plan on the first apply, where
+    // it is recognised as separable: three 1-D tables and -- for this upwind column -- the recurrence middle pass
     PetscCall(build_diag_mat_vec_3D(ctx->Diag, ch[0], ch[1], ch[2], n[0], n[1], n[2], ctx->lambda_x, ctx->lambda_y,
                                     ctx->lambda_z));
     for (int a = 0; a < 3; ++a) {
@@ -103,8 +97,8 @@ PetscErrorCode getFFTPrec3DContextCreate(PetscInt ndim, PetscScalar dt, PetscInt
                                          struct FFTPrecTransportContext **out)
 {
     PetscFunctionBeginUser;
-    PetscCheck(ndim > 0 && ndim < 4, PETSC_COMM_WORLD, PETSC_ERR_ARG_OUTOFRANGE, "Dimension should be 1, 2 or 3");
-    PetscCheck(nbCells > 0 && out, PETSC_COMM_WORLD, PETSC_ERR_ARG_OUTOFRANGE, "nbCells must be positive");
+    PetscCheck(ndim > 0 && ndim < 4, PETSC_COMM_SELF, PETSC_ERR_ARG_OUTOFRANGE, "Dimension should be 1, 2 or 3");
+    PetscCheck(nbCells > 0 && out, PETSC_COMM_SELF, PETSC_ERR_ARG_OUTOFRANGE, "nbCells must be positive");
     FFTPrecTransportContext *ctx = (FFTPrecTransportContext *)calloc(1, sizeof(FFTPrecTransportContext));
     PetscInt n = nbCells;
     if (ndim == 3) {                                   // floor(cbrt(nbCells)), robust to cbrt rounding just below
@@ -142,7 +136,7 @@ PetscErrorCode FFTPrec3DContextFree(struct FFTPrecTransportContext **ctx)
 PetscErrorCode PCShellFFT3DAttach(PC pc, struct FFTPrecTransportContext *ctx)
 {
     PetscFunctionBeginUser;
-    PetscCheck(pc && ctx, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG, "PCShellFFT3DAttach: null argument");
+    PetscCheck(pc && ctx, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "PCShellFFT3DAttach: null argument");
     PetscCall(PCShellSetContext(pc, ctx));
     PetscCall(PCShellSetSetUp(pc, setupFFTPrec3D));
     PetscCall(PCShellSetApply(pc, applyFFT3DPrecTransport));

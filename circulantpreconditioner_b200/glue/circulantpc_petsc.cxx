@@ -1,28 +1,217 @@
 // circulantpc_petsc.cxx -- reference-named solver entry points over the libcirculantpc C ABI.
 // Each function cites the reference lines whose behaviour it reproduces; none of the arithmetic is done here.
+// Only public PETSc functions are used (no Vec / Mat internals), so the file compiles unchanged against
+// <petscksp.h> (-DCPC_WITH_PETSC), against petsc_opaque_stub.h (the compile check) and against petsc_shim.h.
 #include "circulantpc_petsc.h"
 
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
 
 namespace {
 
-// The plan that stands behind an FFT Mat (MatCreateFFT in petsc_shim.cxx; with real PETSc: a plan composed onto
-// the Mat with PetscObjectCompose).
-PetscErrorCode plan_of(Mat FFT_MAT, PetscInt n_x, PetscInt n_y, PetscInt n_z, cpc_plan *plan)
+// What rides on an FFT Mat: the plan and what was last uploaded to it.
+struct CpcMatData {
+    cpc_plan plan;
+    PetscObjectId diag_id;          // Diag Vec whose eigenvalues the plan holds (0: none / set through tables)
+    PetscObjectState diag_state;
+    PetscObjectId proj_id;          // projection Mat handed to cpc_set_projection
+    PetscInt n_x, n_y, n_z;
+};
+
+PetscErrorCode mat_data_destroy(void *p)
 {
-    PetscCheck(FFT_MAT && FFT_MAT->kind == SHIM_MAT_FFT && FFT_MAT->plan, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
-               "FFT_MAT was not created by MatCreateFFT");
-    cpc_plan_info info;
-    PetscCallCPC(cpc_get_info(FFT_MAT->plan, &info));
-    PetscCheck(n_x < 0 || (info.nx == n_x && info.ny == n_y && info.nz == n_z), PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
-               "FFT_MAT is %d x %d x %d but the call says %d x %d x %d", info.nx, info.ny, info.nz, n_x, n_y, n_z);
-    *plan = FFT_MAT->plan;
+    CpcMatData *d = (CpcMatData *)p;
+    if (d) {
+        cpc_destroy(d->plan);
+        free(d);
+    }
+    return PETSC_SUCCESS;
+}
+
+PetscErrorCode mat_data(Mat A, CpcMatData **out)
+{
+    PetscObject obj = nullptr;
+    PetscCheck(A, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "null FFT_MAT");
+    PetscCall(PetscObjectQuery((PetscObject)A, "cpc_plan", &obj));
+    PetscCheck(obj, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG,
+               "FFT_MAT carries no libcirculantpc plan (create it with MatCreateFFT_CPC / CPCMatAttachPlan)");
+    void *p = nullptr;
+    PetscCall(PetscContainerGetPointer((PetscContainer)obj, &p));
+    *out = (CpcMatData *)p;
+    return PETSC_SUCCESS;
+}
+
+// The plan behind an FFT Mat, with the grid extents checked when the caller states them (n_x >= 0).
+PetscErrorCode plan_of(Mat FFT_MAT, PetscInt n_x, PetscInt n_y, PetscInt n_z, CpcMatData **data)
+{
+    PetscCall(mat_data(FFT_MAT, data));
+    PetscCheck(n_x < 0 || ((*data)->n_x == n_x && (*data)->n_y == n_y && (*data)->n_z == n_z), PETSC_COMM_SELF,
+               PETSC_ERR_ARG_WRONG, "FFT_MAT is %d x %d x %d but the call says %d x %d x %d", (int)(*data)->n_x,
+               (int)(*data)->n_y, (int)(*data)->n_z, (int)n_x, (int)n_y, (int)n_z);
+    return PETSC_SUCCESS;
+}
+
+// Arrays of the right-hand side and of the solution in a common memory kind: device pointers when both Vecs live
+// on the GPU (VECCUDA), host pointers otherwise (PETSc brings the host copy of a CUDA Vec up to date on demand).
+struct ApplyArrays {
+    Vec b, X;
+    const PetscScalar *bb;
+    PetscScalar *xx;
+    int kind;
+    bool memtype_access;
+};
+
+PetscErrorCode arrays_get(Vec b, Vec X, ApplyArrays *a)
+{
+    a->b = b; a->X = X; a->bb = nullptr; a->xx = nullptr; a->memtype_access = true;
+    PetscMemType mb = PETSC_MEMTYPE_HOST, mx = PETSC_MEMTYPE_HOST;
+    if (b == X) {                    // Un, Un (tests/TransportEquationFFT_SphericalExplosion_impl_mpi.cxx:111)
+        PetscCall(VecGetArrayAndMemType(X, &a->xx, &mx));
+        a->bb = a->xx;
+        a->kind = PetscMemTypeDevice(mx) ? CPC_MEM_DEVICE : CPC_MEM_HOST;
+        return PETSC_SUCCESS;
+    }
+    PetscCall(VecGetArrayReadAndMemType(b, &a->bb, &mb));
+    PetscCall(VecGetArrayAndMemType(X, &a->xx, &mx));
+    if (PetscMemTypeDevice(mb) == PetscMemTypeDevice(mx)) {
+        a->kind = PetscMemTypeDevice(mb) ? CPC_MEM_DEVICE : CPC_MEM_HOST;
+        return PETSC_SUCCESS;
+    }
+    // one Vec on the GPU, the other on the host: fall back to host arrays for both
+    PetscCall(VecRestoreArrayAndMemType(X, &a->xx));
+    PetscCall(VecRestoreArrayReadAndMemType(b, &a->bb));
+    a->memtype_access = false;
+    PetscCall(VecGetArrayRead(b, &a->bb));
+    PetscCall(VecGetArray(X, &a->xx));
+    a->kind = CPC_MEM_HOST;
+    return PETSC_SUCCESS;
+}
+
+PetscErrorCode arrays_restore(ApplyArrays *a)
+{
+    if (a->memtype_access) {
+        PetscCall(VecRestoreArrayAndMemType(a->X, &a->xx));
+        if (a->b != a->X) PetscCall(VecRestoreArrayReadAndMemType(a->b, &a->bb));
+    } else {
+        PetscCall(VecRestoreArray(a->X, &a->xx));
+        PetscCall(VecRestoreArrayRead(a->b, &a->bb));
+    }
+    return PETSC_SUCCESS;
+}
+
+// cpc_apply on two Vecs.  Device arrays: the call is asynchronous on the plan's stream; PETSc's own kernels run on
+// its default stream, so the result is synchronised before the arrays are handed back.
+PetscErrorCode apply_vecs(cpc_plan plan, Vec b, Vec X)
+{
+    ApplyArrays a;
+    PetscCall(arrays_get(b, X, &a));
+    int st = cpc_apply(plan, a.bb, a.xx, a.kind);
+    if (!st && a.kind == CPC_MEM_DEVICE) st = cpc_sync(plan);
+    PetscCall(arrays_restore(&a));
+    PetscCallCPC(st);
     return PETSC_SUCCESS;
 }
 
 }  // namespace
 
 extern "C" {
+
+PetscErrorCode CPCMatAttachPlan(Mat A, MPI_Comm comm, PetscInt n_x, PetscInt n_y, PetscInt n_z)
+{
+    PetscFunctionBeginUser;
+    int size = 1, rank = 0;
+    MPI_Comm_size(comm, &size);
+    MPI_Comm_rank(comm, &rank);
+    unsigned char id[CPC_NCCL_UNIQUE_ID_BYTES];
+    const void *idp = nullptr;
+    if (size > 1) {
+#ifdef CPC_WITH_PETSC
+        if (rank == 0) PetscCallCPC(cpc_nccl_unique_id(id));
+        MPI_Bcast(id, (int)sizeof(id), MPI_BYTE, 0, comm);
+        idp = id;
+#else
+        idp = ShimWorldNcclId();                  // the test launcher broadcast it (ShimWorldSet)
+        PetscCheck(idp, PETSC_COMM_SELF, PETSC_ERR_ORDER, "ShimWorldSet was not given the NCCL id");
+        (void)id;
+#endif
+    }
+    // PetscScalar of a complex build is complex128; a real build takes the r2c / c2r plan
+#if defined(PETSC_USE_COMPLEX)
+    const int dtype = CPC_C128;
+#else
+    const int dtype = CPC_F64;
+#endif
+    cpc_plan_desc d = { (int)n_x, (int)n_y, (int)n_z, 1, dtype, size, rank, idp, nullptr, -1 };
+    cpc_plan plan = nullptr;
+    PetscCallCPC(cpc_plan_create(&plan, &d));
+    CpcMatData *data = (CpcMatData *)calloc(1, sizeof(CpcMatData));
+    data->plan = plan;
+    data->n_x = n_x; data->n_y = n_y; data->n_z = n_z;
+    PetscContainer c;
+    PetscCall(PetscContainerCreate(PETSC_COMM_SELF, &c));
+    PetscCall(PetscContainerSetPointer(c, data));
+    PetscCall(PetscContainerSetUserDestroy(c, mat_data_destroy));
+    PetscCall(PetscObjectCompose((PetscObject)A, "cpc_plan", (PetscObject)c));
+    PetscCall(PetscContainerDestroy(&c));          // the Mat holds the reference now
+    PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+PetscErrorCode CPCMatGetPlan(Mat A, cpc_plan *plan)
+{
+    PetscFunctionBeginUser;
+    CpcMatData *d = nullptr;
+    PetscCall(mat_data(A, &d));
+    *plan = d->plan;
+    PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+#ifdef CPC_WITH_PETSC
+static PetscErrorCode MatMult_CPC(Mat A, Vec x, Vec y)
+{
+    PetscFunctionBeginUser;
+    cpc_plan plan;
+    PetscCall(CPCMatGetPlan(A, &plan));
+    ApplyArrays a;
+    PetscCall(arrays_get(x, y, &a));
+    int st = cpc_forward(plan, a.bb, a.xx, a.kind);            // unnormalised forward DFT (FftLinearSolver_3D.c:170)
+    if (!st && a.kind == CPC_MEM_DEVICE) st = cpc_sync(plan);
+    PetscCall(arrays_restore(&a));
+    PetscCallCPC(st);
+    PetscFunctionReturn(PETSC_SUCCESS);
+}
+static PetscErrorCode MatMultTranspose_CPC(Mat A, Vec x, Vec y)
+{
+    PetscFunctionBeginUser;
+    cpc_plan plan;
+    PetscCall(CPCMatGetPlan(A, &plan));
+    ApplyArrays a;
+    PetscCall(arrays_get(x, y, &a));
+    int st = cpc_inverse(plan, a.bb, a.xx, a.kind);            // unnormalised backward DFT (FftLinearSolver_3D.c:180)
+    if (!st && a.kind == CPC_MEM_DEVICE) st = cpc_sync(plan);
+    PetscCall(arrays_restore(&a));
+    PetscCallCPC(st);
+    PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+PetscErrorCode MatCreateFFT_CPC(MPI_Comm comm, PetscInt ndim, const PetscInt dims[], Mat *A)
+{
+    PetscFunctionBeginUser;
+    PetscCheck(ndim >= 1 && ndim <= 3 && dims && A, comm, PETSC_ERR_ARG_OUTOFRANGE, "MatCreateFFT_CPC: ndim must be 1..3");
+    PetscInt n[3] = { 1, 1, 1 }, N = 1;                          // nx, ny, nz (x fastest = last entry of dims)
+    for (PetscInt d = 0; d < ndim; ++d) { n[ndim - 1 - d] = dims[d]; N *= dims[d]; }
+    int size = 1;
+    MPI_Comm_size(comm, &size);
+    PetscCheck(n[2] % size == 0, comm, PETSC_ERR_SUP, "z-slabs need nz divisible by the number of ranks");
+    const PetscInt nloc = N / size;
+    PetscCall(MatCreateShell(comm, nloc, nloc, N, N, NULL, A));
+    PetscCall(MatShellSetOperation(*A, MATOP_MULT, (void (*)(void))MatMult_CPC));
+    PetscCall(MatShellSetOperation(*A, MATOP_MULT_TRANSPOSE, (void (*)(void))MatMultTranspose_CPC));
+    PetscCall(CPCMatAttachPlan(*A, comm, n[0], n[1], n[2]));
+    PetscFunctionReturn(PETSC_SUCCESS);
+}
+#endif
 
 // reference FftLinearSolver_3D.c:80-90: zero vector, then c[0] = 1, c[1] = -1 when size > 1
 PetscErrorCode build_transport_col(Vec c, PetscInt size)
@@ -33,6 +222,8 @@ PetscErrorCode build_transport_col(Vec c, PetscInt size)
         PetscCall(VecSetValue(c, 0, 1.0, INSERT_VALUES));
         PetscCall(VecSetValue(c, 1, -1.0, INSERT_VALUES));
     }
+    PetscCall(VecAssemblyBegin(c));
+    PetscCall(VecAssemblyEnd(c));
     PetscFunctionReturn(PETSC_SUCCESS);
 }
 
@@ -45,9 +236,9 @@ PetscErrorCode vec_kronecker_product_identity_left(Vec c, Vec res, PetscInt c_si
     PetscInt sc, sr;
     PetscCall(VecGetSize(c, &sc));
     PetscCall(VecGetSize(res, &sr));
-    PetscCheck(sc == c_size && sr == c_size * id_size, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
-               "vec_kronecker_product_identity_left: c has %d entries, res %d, expected %d and %d", sc, sr, c_size,
-               c_size * id_size);
+    PetscCheck(sc == c_size && sr == c_size * id_size, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG,
+               "vec_kronecker_product_identity_left: c has %d entries, res %d, expected %d and %d", (int)sc, (int)sr,
+               (int)c_size, (int)(c_size * id_size));
     const PetscScalar *cc;
     PetscScalar *rr;
     PetscCall(VecGetArrayRead(c, &cc));
@@ -67,9 +258,9 @@ PetscErrorCode vec_kronecker_product_identity_right(Vec c, Vec res, PetscInt c_s
     PetscInt sc, sr;
     PetscCall(VecGetSize(c, &sc));
     PetscCall(VecGetSize(res, &sr));
-    PetscCheck(sc == c_size && sr == c_size * id_size, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
-               "vec_kronecker_product_identity_right: c has %d entries, res %d, expected %d and %d", sc, sr, c_size,
-               c_size * id_size);
+    PetscCheck(sc == c_size && sr == c_size * id_size, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG,
+               "vec_kronecker_product_identity_right: c has %d entries, res %d, expected %d and %d", (int)sc, (int)sr,
+               (int)c_size, (int)(c_size * id_size));
     const PetscScalar *cc;
     PetscScalar *rr;
     PetscCall(VecGetArrayRead(c, &cc));
@@ -84,75 +275,80 @@ PetscErrorCode vec_kronecker_product_identity_right(Vec c, Vec res, PetscInt c_s
 }
 
 // reference FftLinearSolver_3D.c:136-164: Diag[k,j,i] = 1 + lx cx[i] + ly cy[j] + lz cz[k].
-// The three 1-D tables go to the GPU (cpc_set_symbol_separable) and the N eigenvalues are produced there
-// (cpc_get_diag) -- no per-element VecSetValue loops (reference :92-134 does 3N of them).
+// The three 1-D tables go to the GPU and this rank's planes of Diag are produced there in one launch
+// (cpc_build_diag_separable) -- no per-element VecSetValue loops (reference :92-134 does 3N of them).  Diag may be a
+// host or a CUDA Vec, sequential or a z-slab of an MPI Vec (ownership range = whole planes).
 PetscErrorCode build_diag_mat_vec_3D(Vec Diag, Vec c_x_hat, Vec c_y_hat, Vec c_z_hat, PetscInt n_x, PetscInt n_y,
                                      PetscInt n_z, PetscScalar lambda_x, PetscScalar lambda_y, PetscScalar lambda_z)
 {
     PetscFunctionBeginUser;
-    PetscInt sx, sy, sz, sd;
+    PetscInt sx, sy, sz, sd, lo, hi;
     PetscCall(VecGetSize(c_x_hat, &sx));
     PetscCall(VecGetSize(c_y_hat, &sy));
     PetscCall(VecGetSize(c_z_hat, &sz));
     PetscCall(VecGetSize(Diag, &sd));
-    PetscCheck(sx == n_x && sy == n_y && sz == n_z && sd == n_x * n_y * n_z, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
-               "build_diag_mat_vec_3D: vector sizes do not match %d x %d x %d", n_x, n_y, n_z);
-    PetscCheck(std::imag(lambda_x) == 0 && std::imag(lambda_y) == 0 && std::imag(lambda_z) == 0, PETSC_COMM_WORLD,
-               PETSC_ERR_ARG_WRONG, "build_diag_mat_vec_3D: lambdas must be real");
-    // a scratch plan of the right shape turns the tables into the N eigenvalues on the GPU
-    cpc_plan_desc d = { n_x, n_y, n_z, 1, CPC_C128, 1, 0, nullptr, nullptr, -1 };
-    cpc_plan plan = nullptr;
-    PetscCallCPC(cpc_plan_create(&plan, &d));
+    PetscCall(VecGetOwnershipRange(Diag, &lo, &hi));
+    PetscCheck(sx == n_x && sy == n_y && sz == n_z && sd == n_x * n_y * n_z, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG,
+               "build_diag_mat_vec_3D: vector sizes do not match %d x %d x %d", (int)n_x, (int)n_y, (int)n_z);
+    const PetscInt plane = n_x * n_y;
+    PetscCheck(lo % plane == 0 && hi % plane == 0, PETSC_COMM_SELF, PETSC_ERR_SUP,
+               "build_diag_mat_vec_3D: Diag must own whole z planes (owns [%d, %d), plane = %d)", (int)lo, (int)hi, (int)plane);
+#if defined(PETSC_USE_COMPLEX)
+    PetscCheck(PetscImaginaryPart(lambda_x) == 0 && PetscImaginaryPart(lambda_y) == 0 && PetscImaginaryPart(lambda_z) == 0,
+               PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "build_diag_mat_vec_3D: lambdas must be real");
+#endif
     const PetscScalar *cx, *cy, *cz;
     PetscCall(VecGetArrayRead(c_x_hat, &cx));
     PetscCall(VecGetArrayRead(c_y_hat, &cy));
     PetscCall(VecGetArrayRead(c_z_hat, &cz));
-    int st = cpc_set_symbol_separable(plan, (const double *)cx, (const double *)cy, (const double *)cz,
-                                      std::real(lambda_x), std::real(lambda_y), std::real(lambda_z));
     PetscScalar *dd;
-    PetscCall(VecGetArray(Diag, &dd));
-    if (!st) st = cpc_get_diag(plan, dd, CPC_MEM_HOST);
-    PetscCall(VecRestoreArray(Diag, &dd));
-    cpc_destroy(plan);
-    if (st) return ShimError(PETSC_ERR_LIB, "libcirculantpc: %s", cpc_last_error());
+    PetscMemType mt = PETSC_MEMTYPE_HOST;
+    PetscCall(VecGetArrayAndMemType(Diag, &dd, &mt));
+    const int st = cpc_build_diag_separable((int)n_x, (int)n_y, (int)n_z, (const double *)cx, (const double *)cy,
+                                            (const double *)cz, PetscRealPart(lambda_x), PetscRealPart(lambda_y),
+                                            PetscRealPart(lambda_z), (int)(lo / plane), (int)((hi - lo) / plane), dd,
+                                            PetscMemTypeDevice(mt) ? CPC_MEM_DEVICE : CPC_MEM_HOST);
+    PetscCall(VecRestoreArrayAndMemType(Diag, &dd));
+    PetscCall(VecRestoreArrayRead(c_z_hat, &cz));
+    PetscCall(VecRestoreArrayRead(c_y_hat, &cy));
+    PetscCall(VecRestoreArrayRead(c_x_hat, &cx));
+    PetscCallCPC(st);
     PetscFunctionReturn(PETSC_SUCCESS);
 }
 
 // reference FftLinearSolver_3D.c:166-190 (complex-scalar branch):
 //   MatMult(FFT_MAT, b, b_hat); b_hat ./= Diag; MatMultTranspose(FFT_MAT, b_hat, X); X *= 1/size
 // as ONE cpc_apply (5 HBM passes).  b may alias X.  b_hat is accepted for signature compatibility and not touched.
+// Diag goes to the plan once per (Vec, state): cpc_set_symbol_diag recognises the separable table that
+// build_diag_mat_vec_3D produces and keeps three 1-D tables -- so the PCShell path takes the same kernels as
+// cpc_set_symbol_transport, on device-resident Vecs without any host staging.
 PetscErrorCode solve_3D(Mat FFT_MAT, Vec X, Vec Diag, Vec b, Vec b_hat, PetscInt size)
 {
     PetscFunctionBeginUser;
     (void)b_hat;
-    cpc_plan plan = nullptr;
-    PetscCall(plan_of(FFT_MAT, -1, -1, -1, &plan));
+    CpcMatData *md = nullptr;
+    PetscCall(plan_of(FFT_MAT, -1, -1, -1, &md));
     PetscInt nb, nx_, nd;
     PetscCall(VecGetSize(b, &nb));
     PetscCall(VecGetSize(X, &nx_));
     PetscCall(VecGetSize(Diag, &nd));
-    PetscCheck(nb == size && nx_ == size && nd == size, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
-               "solve_3D: vectors must have %d entries (b %d, X %d, Diag %d)", size, nb, nx_, nd);
-    const PetscScalar *dd;
-    PetscCall(VecGetArrayRead(Diag, &dd));
-    if (FFT_MAT->diag_seen != (const void *)dd || FFT_MAT->diag_state != Diag->state) {
-        PetscCallCPC(cpc_set_symbol_diag(plan, dd, CPC_MEM_HOST));      // once per Diag, then it lives in HBM
-        FFT_MAT->diag_seen = dd;
-        FFT_MAT->diag_state = Diag->state;
+    PetscCheck(nb == size && nx_ == size && nd == size, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG,
+               "solve_3D: vectors must have %d entries (b %d, X %d, Diag %d)", (int)size, (int)nb, (int)nx_, (int)nd);
+    PetscObjectId did;
+    PetscObjectState dst;
+    PetscCall(PetscObjectGetId((PetscObject)Diag, &did));
+    PetscCall(PetscObjectStateGet((PetscObject)Diag, &dst));
+    if (md->diag_id != did || md->diag_state != dst) {
+        const PetscScalar *dd;
+        PetscMemType mt = PETSC_MEMTYPE_HOST;
+        PetscCall(VecGetArrayReadAndMemType(Diag, &dd, &mt));
+        const int st = cpc_set_symbol_diag(md->plan, dd, PetscMemTypeDevice(mt) ? CPC_MEM_DEVICE : CPC_MEM_HOST);
+        PetscCall(VecRestoreArrayReadAndMemType(Diag, &dd));
+        PetscCallCPC(st);
+        md->diag_id = did;
+        md->diag_state = dst;
     }
-    PetscCall(VecRestoreArrayRead(Diag, &dd));
-    const PetscScalar *bb;
-    PetscScalar *xx;
-    PetscCall(VecGetArrayRead(b, &bb));
-    if (b == X) {
-        xx = const_cast<PetscScalar *>(bb);
-        ++X->state;
-    } else {
-        PetscCall(VecGetArray(X, &xx));
-    }
-    PetscCallCPC(cpc_apply(plan, bb, xx, CPC_MEM_HOST));
-    if (b != X) PetscCall(VecRestoreArray(X, &xx));
-    PetscCall(VecRestoreArrayRead(b, &bb));
+    PetscCall(apply_vecs(md->plan, b, X));
     PetscFunctionReturn(PETSC_SUCCESS);
 }
 
@@ -162,24 +358,24 @@ PetscErrorCode Fft3DSolver(PetscInt n_x, PetscInt n_y, PetscInt n_z, PetscScalar
                            PetscScalar lambda_z, Vec X, Vec b, Mat FFT_MAT, Vec c_x_hat, Vec c_y_hat, Vec c_z_hat)
 {
     PetscFunctionBeginUser;
-    cpc_plan plan;
-    PetscCall(plan_of(FFT_MAT, n_x, n_y, n_z, &plan));
+    CpcMatData *md = nullptr;
+    PetscCall(plan_of(FFT_MAT, n_x, n_y, n_z, &md));
     PetscInt size;
     PetscCall(VecGetSize(X, &size));
-    PetscCheck(size == n_x * n_y * n_z, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG, "Fft3DSolver: X has %d entries", size);
+    PetscCheck(size == n_x * n_y * n_z, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "Fft3DSolver: X has %d entries", (int)size);
     // the separable tables go straight to the plan: no N-element Diag round trip
     const PetscScalar *cx, *cy, *cz;
     PetscCall(VecGetArrayRead(c_x_hat, &cx));
     PetscCall(VecGetArrayRead(c_y_hat, &cy));
     PetscCall(VecGetArrayRead(c_z_hat, &cz));
-    PetscCallCPC(cpc_set_symbol_separable(plan, (const double *)cx, (const double *)cy, (const double *)cz,
-                                          std::real(lambda_x), std::real(lambda_y), std::real(lambda_z)));
-    FFT_MAT->diag_seen = nullptr;
-    const PetscScalar *bb;
-    PetscCall(VecGetArrayRead(b, &bb));
-    PetscScalar *xx = (b == X) ? const_cast<PetscScalar *>(bb) : X->array;
-    ++X->state;
-    PetscCallCPC(cpc_apply(plan, bb, xx, CPC_MEM_HOST));
+    const int st = cpc_set_symbol_separable(md->plan, (const double *)cx, (const double *)cy, (const double *)cz,
+                                            PetscRealPart(lambda_x), PetscRealPart(lambda_y), PetscRealPart(lambda_z));
+    PetscCall(VecRestoreArrayRead(c_z_hat, &cz));
+    PetscCall(VecRestoreArrayRead(c_y_hat, &cy));
+    PetscCall(VecRestoreArrayRead(c_x_hat, &cx));
+    PetscCallCPC(st);
+    md->diag_id = 0;
+    PetscCall(apply_vecs(md->plan, b, X));
     PetscFunctionReturn(PETSC_SUCCESS);
 }
 
@@ -189,22 +385,20 @@ PetscErrorCode FftTransportSolver(PetscInt n_x, PetscInt n_y, PetscInt n_z, Pets
                                   PetscScalar lambda_z, Vec X, Vec b, Mat FFT_MAT)
 {
     PetscFunctionBeginUser;
-    cpc_plan plan;
-    PetscCall(plan_of(FFT_MAT, n_x, n_y, n_z, &plan));
+    CpcMatData *md = nullptr;
+    PetscCall(plan_of(FFT_MAT, n_x, n_y, n_z, &md));
     PetscInt nb, nxx;
     PetscCall(VecGetSize(b, &nb));
     PetscCall(VecGetSize(X, &nxx));
-    PetscCheck(nb == n_x * n_y * n_z && nxx == nb, PETSC_COMM_WORLD, PETSC_ERR_ARG_WRONG,
-               "FftTransportSolver: vectors must have %d entries", n_x * n_y * n_z);
-    PetscCheck(std::imag(lambda_x) == 0 && std::imag(lambda_y) == 0 && std::imag(lambda_z) == 0, PETSC_COMM_WORLD,
-               PETSC_ERR_ARG_WRONG, "FftTransportSolver: lambdas must be real");
-    PetscCallCPC(cpc_set_symbol_transport(plan, std::real(lambda_x), std::real(lambda_y), std::real(lambda_z)));
-    FFT_MAT->diag_seen = nullptr;
-    const PetscScalar *bb;
-    PetscCall(VecGetArrayRead(b, &bb));
-    PetscScalar *xx = (b == X) ? const_cast<PetscScalar *>(bb) : X->array;
-    ++X->state;
-    PetscCallCPC(cpc_apply(plan, bb, xx, CPC_MEM_HOST));
+    PetscCheck(nb == n_x * n_y * n_z && nxx == nb, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG,
+               "FftTransportSolver: vectors must have %d entries", (int)(n_x * n_y * n_z));
+#if defined(PETSC_USE_COMPLEX)
+    PetscCheck(PetscImaginaryPart(lambda_x) == 0 && PetscImaginaryPart(lambda_y) == 0 && PetscImaginaryPart(lambda_z) == 0,
+               PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "FftTransportSolver: lambdas must be real");
+#endif
+    PetscCallCPC(cpc_set_symbol_transport(md->plan, PetscRealPart(lambda_x), PetscRealPart(lambda_y), PetscRealPart(lambda_z)));
+    md->diag_id = 0;
+    PetscCall(apply_vecs(md->plan, b, X));
     PetscFunctionReturn(PETSC_SUCCESS);
 }
 
@@ -242,6 +436,62 @@ PetscErrorCode PetscFft3DTransportSolver(struct StructuredTransportContext c, Ve
     PetscFunctionBeginUser;
     PetscCall(Fft3DTransportSolver(c.n_x, c.n_y, c.n_z, c.a_x, c.a_y, c.a_z, c.dt, c.delta_x, c.delta_y, c.delta_z, x, b,
                                    c.FFT_MAT));
+    PetscFunctionReturn(PETSC_SUCCESS);
+}
+
+// x = P^T solve_3D(P b) for applyFFT3DPrecTransport (circulantpc_pcshell.cxx): the projection (a SeqAIJ Mat with
+// N = n_x n_y n_z rows) is handed to the plan once, the eigenvalues as in solve_3D.
+PetscErrorCode CPCApplyProjected(Mat FFT_MAT, Mat P, Vec Diag, Vec b, Vec x, PetscInt N)
+{
+    PetscFunctionBeginUser;
+    CpcMatData *md = nullptr;
+    PetscCall(plan_of(FFT_MAT, -1, -1, -1, &md));
+    PetscInt rows, cols, nb, nxx;
+    PetscCall(MatGetSize(P, &rows, &cols));
+    PetscCheck(rows == N, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "intersectionMatrix must have %d rows", (int)N);
+    PetscCall(VecGetSize(b, &nb));
+    PetscCall(VecGetSize(x, &nxx));
+    PetscCheck(nb == cols && nxx == cols, PETSC_COMM_SELF, PETSC_ERR_ARG_WRONG, "b and x must have %d entries", (int)cols);
+    PetscObjectId pid;
+    PetscCall(PetscObjectGetId((PetscObject)P, &pid));
+    if (md->proj_id != pid) {
+        PetscInt nrow = 0;
+        const PetscInt *ia = nullptr, *ja = nullptr;
+        PetscBool done = PETSC_FALSE;
+        PetscCall(MatGetRowIJ(P, 0, PETSC_FALSE, PETSC_FALSE, &nrow, &ia, &ja, &done));
+        PetscCheck(done && nrow == rows, PETSC_COMM_SELF, PETSC_ERR_SUP, "intersectionMatrix must be a SeqAIJ matrix");
+        const PetscScalar *va = nullptr;
+        PetscCall(MatSeqAIJGetArrayRead(P, &va));
+        std::vector<int64_t> rp(ia, ia + rows + 1);
+        std::vector<int32_t> ci(ja, ja + ia[rows]);
+        std::vector<double> val((size_t)ia[rows]);
+        for (size_t q = 0; q < val.size(); ++q) val[q] = PetscRealPart(va[q]);
+        const int st = cpc_set_projection(md->plan, cols, rp.data(), ci.data(), val.data());
+        PetscCall(MatSeqAIJRestoreArrayRead(P, &va));
+        PetscCall(MatRestoreRowIJ(P, 0, PETSC_FALSE, PETSC_FALSE, &nrow, &ia, &ja, &done));
+        PetscCallCPC(st);
+        md->proj_id = pid;
+    }
+    PetscObjectId did;
+    PetscObjectState dst;
+    PetscCall(PetscObjectGetId((PetscObject)Diag, &did));
+    PetscCall(PetscObjectStateGet((PetscObject)Diag, &dst));
+    if (md->diag_id != did || md->diag_state != dst) {
+        const PetscScalar *dd;
+        PetscMemType mt = PETSC_MEMTYPE_HOST;
+        PetscCall(VecGetArrayReadAndMemType(Diag, &dd, &mt));
+        const int st = cpc_set_symbol_diag(md->plan, dd, PetscMemTypeDevice(mt) ? CPC_MEM_DEVICE : CPC_MEM_HOST);
+        PetscCall(VecRestoreArrayReadAndMemType(Diag, &dd));
+        PetscCallCPC(st);
+        md->diag_id = did;
+        md->diag_state = dst;
+    }
+    ApplyArrays a;
+    PetscCall(arrays_get(b, x, &a));
+    int st = cpc_apply_projected(md->plan, a.bb, a.xx, a.kind);
+    if (!st && a.kind == CPC_MEM_DEVICE) st = cpc_sync(md->plan);
+    PetscCall(arrays_restore(&a));
+    PetscCallCPC(st);
     PetscFunctionReturn(PETSC_SUCCESS);
 }
 

@@ -17,11 +17,22 @@
 #ifndef CIRCULANTPC_PETSC_H
 #define CIRCULANTPC_PETSC_H
 
-#ifdef CPC_WITH_PETSC
+#if defined(CPC_WITH_PETSC) && defined(CPC_PETSC_STUB)
+#include "petsc_opaque_stub.h"      /* compile check only: opaque PETSc types + the public prototypes this glue calls */
+#elif defined(CPC_WITH_PETSC)
 #include <petscksp.h>
 #else
 #include "petsc_shim.h"
 #endif
+#include "../../include/circulantpc.h"
+
+/* a libcirculantpc status becomes a PETSc error carrying cpc_last_error() */
+#define PetscCallCPC(call)                                                                                         \
+    do {                                                                                                           \
+        const int _st = (call);                                                                                    \
+        PetscCheck(_st == 0, PETSC_COMM_SELF, _st == CPC_ERR_ARG ? PETSC_ERR_ARG_WRONG : PETSC_ERR_LIB,            \
+                   "libcirculantpc: %s", cpc_last_error());                                                        \
+    } while (0)
 
 #ifndef CPC_WITH_SOLVERLAB
 /* SOLVERLAB's Mesh is only an unused by-value argument of getFFTPrec3DContext (reference PCSHELLFft_3D.hxx:40). */
@@ -87,6 +98,22 @@ PetscErrorCode getFFTPrec3DContext(PetscInt ndim, PetscScalar dt, PetscInt nbCel
                                    PetscScalar Xmax, PetscScalar Ymax, PetscScalar Zmax, Mesh srcMesh);
 
 extern "C" {
+/* additions (not in the reference): the plan that replaces the FFTW plan rides on the FFT Mat.
+ *   CPCMatAttachPlan  creates the libcirculantpc plan for an n_x x n_y x n_z grid (z-slabs over comm's ranks) and
+ *                     composes it onto A (PetscObjectCompose of a PetscContainer; destroyed with the Mat).  The shim's
+ *                     MatCreateFFT calls it; with a real PETSc use MatCreateFFT_CPC below, or call it on the Mat that
+ *                     MatCreateFFT returned.
+ *   CPCMatGetPlan     the composed plan (error if none).                                                          */
+PetscErrorCode CPCMatAttachPlan(Mat A, MPI_Comm comm, PetscInt n_x, PetscInt n_y, PetscInt n_z);
+PetscErrorCode CPCMatGetPlan(Mat A, cpc_plan *plan);
+#ifdef CPC_WITH_PETSC
+/* MatCreateFFT(comm, ndim, dims, MATFFTW, A) without FFTW: a MATSHELL whose MatMult / MatMultTranspose are cpc_forward /
+ * cpc_inverse, with the plan composed onto it (reference call sites: src/PCSHELLFft_3D.cxx:34-35,
+ * tests/TransportEquationFFT_SphericalExplosion_impl_mpi.cxx:97-100; dims slowest first). */
+PetscErrorCode MatCreateFFT_CPC(MPI_Comm comm, PetscInt ndim, const PetscInt dims[], Mat *A);
+#endif
+/* x = P^T solve_3D(P b) on the GPU in one call (used by applyFFT3DPrecTransport when ctx->intersectionMatrix is set) */
+PetscErrorCode CPCApplyProjected(Mat FFT_MAT, Mat P, Vec Diag, Vec b, Vec x, PetscInt N);
 /* additions (not in the reference): the missing wiring */
 PetscErrorCode getFFTPrec3DContextCreate(PetscInt ndim, PetscScalar dt, PetscInt nbCells, PetscScalar a_x,
                                          PetscScalar a_y, PetscScalar a_z, PetscScalar Xmin, PetscScalar Ymin,

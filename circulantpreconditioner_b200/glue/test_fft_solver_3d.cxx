@@ -166,6 +166,38 @@ static int pcshell_case()
     }
     printf("%-28s %4d x %3d x %3d : worst rel error over 3 PCApply %.2e\n", "PCSHELL life cycle", n, n, n, worst);
     EXPECT(worst < 1e-12, "PCApply");
+    {
+        // the Diag that setupFFTPrec3D built went to the plan through solve_3D and was recognised as separable:
+        // three 1-D tables and the recurrence form of the middle pass -- the same kernels as cpc_set_symbol_transport
+        cpc_plan plan = nullptr;
+        cpc_plan_info info;
+        CHK(CPCMatGetPlan(ctx->FFT_MAT, &plan));
+        EXPECT(cpc_get_info(plan, &info) == 0 && info.symbol_kind == CPC_SYMBOL_SEPARABLE && info.fast_path[2] == 2,
+               "PCShell path did not take the separable / recurrence kernels (symbol %d, fast_path[2] %d)",
+               info.symbol_kind, info.fast_path[2]);
+    }
+    {
+        // device-resident Vecs (VECCUDA): no host staging; same answer
+        Vec Bd, Xd;
+        CHK(VecCreateSeqCUDA(PETSC_COMM_WORLD, N, &Bd));
+        CHK(VecDuplicate(Bd, &Xd));
+        CHK(VecCopy(B, Bd));
+        cpc_plan plan = nullptr;
+        cpc_plan_info i0, i1;
+        CHK(CPCMatGetPlan(ctx->FFT_MAT, &plan));
+        cpc_get_info(plan, &i0);
+        CHK(PCApply(pc, Bd, Xd));
+        cpc_get_info(plan, &i1);
+        EXPECT(i1.h2d_bytes == i0.h2d_bytes && i1.d2h_bytes == i0.d2h_bytes, "PCApply on CUDA Vecs staged through the host");
+        const PetscScalar *xd;
+        CHK(VecGetArrayRead(Xd, &xd));
+        const double ed = rel_err(xd, xref);
+        CHK(VecRestoreArrayRead(Xd, &xd));
+        printf("%-28s %4d x %3d x %3d : rel error %.2e (CUDA Vecs, no staging)\n", "PCSHELL on device Vecs", n, n, n, ed);
+        EXPECT(ed < 1e-12, "PCApply on CUDA Vecs");
+        CHK(VecDestroy(&Bd));
+        CHK(VecDestroy(&Xd));
+    }
     CHK(PCDestroy(&pc));
     EXPECT(ctx->FFT_MAT == nullptr && ctx->Diag == nullptr, "destroyFFTPrec3D released the context's objects");
     CHK(FFTPrec3DContextFree(&ctx));

@@ -112,15 +112,23 @@ int cpc_set_symbol_wave(cpc_plan plan, double c0, double mu_x, double mu_y, doub
 enum cpc_option {
     CPC_OPT_Z_RECURRENCE = 1,   /* 1 (default): a transport symbol's middle pass is the cyclic recurrence along z;
                                    0: keep the fused forward-FFT / division / backward-FFT form for every symbol */
-    CPC_OPT_L2_CHUNK_BYTES = 2, /* bytes of x per z-chunk of the L2-chained x / y passes (default 32 MiB: Fx and Fy,
-                                   By and Bx run back to back on each chunk so the second pass reads it from L2);
-                                   0 = whole-array passes; < 0 = default */
+    CPC_OPT_L2_CHUNK_BYTES = 2, /* > 0: run the x / y passes z-chunk by z-chunk with this many bytes of x per chunk (Fx and
+                                   Fy, By and Bx back to back on each chunk, so the second pass reads it from L2);
+                                   0 (default) = whole-array passes, which measured faster at 512^3 */
     CPC_OPT_CHAIN_STREAMS = 3   /* 1 (default) or 2: alternate the chunks' chains between two streams */
 };
 int cpc_set_option(cpc_plan plan, int option, long long value);
 
-/* Writes the N eigenvalues currently in force (complex128) -- what the reference keeps in ctx->Diag. */
+/* Writes the N eigenvalues currently in force (complex128) -- what the reference keeps in ctx->Diag.  Single-rank
+ * plans only; cpc_build_diag_separable below serves z-slabs. */
 int cpc_get_diag(cpc_plan plan, void *diag_c128, int mem_kind);
+/* build_diag_mat_vec_3D (FftLinearSolver_3D.c:136-164) without a plan: planes [z0, z0 + nzl) of
+ *   Diag[k,j,i] = 1 + lambda_x cx_hat[i] + lambda_y cy_hat[j] + lambda_z cz_hat[k]
+ * computed on the current CUDA device from the three HOST complex128 tables and written to diag (host or device,
+ * nx*ny*nzl complex128): one launch instead of the reference's 3 N VecSetValue calls. */
+int cpc_build_diag_separable(int nx, int ny, int nz, const double *cx_hat, const double *cy_hat, const double *cz_hat,
+                             double lambda_x, double lambda_y, double lambda_z, int z0, int nzl, void *diag_c128,
+                             int mem_kind);
 
 /* ---- the hot path -----------------------------------------------------------------------------
  * cpc_apply   <- solve_3D (FftLinearSolver_3D.c:166-190): x = (1/N) F^H( F(b) ./ Lambda ).
