@@ -202,3 +202,53 @@ def test_two_rank_ny_not_divisible_takes_the_zslab_schedule():
     errs = _run((32, 15, 64), (55.5556, 0.3, 2.5), P=2, opts={"expect_dist_mode": 3, "skip_transforms": 1})
     for r, (e1, e2, e3) in errs.items():
         assert e1 < 1e-12 and e2 < 1e-12, (r, e1, e2, e3)
+
+
+# ---- the reference-named boundary on several ranks: MatCreateFFT(PETSC_COMM_WORLD, ...) of setupFFTPrec3D
+# (src/PCSHELLFft_3D.cxx:35) makes a z-slab plan, Diag / b / x are z-slabs of MPI CUDA Vecs -------------------------
+def _worker_pcshell(rank, P, port, shape, lam, b_full, want, errs):
+    import circulantpreconditioner_b200 as cpc
+    from circulantpreconditioner_b200 import glue_binding as G
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=P, device_id=torch.device("cuda", rank))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(cpc.nccl_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    nx, ny, nz = shape
+    N = nx * ny * nz
+    z0, nzl = cpc.slab_range(nz, P, rank)
+    plane = nx * ny
+    G.world_set(P, rank, idt.cpu().numpy().tobytes())
+    G.set_default_vec_cuda(True)
+    tb = torch.from_numpy(b_full[z0 * plane:(z0 + nzl) * plane].copy()).cuda()
+    tx = torch.empty_like(tb)
+    with G.PCShellFFT3D(3, nx, ny, nz, *lam) as pc:
+        vb, vx = G.Vec.from_device_tensor(tb, N=N), G.Vec.from_device_tensor(tx, N=N)
+        pc.apply(vb, vx)
+        pc.apply(vb, vx)
+        info = pc.info()
+        e = np.linalg.norm(tx.cpu().numpy() - want[z0 * plane:(z0 + nzl) * plane]) / np.linalg.norm(want)
+        errs[rank] = (float(e), int(info["nranks"]), int(info["dist_mode"]), int(info["symbol_kind"]))
+    G.world_set(1, 0)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_multi_rank_pcshell_boundary(P):
+    from oracle import circulant_oracle as O
+    if torch.cuda.device_count() < P:
+        pytest.skip(f"needs {P} GPUs")
+    shape, lam = (32, 16, 64), (55.5556, 0.3, 2.5)
+    nx, ny, nz = shape
+    rng = np.random.default_rng(21)
+    b = rng.standard_normal(nx * ny * nz) + 1j * rng.standard_normal(nx * ny * nz)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b)
+    mgr = mp.Manager()
+    errs = mgr.dict()
+    mp.spawn(_worker_pcshell, args=(P, 29800 + (os.getpid() % 2000), shape, lam, b, want, errs), nprocs=P, join=True)
+    assert len(errs) == P
+    for r, (e, nranks, mode, kind) in dict(errs).items():
+        assert e < 1e-12 and nranks == P and mode == 3 and kind == 1, (r, e, nranks, mode, kind)
