@@ -458,8 +458,6 @@ def pcshell_block(torch, b, x_ref, steps):
     out = {"api": "PCShellFFT3DAttach + PCSetUp + PCApply (reference names, src/PCSHELLFft_3D.hxx:23-25) over the C ABI",
            "steps": steps}
     with G.PCShellFFT3D(3, n, n, n, *LAMBDA) as pc:
-        out["symbol_kind_after_setup"] = pc.symbol_kind()
-        out["middle_pass_is_recurrence"] = pc.fast_path()[2] == 2
         # device-resident Vecs (VecCreateSeqCUDA-like; the glue asks VecGetArrayReadAndMemType and gets device pointers)
         vb = G.Vec.from_device_tensor(b)
         xd = torch.empty_like(b)
@@ -467,6 +465,9 @@ def pcshell_block(torch, b, x_ref, steps):
         for _ in range(3):
             pc.apply(vb, vx)
         torch.cuda.synchronize()
+        # solve_3D handed ctx->Diag to the plan on the first apply; 1 = separable tables (recognised), 2 = N-entry table
+        out["symbol_kind"] = pc.symbol_kind()
+        out["middle_pass_is_recurrence"] = pc.fast_path()[2] == 2
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):

@@ -187,7 +187,8 @@ class CirculantPlan:
         """x = P^T solve_3D(P b)  (reference applyFFT3DPrecTransport, PCSHELLFft_3D.cxx:10-24, plus back-projection)."""
         if x is None:
             x = torch.empty_like(b) if (torch is not None and isinstance(b, torch.Tensor)) else np.empty_like(b)
-        return self._call(lib().cpc_apply_projected, b, x, count=self.proj_cols)
+        # without a projection the library reports the call-order error itself (CPC_ERR_STATE)
+        return self._call(lib().cpc_apply_projected, b, x, count=self.proj_cols or (b.numel() if hasattr(b, "numel") else b.size))
 
     def apply_profiled(self, b, x):
         """Device-pointer apply that also returns the per-pass durations in ms (CUDA events on the plan stream)."""
