@@ -238,6 +238,7 @@ template <typename T> struct PlanT : PlanBase {
     void *peer_g[CPC_MAX_PEERS] = {}, *peer_z[CPC_MAX_PEERS] = {};
     int zslab_e = 0;              // points per thread for nz / P point lines (0: no tile form fits -> one thread per line)
     bool zslab_line = false;      // tuning hook: always take the thread-per-line form of the second sweep
+    bool end_trunc = true;        // end values summed over the planes that can still matter (zs_end_accum_kernel)
 
     ~PlanT() override
     {
@@ -343,6 +344,7 @@ template <typename T> struct PlanT : PlanBase {
         }
         if (const char *sg = tune("CPC_STAGGER")) stagger = atoi(sg);
         if (const char *zl = tune("CPC_ZSLAB_LINE")) zslab_line = atoi(zl) != 0;
+        if (const char *et = tune("CPC_END_TRUNC")) end_trunc = atoi(et) != 0;
         CPC_TRACE("got smem attribute");
 
         // multi-rank plans whose ny is not divisible by the ranks can only run the transpose-free z-slab schedule:
@@ -1263,7 +1265,7 @@ template <typename T> struct PlanT : PlanBase {
         const int kf[2] = { 0, 1 }, kb[2] = { 4, 5 };
         const int egrid = (int)((L + 255) / 256);
         auto end_acc = [&](int zb, int zc, cudaStream_t st) -> int {
-            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(x, L, n[0], zb, zc, zb > 0 ? 1 : 0, ebuf, za);
+            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(x, L, n[0], zb, zc, zb > 0 ? 1 : 0, end_trunc ? 1 : 0, ebuf, za);
             ++launches;
             CPC_CUDA(cudaGetLastError());
             return prof_mark(2);
@@ -1649,7 +1651,8 @@ template <typename T> struct PlanT : PlanBase {
         info->nranks = desc.nranks; info->rank = desc.rank;
         info->symbol_kind = symbol_kind;
         info->passes_per_apply = 1 + 2 * ((n[0] > 1) + (n[1] > 1));
-        info->dist_mode = desc.nranks == 1 ? 0 : (use_zslab() ? 3 : (p2p ? 2 : 1));
+        // before the transposing schedule's buffers exist (first use) report what it will try
+        info->dist_mode = desc.nranks == 1 ? 0 : (use_zslab() ? 3 : ((tbuf_tried ? p2p : want_p2p) ? 2 : 1));
         for (int a = 0; a < 3; ++a) info->fast_path[a] = cfg[a].fast ? 1 : 0;
         if (desc.nranks > 1 ? use_zslab()
                             : (symbol_kind == CPC_SYMBOL_SEPARABLE && zrec && !zrec_off && zrec_e > 0 && nc == 1))
