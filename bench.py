@@ -320,7 +320,8 @@ def run_gpu(args):
     if world == 1:
         names = ["Fx", "Fy", "Fz*Lambda^-1*Bz", "By", "Bx"]
     elif dist_mode == 3:      # no transposes: z recurrence on the local slab, one carry per (kx, ky) line exchanged
-        names = ["Fx", "Fy", "z end values + carry exchange", "Fz*Lambda^-1*Bz (z solve with carries)", "By", "Bx"]
+        names = ["Fx", "Fy", "z end values (read-only sweep)", "carry exchange", "Fz*Lambda^-1*Bz (z solve with carries)",
+                 "By", "Bx"]
     elif dist_mode == 2:      # transposes fused into the passes (NVLink peer stores), stream-ordered barriers between
         names = ["Fx", "Fy+transpose", "barrier", "Fz*Lambda^-1*Bz+transpose", "barrier", "By", "Bx"]
     else:
@@ -390,7 +391,8 @@ def run_gpu(args):
         peak, peak_src = measured_peaks()
         bytes_pass = 2 * nloc * ELEM_BYTES
         not_kernel = ("all-to-all", "barrier")
-        kern = [(nm, m) for nm, m in zip(names, pass_ms) if nm not in not_kernel and "exchange" not in nm]
+        kern = [(nm, m) for nm, m in zip(names, pass_ms)
+                if nm not in not_kernel and "exchange" not in nm and "end values" not in nm]
         dom_name, dom_ms = max(kern, key=lambda kv: kv[1])
         achieved = bytes_pass / dom_ms / 1e6
         traffic, traffic_src = None, None
@@ -407,17 +409,19 @@ def run_gpu(args):
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "alg_bytes_per_launch": bytes_pass, "middle_pass": middle, "general_symbol_form": general_form,
                     "passes": [{"name": nm, "ms": m,
-                                "GB/s": (bytes_pass / m / 1e6) if nm not in not_kernel and "exchange" not in nm and m > 0 else None}
+                                "GB/s": (bytes_pass / m / 1e6) if nm not in not_kernel and "exchange" not in nm
+                                and "end values" not in nm and m > 0 else None}
                                for nm, m in zip(names, pass_ms)],
                     "apply": {"alg_bytes": apply_alg, "achieved": apply_alg / ms_step / 1e6,
                               "frac": apply_alg / ms_step / 1e6 / peak}}
         if world > 1 and dist_mode == 3:
-            ci = names.index("z end values + carry exchange") if "z end values + carry exchange" in names else None
             roofline["carry_exchange"] = {
-                "how": "end values accumulated behind Fy per z-chunk (L2), pushed to line owners over NVLink, cycle closed "
-                       "by the owner, carry-in pushed back; two stream-ordered barriers; replaces both global transposes",
+                "how": "end values of the local lines (sweep over the planes whose weight can reach 1e-17), pushed to line "
+                       "owners over NVLink, cycle closed by the owner, carry-in pushed back; two peer-flag barriers; "
+                       "replaces both global transposes",
                 "bytes_sent_per_gpu": 2 * N_GRID * N_GRID * ELEM_BYTES * (world - 1) / world,
-                "ms": pass_ms[ci] if ci is not None else None}
+                "end_values_ms": pass_ms[names.index("z end values (read-only sweep)")],
+                "ms": pass_ms[names.index("carry exchange")]}
         if alltoall is not None:
             roofline["alltoall"] = alltoall
         line = {"metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,

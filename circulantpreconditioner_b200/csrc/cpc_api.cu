@@ -117,7 +117,7 @@ int cpc_sync(cpc_plan plan)
     CHECK_PLAN(plan);
     CPC_CUDA(cudaSetDevice(plan->impl->device));
     CPC_CUDA(cudaStreamSynchronize(plan->impl->stream));
-    return CPC_OK;
+    return plan->impl->health();
 }
 
 int cpc_set_symbol_transport(cpc_plan plan, double lx, double ly, double lz)

@@ -112,6 +112,14 @@ int dist_init(DistState &d, int nranks, int rank, const void *unique_id128, int 
 
 void dist_destroy(DistState &d)
 {
+    if (d.flag_barrier) {
+        dist_unmap_peers(d, d.peer_flags);
+        d.flag_barrier = false;
+    }
+    if (d.flags) cudaFree(d.flags);
+    if (d.timeout_flag) cudaFree(d.timeout_flag);
+    d.flags = nullptr;
+    d.timeout_flag = nullptr;
     if (d.barrier_buf) cudaFree(d.barrier_buf);
     d.barrier_buf = nullptr;
     if (d.comm && g_api.ok) g_api.CommDestroy((ncclComm_tt)d.comm);
@@ -197,9 +205,55 @@ int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes
     return CPC_OK;
 }
 
+struct FlagPeers {
+    unsigned long long *p[CPC_DIST_MAX_PEERS];
+};
+
+// Thread q: signal rank q (store this rank's epoch into slot [rank] of q's flag array, release at system scope so that
+// everything this GPU wrote before -- the preceding kernels of the stream have completed -- is visible first), then
+// wait for q's signal in the local array (acquire).  Epochs only grow, so a peer that is already one barrier ahead
+// still satisfies the wait.
+__global__ void flag_barrier_kernel(FlagPeers peers, unsigned long long *mine, int nranks, int rank,
+                                    unsigned long long epoch, int *timeout_flag)
+{
+    const int q = threadIdx.x;
+    if (q >= nranks) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peers.p[q] + rank), "l"(epoch) : "memory");
+    const long long t0 = clock64();
+    unsigned long long seen = 0;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine + q) : "memory");
+        if (seen >= epoch) break;
+        if (clock64() - t0 > 4000000000ll) { *timeout_flag = 1; break; }       // ~2 s: a peer is gone
+    }
+    __threadfence_system();
+}
+
+int dist_flag_barrier_init(DistState &d, int device, cudaStream_t stream)
+{
+    if (d.nranks == 1 || d.nranks > CPC_DIST_MAX_PEERS) return CPC_OK;
+    CPC_CUDA(cudaSetDevice(device));
+    CPC_CUDA(cudaMalloc(&d.flags, sizeof(unsigned long long) * CPC_DIST_MAX_PEERS));
+    CPC_CUDA(cudaMemset(d.flags, 0, sizeof(unsigned long long) * CPC_DIST_MAX_PEERS));
+    CPC_CUDA(cudaMalloc(&d.timeout_flag, sizeof(int)));
+    CPC_CUDA(cudaMemset(d.timeout_flag, 0, sizeof(int)));
+    int rc = dist_map_peers(d, d.flags, d.peer_flags, device, stream);
+    if (rc == CPC_OK) d.flag_barrier = true;
+    else if (rc != CPC_ERR_UNSUPPORTED) return rc;
+    return CPC_OK;
+}
+
 int dist_barrier(DistState &d, cudaStream_t stream)
 {
     if (d.nranks == 1) return CPC_OK;
+    if (d.flag_barrier) {
+        FlagPeers fp{};
+        for (int q = 0; q < d.nranks; ++q) fp.p[q] = (unsigned long long *)d.peer_flags[q];
+        flag_barrier_kernel<<<1, 32, 0, stream>>>(fp, d.flags, d.nranks, d.rank, ++d.epoch, d.timeout_flag);
+        CPC_CUDA(cudaGetLastError());
+        return CPC_OK;
+    }
     if (!d.barrier_buf) {
         CPC_CUDA(cudaMalloc(&d.barrier_buf, sizeof(float)));
         CPC_CUDA(cudaMemsetAsync(d.barrier_buf, 0, sizeof(float), stream));

@@ -41,6 +41,7 @@ struct PlanBase {
     virtual int set_symbol_first_column(const void *col, int mem_kind) = 0;
     virtual int set_symbol_wave(double c0, double mx, double my, double mz) = 0;
     virtual int set_option(int option, long long value) = 0;
+    virtual int health() { return CPC_OK; }
     virtual int get_diag(void *diag, int mem_kind) = 0;
     virtual int apply(const void *b, void *x, int mem_kind, float *pass_ms, int *npasses) = 0;
     virtual int transform(const void *in, void *out, int mem_kind, int dir) = 0;

@@ -517,6 +517,8 @@ template <typename T> struct PlanT : PlanBase {
             // (or with the tuning hook CPC_DIST_MODE=nccl) both fall back to NCCL collectives.
             const char *mode = tune("CPC_DIST_MODE");
             want_p2p = !(mode && strcmp(mode, "nccl") == 0) && desc.nranks <= CPC_MAX_PEERS;
+            const char *fb = tune("CPC_FLAG_BARRIER");
+            if (want_p2p && !(fb && atoi(fb) == 0) && (rc = dist_flag_barrier_init(dist, device, stream))) return rc;
             if (!real && nc == 1) {
                 zslab_e = zsolve_points_per_thread(nzl);
                 const long long L = (long long)n[0] * n[1];
@@ -1085,6 +1087,16 @@ template <typename T> struct PlanT : PlanBase {
         return CPC_OK;
     }
 
+    // a flag barrier that gave up waiting (dist.cu) leaves a mark: report it instead of returning wrong numbers
+    int health() override
+    {
+        if (!dist.flag_barrier || !dist.timeout_flag) return CPC_OK;
+        int t = 0;
+        CPC_CUDA(cudaMemcpy(&t, dist.timeout_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (t) { set_error("a peer rank did not reach a barrier within 2 s (multi-rank apply aborted)"); return CPC_ERR_NCCL; }
+        return CPC_OK;
+    }
+
     int set_option(int option, long long value) override
     {
         switch (option) {
@@ -1254,7 +1266,7 @@ template <typename T> struct PlanT : PlanBase {
 
     // Multi-rank apply for a transport symbol: no transposes.  [Fx, Fy, end-value accumulation] z-chunk by z-chunk
     // (L2-chained), the carry exchange (zsolve.cuh), the z solve on the local slab from the exchanged carry-in,
-    // [By, Bx] z-chunk by z-chunk.  Pass kinds: Fx, Fy, carry (end values + exchange), z solve, By, Bx.
+    // [By, Bx] z-chunk by z-chunk.  Pass kinds: Fx, Fy, end values, carry exchange, z solve, By, Bx.
     int apply_device_zslab(const C *b, C *x, float *pass_ms, int *npasses)
     {
         int rc;
@@ -1262,7 +1274,7 @@ template <typename T> struct PlanT : PlanBase {
         const long long L = (long long)n[0] * n[1];
         ZSolveArgs za = zsolve_args();
         za.nline = nzl;
-        const int kf[2] = { 0, 1 }, kb[2] = { 4, 5 };
+        const int kf[2] = { 0, 1 }, kb[2] = { 5, 6 };
         const int egrid = (int)((L + 255) / 256);
         auto end_acc = [&](int zb, int zc, cudaStream_t st) -> int {
             zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(x, L, n[0], zb, zc, zb > 0 ? 1 : 0, end_trunc ? 1 : 0, ebuf, za);
@@ -1301,7 +1313,7 @@ template <typename T> struct PlanT : PlanBase {
             ++launches;
             CPC_CUDA(cudaGetLastError());
         }
-        if ((rc = prof_mark(2))) return rc;
+        if ((rc = prof_mark(3))) return rc;
         if (zslab_e > 0 && !zslab_line) {
             long long off = 0;
             const PassGeom g = make_geom(2, 128 / (int)sizeof(C), 0, nzl, 0, &off);
@@ -1311,9 +1323,9 @@ template <typename T> struct PlanT : PlanBase {
         }
         ++launches;
         CPC_CUDA(cudaGetLastError());
-        if ((rc = prof_mark(3))) return rc;
+        if ((rc = prof_mark(4))) return rc;
         if ((rc = run_xy(false, x, x, kb, no_after))) return rc;
-        return prof_end(pass_ms, npasses, 6);
+        return prof_end(pass_ms, npasses, 7);
     }
 
     int apply_device_dist(const C *b, C *x, float *pass_ms, int *npasses)
