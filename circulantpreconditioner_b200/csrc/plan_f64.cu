@@ -47,16 +47,6 @@ __global__ void diag_check_separable_kernel(const double2 *__restrict__ diag, co
 }
 
 __global__ void __launch_bounds__(256)
-zs_carry_push_kernel(const double2 *__restrict__ e, long long lines, long long lsub, int rank, ZCarryPeers gpeer)
-{
-    for (long long line = blockIdx.x * (long long)blockDim.x + threadIdx.x; line < lines;
-         line += (long long)gridDim.x * blockDim.x) {
-        const int q = (int)(line / lsub);
-        gpeer.p[q][(long long)rank * lsub + (line - (long long)q * lsub)] = e[line];
-    }
-}
-
-__global__ void __launch_bounds__(256)
 zs_carry_owner_kernel(const double2 *__restrict__ gbuf, long long gstride, long long line0, long long count, int nx,
                       int nzl, int nranks, int rank, int self_only, ZCarryPeers zpeer, const ZSolveArgs a)
 {

@@ -1276,8 +1276,13 @@ template <typename T> struct PlanT : PlanBase {
         za.nline = nzl;
         const int kf[2] = { 0, 1 }, kb[2] = { 5, 6 };
         const int egrid = (int)((L + 255) / 256);
+        ZCarryPeers gp{}, zp{};
+        for (int q = 0; q < desc.nranks; ++q) { gp.p[q] = (double2 *)peer_g[q]; zp.p[q] = (double2 *)peer_z[q]; }
+        // the end values of the last chunk go straight to the ranks that own the lines (peer stores) when peers are mapped
         auto end_acc = [&](int zb, int zc, cudaStream_t st) -> int {
-            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(x, L, n[0], zb, zc, zb > 0 ? 1 : 0, end_trunc ? 1 : 0, ebuf, za);
+            const bool last = zb + zc >= nzl;
+            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(x, L, n[0], zb, zc, zb > 0 ? 1 : 0, end_trunc ? 1 : 0, ebuf, za,
+                                                          (carry_p2p && last) ? desc.rank : -1, lsub, gp);
             ++launches;
             CPC_CUDA(cudaGetLastError());
             return prof_mark(2);
@@ -1290,11 +1295,6 @@ template <typename T> struct PlanT : PlanBase {
         if (rc) return rc;
         const int cgrid = 148 * 8;
         if (carry_p2p) {
-            ZCarryPeers gp{}, zp{};
-            for (int q = 0; q < desc.nranks; ++q) { gp.p[q] = (double2 *)peer_g[q]; zp.p[q] = (double2 *)peer_z[q]; }
-            zs_carry_push_kernel<<<cgrid, 256, 0, stream>>>(ebuf, L, lsub, desc.rank, gp);
-            ++launches;
-            CPC_CUDA(cudaGetLastError());
             if ((rc = dist_barrier(dist, stream))) return rc;            // every rank's end values have landed
             const long long line0 = lsub * desc.rank;
             const long long cnt = line0 >= L ? 0 : (L - line0 < lsub ? L - line0 : lsub);
@@ -1307,9 +1307,9 @@ template <typename T> struct PlanT : PlanBase {
             if ((rc = dist_barrier(dist, stream))) return rc;            // every line's carry-in has landed
         } else {
             if ((rc = dist_allgather(dist, ebuf, gbuf, sizeof(double2) * (size_t)L, stream))) return rc;
-            ZCarryPeers zp{};
-            zp.p[0] = zinbuf;
-            zs_carry_owner_kernel<<<cgrid, 256, 0, stream>>>(gbuf, L, 0, L, n[0], nzl, desc.nranks, desc.rank, 1, zp, za);
+            ZCarryPeers zl{};
+            zl.p[0] = zinbuf;
+            zs_carry_owner_kernel<<<cgrid, 256, 0, stream>>>(gbuf, L, 0, L, n[0], nzl, desc.nranks, desc.rank, 1, zl, za);
             ++launches;
             CPC_CUDA(cudaGetLastError());
         }

@@ -22,10 +22,10 @@
 //   3. x_k = r (y_k + c^(k - sE + 1) carry) / (nx ny), stored straight to HBM (or pushed to a peer, GEN builds).
 //
 // z-slab plans (one process per GPU) need NO transpose for this pass: a recurrence only hands a carry from one slab to
-// the next.  The value at the end of every local line from a zero carry-in is accumulated plane by plane
-// (zs_end_accum_kernel; it rides behind the forward y pass of the same z-chunk while that chunk is still in L2), the
+// the next.  The value at the end of every local line from a zero carry-in is accumulated plane by plane over the
+// planes whose weight can still matter (zs_end_accum_kernel, a read-only sweep right behind the forward y pass), the
 // carries are exchanged -- each rank owns 1/P of the (kx, ky) lines, gathers their P end values through peer stores,
-// closes the cycle over the ranks and pushes one carry-in per line back to every rank (zs_carry_*_kernel; 2 x 3.5 MB
+// closes the cycle over the ranks and pushes one carry-in per line back to every rank (zs_carry_owner_kernel; 2 x 3.5 MB
 // over NVLink per rank at 512^2 and 8 ranks instead of two 235 MB all-to-alls) -- and the second sweep (ZS_DIST)
 // solves the local lines from that carry-in.
 //
@@ -229,15 +229,21 @@ zsolve_kernel(const cplx_t<T> *in, cplx_t<T> *out, const PassGeom g, const ZSolv
 // ---------------------------------------------------------------------------------------------------------------
 // z-slab plans: end values and the carry exchange
 // ---------------------------------------------------------------------------------------------------------------
+struct ZCarryPeers {
+    double2 *p[CPC_MAX_PEERS];
+};
+
 // e[line] = c^zc e[line] (if carry_in) + sum_{k < zc} c^(zc-1-k) v[zb + k][line]: the value at the end of planes
 // [zb, zb + zc) of every local line, continuing the planes before zb.  One thread per (kx, ky) line, coalesced over kx.
 // With `trunc` the sum starts at the first plane whose weight |c|^(zc-1-k) can still reach 1e-17 of the last plane's:
 // earlier planes (and the carry-in) are below the rounding of the sum itself.  At lambda = 55.56 seven lines out of
 // eight have |c| < 0.54 and need fewer than 64 planes -- the planes the forward y pass wrote last, still in L2.
+// With push_rank >= 0 (the last chunk, peers mapped) the result is stored straight into the gather buffer of the
+// rank q = line / lsub that owns the line, G_q[push_rank][line - q lsub], over NVLink.
 template <typename T>
 __global__ void __launch_bounds__(256)
 zs_end_accum_kernel(const cplx_t<T> *__restrict__ x, long long lines, int nx, int zb, int zc, int carry_in, int trunc,
-                    double2 *__restrict__ e, const ZSolveArgs a)
+                    double2 *__restrict__ e, const ZSolveArgs a, int push_rank, long long lsub, ZCarryPeers gpeer)
 {
     const long long line = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (line >= lines) return;
@@ -268,7 +274,12 @@ zs_end_accum_kernel(const cplx_t<T> *__restrict__ x, long long lines, int nx, in
         acc.x = fma(c.x, t.x, fma(-c.y, t.y, v.x));
         acc.y = fma(c.x, t.y, fma(c.y, t.x, v.y));
     }
-    e[line] = acc;
+    if (push_rank >= 0) {
+        const int q = (int)(line / lsub);
+        gpeer.p[q][(long long)push_rank * lsub + (line - (long long)q * lsub)] = acc;
+    } else {
+        e[line] = acc;
+    }
 }
 
 // Second sweep for slabs whose plane count fits no tile form of zsolve_kernel (nz / P = 8 planes at 8 ranks of a 64^3
@@ -308,15 +319,6 @@ zs_dist_line_kernel(cplx_t<T> *x, long long lines, int nx, int nzl, const ZSolve
         p[(long long)k * lines] = from_d2<CS>(cmul(acc, rs));
     }
 }
-
-struct ZCarryPeers {
-    double2 *p[CPC_MAX_PEERS];
-};
-
-// Rank `rank` hands the end values of the lines owned by rank q (lines [q lsub, (q+1) lsub)) to q: peer store into
-// q's gather buffer G_q[rank][line - q lsub].
-__global__ void __launch_bounds__(256)
-zs_carry_push_kernel(const double2 *__restrict__ e, long long lines, long long lsub, int rank, ZCarryPeers gpeer);
 
 // Owner of lines [line0, line0 + count): from the P end values of each line, the carry into every rank's first plane
 //   Zin_r = sum_{m < P} cL^m e_{r-1-m} / (1 - cL^P),  cL = c^(nz / P)       (the cycle closed over the ranks),
