@@ -1,0 +1,137 @@
+"""BASELINE config 5: TransportEquation on the reference's cube meshes with the structured circulant approximation as
+GMRES preconditioner -- iteration-count parity between the CUDA preconditioner (cpc_apply_projected: P^T solve_3D(P b),
+reference src/PCSHELLFft_3D.cxx:10-24) and the CPU-oracle preconditioner.
+
+Meshes: tests/golden/mesh_*.npz, generated from the reference's Gmsh text files by tests/golden/make_mesh_fixtures.py
+(3DKershawTetra1 = the Kershaw family tetrahedrised, mesh_hexa_3 / mesh_hexa_4 = uniform hexahedra).  The polyhedral
+meshes/3DKershaw/*.med are HDF5 and cannot be read in this image.
+"""
+import numpy as np
+import pytest
+import torch
+
+from circulantpreconditioner_b200 import krylov as K
+from circulantpreconditioner_b200 import meshes as MS
+from oracle import circulant_oracle as O
+
+A_VEL = (1.0, 0.0, 0.0)           # tests/TransportEquation_SphericalExplosion_impl_mpi.cxx:258-259
+
+
+def _setup(name, quirk=False):
+    mesh = MS.load_fixture(name)
+    dt = MS.reference_dt(mesh, A_VEL)
+    A = MS.transport_matrix(mesh, A_VEL, dt, ref_sign_quirk=quirk)
+    n, lam = MS.prec_context(mesh, A_VEL, dt)
+    P = MS.cell_centre_projection(mesh, n)
+    b = MS.spherical_step(mesh).astype(np.complex128)
+    return mesh, dt, A, n, lam, P, b
+
+
+def _oracle_pc(P, n, lam):
+    def M(v):
+        y = O.FftTransportSolver(n, n, n, *lam, P @ v.cpu().numpy())
+        return torch.from_numpy(P.T @ y).to(v.device)
+    return M
+
+
+def test_fixtures_are_consistent():
+    for name, ncell in (("hexa_3", 512), ("hexa_4", 4096), ("kershaw_tetra1", 11072)):
+        m = MS.load_fixture(name)
+        assert len(m["volume"]) == ncell and abs(m["volume"].sum() - 1.0) < 1e-12
+        # every interior face's area vector points from its first to its second cell
+        d = m["centre"][m["face_cells"][:, 1]] - m["centre"][m["face_cells"][:, 0]]
+        assert np.all(np.einsum("ij,ij->i", d, m["face_area"]) > 0)
+        # closed cells: interior + border areas; the divergence of a constant field vanishes over interior cells
+        assert np.all(m["surface"] > 0)
+
+
+def test_hexa_mesh_operator_equals_the_structured_restatement():
+    """On the uniform hexahedra the unstructured assembly must be the Cartesian upwind operator of krylov.py (a cell
+    permutation apart), and getFFTPrec3DContext's n is the mesh's own resolution, so P is a permutation."""
+    mesh, dt, A, n, lam, P, b = _setup("hexa_3")
+    assert n == 8 and abs(lam[0] - dt * 8) < 1e-12 and lam[1] == lam[2] == 0.0
+    assert P.shape == (512, 512) and P.nnz == 512 and np.allclose(P.data, 1.0)
+    perm = P.indices                        # Cartesian cell k holds mesh cell perm[k]
+    u = np.random.default_rng(0).standard_normal(512)
+    want = K.transport_operator((8, 8, 8), lam)(torch.from_numpy(u[perm]).to(torch.complex128)).numpy().real
+    assert np.allclose((A @ u)[perm], want, rtol=1e-12, atol=1e-12)
+
+
+def _kershaw_two_level(device):
+    """The Kershaw tetrahedra with a preconditioner that can converge: 8^3 Cartesian cells (one empty), P with
+    orthonormal rows, identity on the complement (meshes.two_level_pc)."""
+    mesh = MS.load_fixture("kershaw_tetra1")
+    dt = MS.reference_dt(mesh, A_VEL)
+    A = MS.transport_matrix(mesh, A_VEL, dt)
+    n = 8
+    lo, hi = mesh["bbox"]
+    lam = tuple(A_VEL[d] * dt * n / float(hi[d] - lo[d]) for d in range(3))
+    P = MS.cell_centre_projection(mesh, n, orthonormal=True)
+    PtP = MS.torch_operator((P.T @ P).tocsr(), device)
+    b = MS.spherical_step(mesh).astype(np.complex128)
+    return A, n, lam, P, PtP, b
+
+
+def test_oracle_preconditioned_gmres_cpu():
+    # uniform hexahedra: the circulant model is exact up to the border faces -> 2 iterations instead of 8
+    mesh, dt, A, n, lam, P, b = _setup("hexa_3")
+    Aop = MS.torch_operator(A, "cpu")
+    bt = torch.from_numpy(b)
+    assert K.gmres(Aop, bt)[1] == 8
+    x, its, reason, _ = K.gmres(Aop, bt, _oracle_pc(P, n, lam))
+    assert its == 2 and reason in (2, 3)
+    assert (torch.linalg.vector_norm(Aop(x) - bt) / torch.linalg.vector_norm(bt)).item() < 1e-10
+    # Kershaw tetrahedra: the reference's form P^T solve(P .) with n = floor(cbrt(11072)) = 22 leaves 4719 of the 10648
+    # Cartesian cells empty and cannot converge; the completed two-level form does
+    mesh, dt, A, n, lam, P, b = _setup("kershaw_tetra1")
+    assert n == 22 and int((np.asarray(P.sum(axis=1)).ravel() == 0).sum()) == 4719
+    A, n, lam, P, PtP, b = _kershaw_two_level("cpu")
+    Aop = MS.torch_operator(A, "cpu")
+    bt = torch.from_numpy(b)
+    x, its, reason, _ = K.gmres(Aop, bt, MS.two_level_pc(PtP, _oracle_pc(P, n, lam)))
+    assert reason in (2, 3) and its < 400
+    assert (torch.linalg.vector_norm(Aop(x) - bt) / torch.linalg.vector_norm(bt)).item() < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,quirk", [("hexa_3", False), ("hexa_3", True), ("hexa_4", False)])
+def test_config5_iteration_parity_gpu_vs_oracle(name, quirk):
+    import circulantpreconditioner_b200 as cpc
+    mesh, dt, A, n, lam, P, b = _setup(name, quirk)
+    # CPU: oracle preconditioner
+    x_c, its_c, reason_c, hist_c = K.gmres(MS.torch_operator(A, "cpu"), torch.from_numpy(b), _oracle_pc(P, n, lam))
+    # GPU: the projection and the five passes in one cpc_apply_projected call
+    with cpc.CirculantPlan(n, n, n) as plan:
+        plan.set_symbol_transport(*lam)
+        plan.set_projection(P.shape[1], P.indptr, P.indices, P.data)
+        Aop = MS.torch_operator(A, "cuda")
+        bt = torch.from_numpy(b).cuda()
+        x_g, its_g, reason_g, hist_g = K.gmres(Aop, bt, lambda v: plan.apply_projected(v.contiguous()))
+    assert its_g == its_c and reason_g == reason_c, (its_g, its_c)
+    assert np.allclose(hist_g, hist_c, rtol=1e-6, atol=1e-9)
+    assert torch.allclose(x_g.cpu(), x_c, rtol=1e-6, atol=1e-6 * float(np.abs(b).max()))
+
+
+@pytest.mark.gpu
+def test_config5_kershaw_tetrahedra_gpu_vs_oracle():
+    """The Kershaw family: (i) the reference's form P^T solve_3D(P b) with getFFTPrec3DContext's n = 22 -- one apply
+    against the oracle; (ii) GMRES(30) with the completed two-level preconditioner: identical iteration counts."""
+    import circulantpreconditioner_b200 as cpc
+    mesh, dt, A22, n, lam, P, b = _setup("kershaw_tetra1")
+    with cpc.CirculantPlan(n, n, n) as plan:
+        plan.set_symbol_transport(*lam)
+        plan.set_projection(P.shape[1], P.indptr, P.indices, P.data)
+        one = plan.apply_projected(torch.from_numpy(b).cuda()).cpu().numpy()
+    want = P.T @ O.FftTransportSolver(n, n, n, *lam, P @ b)
+    assert np.linalg.norm(one - want) / np.linalg.norm(want) < 1e-12
+    A, n, lam, P, PtP_c, b = _kershaw_two_level("cpu")
+    x_c, its_c, reason_c, hist_c = K.gmres(MS.torch_operator(A, "cpu"), torch.from_numpy(b),
+                                           MS.two_level_pc(PtP_c, _oracle_pc(P, n, lam)))
+    PtP_g = MS.torch_operator((P.T @ P).tocsr(), "cuda")
+    with cpc.CirculantPlan(n, n, n) as plan:
+        plan.set_symbol_transport(*lam)
+        plan.set_projection(P.shape[1], P.indptr, P.indices, P.data)
+        M = MS.two_level_pc(PtP_g, lambda v: plan.apply_projected(v.contiguous()))
+        x_g, its_g, reason_g, hist_g = K.gmres(MS.torch_operator(A, "cuda"), torch.from_numpy(b).cuda(), M)
+    assert reason_c in (2, 3) and its_g == its_c and reason_g == reason_c, (its_g, its_c, reason_g, reason_c)
+    assert np.allclose(hist_g, hist_c, rtol=1e-5, atol=1e-8)
