@@ -381,6 +381,12 @@ def run_gpu(args):
         except Exception as exc:      # the glue is optional for the headline; say why it is missing
             pcshell = {"unavailable": f"{type(exc).__name__}: {exc}"}
 
+    ksp = None
+    if not args.no_ksp:
+        del x_ref, b, x
+        torch.cuda.empty_cache()
+        ksp = ksp_block(torch, cpc, world, rank, new_nccl_id)
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         # N = 1: the oracle applies the very b of the timed run and the GPU result is compared with it
@@ -441,6 +447,8 @@ def run_gpu(args):
                 "gpu_launches": launches, "clocks": clocks}
         if pcshell is not None:
             line["pcshell"] = pcshell
+        if ksp is not None:
+            line["ksp"] = ksp
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -451,6 +459,65 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Full Krylov solves (BASELINE configs 2 and 3) on the same ranks: PETSc-free GMRES(30) harness (krylov.py: the
+# reference's KSP settings, tests/TransportEquation_SphericalExplosion_impl_mpi.cxx:120-126), z-slab operators with a
+# one-plane halo, global dots through torch.distributed, the preconditioner = the multi-rank plan
+# ---------------------------------------------------------------------------------------------------------------
+def ksp_block(torch, cpc, world, rank, new_nccl_id):
+    from circulantpreconditioner_b200 import krylov as K
+    slab = K.Slab()
+    out = {"harness": "krylov.gmres: GMRES(30), left PC, rtol = atol = 1e-5, maxits 1000; z-slabs over the ranks"}
+
+    def solve(A, b, plan):
+        M = lambda v: plan.apply(v.contiguous())
+        K.gmres(A, b, M, maxits=2, slab=slab)                    # warm-up (plan buffers, NCCL)
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        x, its, reason, hist = K.gmres(A, b, M, slab=slab)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        r = A(x) - b
+        num = slab.sum(torch.sum(torch.abs(r) ** 2)).item()
+        den = slab.sum(torch.sum(torch.abs(b) ** 2)).item()
+        return {"its": its, "reason": reason, "solve_s": dt, "true_rel_residual": (num / den) ** 0.5}
+
+    # config 2: transport 128^3, a = (1, 0, 0): lambda = (55.5556, 0, 0)
+    shape, lam = (128,) * 3, (55.5556, 0.0, 0.0)
+    b = K.spherical_step(shape, 650.0, 600.0, device="cuda", slab=slab).to(torch.complex128)
+    with cpc.CirculantPlan(*shape, nranks=world, rank=rank, nccl_id=new_nccl_id()) as plan:
+        plan.set_symbol_transport(*lam)
+        for quirk in (False, True):
+            A = K.transport_operator(shape, lam, ref_sign_quirk=quirk, slab=slab)
+            out[f"config2_transport_128cube_{'ref_sign_quirk' if quirk else 'consistent_sign'}"] = solve(A, b, plan)
+    # config 3: wave system 256^3 x 4 unknowns, wall boundaries, c0 = 700, dt / dx = 55.5556 / 700
+    n = 256
+    shape, c0, mu = (n,) * 3, 700.0, (0.0793651,) * 3
+    p0 = K.spherical_step(shape, 155e5, 70e5, device="cuda", slab=slab)
+    b = torch.zeros(p0.numel(), 4, dtype=torch.complex128, device="cuda")
+    b[:, 0] = p0
+    b = b.reshape(-1)
+    with cpc.CirculantPlan(*shape, ncomp=4, nranks=world, rank=rank, nccl_id=new_nccl_id()) as plan:
+        plan.set_symbol_wave(c0, *mu)
+        xw = torch.empty_like(b)
+        for _ in range(3):
+            plan.apply(b, xw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            plan.apply(b, xw)
+        e1.record()
+        torch.cuda.synchronize()
+        out["wave_block_apply_256cube"] = {"applies_per_s": 1e4 / e0.elapsed_time(e1), "ms": e0.elapsed_time(e1) / 10,
+                                           "dist_mode": plan.info()["dist_mode"]}
+        del xw
+        out["config3_wave_256cube_wall"] = solve(K.wave_operator(shape, c0, mu, slab=slab), b, plan)
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -510,6 +577,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pcshell", action="store_true")
+    ap.add_argument("--no-ksp", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 20:      # defaults sized for the GPU arm; keep the CPU arm to minutes

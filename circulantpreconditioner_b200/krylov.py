@@ -16,9 +16,45 @@ import torch
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# z-slab distribution (one process per GPU, torch.distributed): rank r holds planes [r nz/P, (r+1) nz/P), the layout of
+# the multi-rank plans.  The operators need one halo plane from each z neighbour, GMRES needs global dots and norms.
+# ---------------------------------------------------------------------------------------------------------------
+class Slab:
+    """Halo exchange and reductions over the z-slabs.  `Slab(None)` (or world size 1) is the single-process case."""
+
+    def __init__(self, group=None, enabled=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.on = dist.is_available() and dist.is_initialized() if enabled is None else enabled
+        self.world = dist.get_world_size(group) if self.on else 1
+        self.rank = dist.get_rank(group) if self.on else 0
+        self.group = group
+        self.on = self.on and self.world > 1
+
+    def sum(self, t):
+        """In-place global sum of a tensor of partial sums (identical on every rank afterwards)."""
+        if self.on:
+            if t.is_complex():
+                self.dist.all_reduce(torch.view_as_real(t), group=self.group)
+            else:
+                self.dist.all_reduce(t, group=self.group)
+        return t
+
+    def halo(self, U):
+        """(plane below this slab's first plane, plane above its last plane) from the z neighbours, cyclic in rank;
+        U is [nzl, ...].  Single process: the array's own last / first plane."""
+        if not self.on:
+            return U[-1], U[0]
+        edges = torch.stack([U[0], U[-1]]).contiguous()
+        allv = [torch.empty_like(edges) for _ in range(self.world)]
+        self.dist.all_gather(allv, edges, group=self.group)
+        return allv[(self.rank - 1) % self.world][1], allv[(self.rank + 1) % self.world][0]
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # Operators
 # ---------------------------------------------------------------------------------------------------------------
-def transport_operator(shape, lam, periodic=False, ref_sign_quirk=False):
+def transport_operator(shape, lam, periodic=False, ref_sign_quirk=False, slab=None):
     """A = I + upwind divergence on an nx x ny x nz Cartesian grid, velocity components >= 0.
 
     Interior face with outward normal n: un = n.a; un > 0 adds lambda to the diagonal, un < 0 adds -lambda*un/|un| ...
@@ -29,34 +65,49 @@ def transport_operator(shape, lam, periodic=False, ref_sign_quirk=False):
     """
     nx, ny, nz = shape
     sgn = +1.0 if ref_sign_quirk else -1.0
+    slab = slab or Slab(enabled=False)
+    nzl = nz // slab.world                                  # u is this rank's z-slab (all of it for one process)
+    first, last = slab.rank == 0, slab.rank == slab.world - 1
 
     def apply(u):
-        U = u.reshape(nz, ny, nx)
+        U = u.reshape(nzl, ny, nx)
         out = U.clone()
         for ax, n, l in ((2, nx, lam[0]), (1, ny, lam[1]), (0, nz, lam[2])):
             if n == 1 or l == 0:
                 continue
-            if periodic:
-                out = out + l * U + sgn * l * torch.roll(U, 1, dims=ax)
-                continue
-            diag = torch.ones(n, dtype=U.real.dtype, device=U.device)
-            diag[-1] = 0.0                                  # last cell: its +d face is a border -> nothing
-            shp = [1, 1, 1]
-            shp[ax] = n
-            out = out + l * U * diag.reshape(shp)
-            sh = torch.zeros_like(U)
+            nloc = nzl if ax == 0 else n
+            below = slab.halo(U)[0] if (ax == 0 and slab.on) else None      # plane z0 - 1 from the rank below
+            sh = torch.zeros_like(U)                          # sh[i] = U[i - 1]
             idx_dst = [slice(None)] * 3
             idx_src = [slice(None)] * 3
             idx_dst[ax] = slice(1, None)
             idx_src[ax] = slice(0, -1)
-            sh[tuple(idx_dst)] = U[tuple(idx_src)]           # first cell: its -d face is a border -> nothing
+            sh[tuple(idx_dst)] = U[tuple(idx_src)]
+            if periodic:
+                if below is not None:
+                    sh[0] = below
+                else:
+                    idx0 = [slice(None)] * 3
+                    idxl = [slice(None)] * 3
+                    idx0[ax], idxl[ax] = 0, -1
+                    sh[tuple(idx0)] = U[tuple(idxl)]
+                out = out + l * U + sgn * l * sh
+                continue
+            diag = torch.ones(nloc, dtype=U.real.dtype, device=U.device)
+            if ax != 0 or last:
+                diag[-1] = 0.0                              # last cell: its +d face is a border -> nothing
+            shp = [1, 1, 1]
+            shp[ax] = nloc
+            out = out + l * U * diag.reshape(shp)
+            if below is not None and not first:
+                sh[0] = below                               # (global first cell: its -d face is a border -> nothing)
             out = out + sgn * l * sh
         return out.reshape(-1)
 
     return apply
 
 
-def wave_operator(shape, c0, mu, periodic=False):
+def wave_operator(shape, c0, mu, periodic=False, slab=None):
     """A = I + divMat for the wave system, unknowns [p, q_x, q_y, q_z] per cell (interleaved).
 
     Am(n) = (A(n) - |A|(n))/2 * mu_d  (jacobianMatrices, src/WaveSystem.cxx:92-107); interior faces add Am to (j, nb)
@@ -64,10 +115,14 @@ def wave_operator(shape, c0, mu, periodic=False):
     interior faces (:159-167).
     """
     nx, ny, nz = shape
+    slab = slab or Slab(enabled=False)
+    nzl = nz // slab.world
+    first, last = slab.rank == 0, slab.rank == slab.world - 1
 
     def apply(u):
-        U = u.reshape(nz, ny, nx, 4)
+        U = u.reshape(nzl, ny, nx, 4)
         out = U.clone()
+        halo = slab.halo(U) if (slab.on and nz > 1) else None
         for d, (ax, n) in enumerate(((2, nx), (1, ny), (0, nz))):
             if n == 1:
                 continue
@@ -79,15 +134,18 @@ def wave_operator(shape, c0, mu, periodic=False):
                 Am[d + 1, 0] = 0.5 * s * m
                 Am[d + 1, d + 1] = -0.5 * c0 * m
                 nb = torch.roll(U, int(-s), dims=ax)        # neighbour across the face with outward normal s*e_d
+                if ax == 0 and halo is not None:            # the neighbour of the slab's edge plane lives on the next rank
+                    nb = nb.clone()
+                    nb[-1 if s > 0 else 0] = halo[1] if s > 0 else halo[0]
                 contrib = (nb - U) @ Am.T
-                if not periodic:
+                if not periodic and (ax != 0 or (last if s > 0 else first)):
                     # border cells: replace the interior-face term by the wall term -Am (2 v v^T) U
                     W = torch.zeros(4, 4, dtype=U.dtype, device=U.device)
                     W[0, d + 1] = -c0 * c0 * s * m
                     W[d + 1, d + 1] = c0 * m
                     wall = U @ W.T
                     sel = [slice(None)] * 4
-                    sel[ax] = (n - 1) if s > 0 else 0
+                    sel[ax] = -1 if s > 0 else 0
                     contrib[tuple(sel)] = wall[tuple(sel)]
                 out = out + contrib
         return out.reshape(-1)
@@ -98,7 +156,7 @@ def wave_operator(shape, c0, mu, periodic=False):
 # ---------------------------------------------------------------------------------------------------------------
 # GMRES(m), left preconditioned, PETSc's default test on the preconditioned residual
 # ---------------------------------------------------------------------------------------------------------------
-def gmres(A, b, M=None, rtol=1e-5, atol=1e-5, maxits=1000, restart=30):
+def gmres(A, b, M=None, rtol=1e-5, atol=1e-5, maxits=1000, restart=30, slab=None):
     """Solve A x = b from x0 = 0.  Returns (x, iterations, reason, residual_history).
 
     reason follows KSPConvergedReason: 2 = rtol, 3 = atol, -3 = its.  The test is PETSc's KSPConvergedDefault for a
@@ -106,9 +164,14 @@ def gmres(A, b, M=None, rtol=1e-5, atol=1e-5, maxits=1000, restart=30):
     """
     ident = M is None
     M = (lambda v: v) if ident else M
+    slab = slab or Slab(enabled=False)
+
+    def norm(v):                                             # global 2-norm (b, x, the Krylov vectors are z-slabs)
+        return math.sqrt(slab.sum(torch.sum(v.real * v.real + v.imag * v.imag if v.is_complex() else v * v)).item())
+
     x = torch.zeros_like(b)
     r = M(b)
-    beta = torch.linalg.vector_norm(r).item()
+    beta = norm(r)
     rnorm0 = beta
     hist = [beta]
     its = 0
@@ -131,12 +194,12 @@ def gmres(A, b, M=None, rtol=1e-5, atol=1e-5, maxits=1000, restart=30):
             # classical Gram-Schmidt with one refinement pass (PETSc: KSPGMRESClassicalGramSchmidtOrthogonalization,
             # refine "if needed"; always refining is the conservative choice and keeps iteration counts stable)
             Vk = torch.stack(V, dim=0)
-            h = torch.mv(Vk.conj(), w)
+            h = slab.sum(torch.mv(Vk.conj(), w))
             w = w - torch.mv(Vk.T, h)
-            h2 = torch.mv(Vk.conj(), w)
+            h2 = slab.sum(torch.mv(Vk.conj(), w))
             w = w - torch.mv(Vk.T, h2)
             h = (h + h2).cpu()
-            hn = torch.linalg.vector_norm(w).item()
+            hn = norm(w)
             H[: k + 1, k] = h
             H[k + 1, k] = hn
             for i in range(k):                               # previous rotations
@@ -172,19 +235,24 @@ def gmres(A, b, M=None, rtol=1e-5, atol=1e-5, maxits=1000, restart=30):
         if reason != 0:
             return x, its, reason, hist
         r = M(b - A(x))
-        beta = torch.linalg.vector_norm(r).item()
+        beta = norm(r)
         if beta <= ttol:
             return x, its, 2 if beta <= rtol * rnorm0 else 3, hist
 
 
-def spherical_step(shape, inside, outside, rmax=0.3, lo=-0.5, hi=0.5, device="cpu", dtype=torch.float64):
-    """Cell-centred spherical step initial condition (src/TransportEquation.cxx:25-73, src/WaveSystem.cxx:26-76)."""
+def spherical_step(shape, inside, outside, rmax=0.3, lo=-0.5, hi=0.5, device="cpu", dtype=torch.float64, slab=None):
+    """Cell-centred spherical step initial condition (src/TransportEquation.cxx:25-73, src/WaveSystem.cxx:26-76);
+    with a slab, this rank's z planes only."""
     nx, ny, nz = shape
 
     def centres(n):
         d = (hi - lo) / n
         return lo + d * (torch.arange(n, dtype=torch.float64, device=device) + 0.5)
-    z, y, x = torch.meshgrid(centres(nz), centres(ny), centres(nx), indexing="ij")
+    zc = centres(nz)
+    if slab is not None and slab.world > 1:
+        nzl = nz // slab.world
+        zc = zc[slab.rank * nzl:(slab.rank + 1) * nzl]
+    z, y, x = torch.meshgrid(zc, centres(ny), centres(nx), indexing="ij")
     c = 0.5 * (lo + hi)
     r = torch.sqrt((x - c) ** 2 + (y - c) ** 2 + (z - c) ** 2)
     return torch.where(r < rmax, torch.tensor(inside, dtype=dtype, device=device),

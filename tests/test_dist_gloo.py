@@ -163,3 +163,69 @@ def test_zslab_recurrence_schedule(shape, P):
     port = 31500 + (os.getpid() % 2000)
     mp.spawn(_worker_zslab, args=(P, port, shape, lam, b, ret), nprocs=P, join=True)
     assert rel_l2(ret["x"], want) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Distributed GMRES harness (circulantpreconditioner_b200/krylov.py with a Slab): world_size-2 gloo ranks must give
+# the single-process operators, residual histories and iteration counts.
+# ---------------------------------------------------------------------------------------------------------------
+def _worker_krylov(rank, P, port, ret):
+    from circulantpreconditioner_b200 import krylov as K
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=P)
+    slab = K.Slab()
+    out = {}
+    for name, shape, lam, periodic, quirk in (("t", (6, 5, 8), (3.0, 0.5, 1.5), False, False),
+                                              ("tq", (6, 5, 8), (3.0, 0.5, 1.5), False, True),
+                                              ("tp", (6, 5, 8), (3.0, 0.5, 1.5), True, False)):
+        nx, ny, nz = shape
+        nzl = nz // P
+        b_full = K.spherical_step(shape, 650.0, 600.0).to(torch.complex128)
+        b = K.spherical_step(shape, 650.0, 600.0, slab=slab).to(torch.complex128)
+        assert torch.equal(b, b_full.reshape(nz, -1)[rank * nzl:(rank + 1) * nzl].reshape(-1))
+        A = K.transport_operator(shape, lam, periodic=periodic, ref_sign_quirk=quirk, slab=slab)
+        x, its, reason, hist = K.gmres(A, b, slab=slab)
+        out[name] = (A(b).numpy(), x.numpy(), its, reason, hist)
+    shape = (4, 3, 6)
+    g = torch.Generator().manual_seed(3)
+    u_full = torch.randn(4 * 4 * 3 * 6, dtype=torch.float64, generator=g).to(torch.complex128)
+    nloc = u_full.numel() // P
+    u = u_full[rank * nloc:(rank + 1) * nloc].clone()
+    for name, periodic in (("w", False), ("wp", True)):
+        Aw = K.wave_operator(shape, 3.0, (0.08, 0.05, 0.03), periodic=periodic, slab=slab)
+        x, its, reason, hist = K.gmres(Aw, u, slab=slab)
+        out[name] = (Aw(u).numpy(), x.numpy(), its, reason, hist)
+    ret[rank] = out
+    dist.destroy_process_group()
+
+
+def test_distributed_krylov_harness_world_size_2():
+    from circulantpreconditioner_b200 import krylov as K
+    P = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_krylov, args=(P, 33500 + (os.getpid() % 2000), ret), nprocs=P, join=True)
+    got = {r: ret[r] for r in range(P)}
+
+    def cat(name, i):
+        return np.concatenate([got[r][name][i] for r in range(P)])
+
+    for name, shape, lam, periodic, quirk in (("t", (6, 5, 8), (3.0, 0.5, 1.5), False, False),
+                                              ("tq", (6, 5, 8), (3.0, 0.5, 1.5), False, True),
+                                              ("tp", (6, 5, 8), (3.0, 0.5, 1.5), True, False)):
+        b = K.spherical_step(shape, 650.0, 600.0).to(torch.complex128)
+        A = K.transport_operator(shape, lam, periodic=periodic, ref_sign_quirk=quirk)
+        x, its, reason, hist = K.gmres(A, b)
+        assert np.allclose(cat(name, 0), A(b).numpy(), rtol=1e-13, atol=1e-10)
+        assert got[0][name][2] == its and got[1][name][2] == its and got[0][name][3] == reason
+        assert np.allclose(got[0][name][4], hist, rtol=1e-8, atol=1e-12)
+        assert np.allclose(cat(name, 1), x.numpy(), rtol=1e-8, atol=1e-8)
+    shape = (4, 3, 6)
+    g = torch.Generator().manual_seed(3)
+    u = torch.randn(4 * 4 * 3 * 6, dtype=torch.float64, generator=g).to(torch.complex128)
+    for name, periodic in (("w", False), ("wp", True)):
+        Aw = K.wave_operator(shape, 3.0, (0.08, 0.05, 0.03), periodic=periodic)
+        x, its, reason, hist = K.gmres(Aw, u)
+        assert np.allclose(cat(name, 0), Aw(u).numpy(), rtol=1e-13, atol=1e-12)
+        assert got[0][name][2] == its and got[0][name][3] == reason
+        assert np.allclose(cat(name, 1), x.numpy(), rtol=1e-8, atol=1e-8)
