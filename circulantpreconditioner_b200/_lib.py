@@ -69,7 +69,7 @@ CPC_MAX_PASSES = 16
 CPC_NCCL_UNIQUE_ID_BYTES = 128
 DTYPES = {"c128": 0, "c64": 1, "f64": 2, "f32": 3}
 MEM_DEVICE, MEM_HOST = 0, 1
-OPTIONS = {"z_recurrence": 1, "l2_chunk_bytes": 2, "chain_streams": 3}
+OPTIONS = {"z_recurrence": 1, "l2_chunk_bytes": 2, "chain_streams": 3, "z_line_form": 4}
 
 
 def library_path():

@@ -118,6 +118,21 @@ __device__ __forceinline__ long long point_off(int i, long long S, int D, int sh
 
 template <int A, int B> struct CMax { static constexpr int v = A > B ? A : B; };
 
+// 16-byte (8-byte for float2) read-only load that the compiler keeps where it is written
+__device__ __forceinline__ double2 ld_nc_ordered(const double2 *p)
+{
+    double2 r;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ float2 ld_nc_ordered(const float2 *p)
+{
+    float2 r;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+    return r;
+}
+
+
 // ---------------------------------------------------------------------------------------------------------------
 // Shared-memory index of point i of lane-line l.
 // ---------------------------------------------------------------------------------------------------------------
@@ -239,8 +254,19 @@ __device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int k0, int kste
             v[m] = cmul(v[m], crecip_scaled<T>(lam, s.scale));   // b_hat / Diag (:174) and 1/size (:184)
         }
     } else if (MODE == MODE_FUSED_TABLE) {
+        // Four table entries at a time: with all E loads hoisted to the top (what ptxas does when left alone) the
+        // fused kernel needs 2 E more registers than it has and spills 100-140 B per thread.  The rows were pulled
+        // into L2 at the top of the kernel (prefetch_symbol_table), so each group waits for L2, not for HBM.
+        constexpr int GRP = (E % 4 == 0) ? 4 : 1;
 #pragma unroll
-        for (int m = 0; m < E; ++m) v[m] = cmul(v[m], s.inv_table[gbase_l + (long long)(k0 + kstep * m) * SI]);
+        for (int m0 = 0; m0 < E; m0 += GRP) {
+            C t[GRP];
+#pragma unroll
+            for (int i = 0; i < GRP; ++i) t[i] = ld_nc_ordered(&s.inv_table[gbase_l + (long long)(k0 + kstep * (m0 + i)) * SI]);
+#pragma unroll
+            for (int i = 0; i < GRP; ++i) v[m0 + i] = cmul(v[m0 + i], t[i]);
+            asm volatile("" ::: "memory");
+        }
     } else if (MODE == MODE_FUSED_WAVE) {
         // 4 consecutive lanes hold (p, rho0 u, rho0 v, rho0 w) of one cell.  Arrow-matrix Schur solve
         // (blocks from reference src/WaveSystem.cxx:92-107):
@@ -280,6 +306,18 @@ __device__ __forceinline__ void apply_symbol(cplx_t<T> (&v)[E], int k0, int kste
                 v[m] = mk<T>((v[m].x * s.scale + sd * p.y) * iDd, (v[m].y * s.scale - sd * p.x) * iDd);
         }
     }
+}
+
+// Table symbols: pull the thread's E table rows towards L2 at the top of the fused kernel (no registers held); one
+// lane per 128-byte row issues the prefetch.
+template <typename T, int E>
+__device__ __forceinline__ void prefetch_symbol_table(const SymbolArgs<T> &s, long long gbase_l, long long SI, int k0, int kstep,
+                                                      bool row_leader)
+{
+    if (!row_leader) return;
+#pragma unroll
+    for (int m = 0; m < E; ++m)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(s.inv_table + gbase_l + (long long)(k0 + kstep * m) * SI));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -343,6 +381,8 @@ fft_pass_kernel(const cplx_t<T> *in, cplx_t<T> *out, const PassGeom g,
             }
         }
     }
+
+    if (MODE == MODE_FUSED_TABLE && active) prefetch_symbol_table<T, E>(sym, gbase, g.SI, j, TPL, XMAP || (l % (128 / (int)sizeof(C))) == 0);
 
     C v[E];
     if (active) {

@@ -188,6 +188,13 @@ template <typename T> struct PlanT : PlanBase {
     bool zrec_off = false;        // CPC_ZSOLVE=0: keep the FFT-based fused pass (comparison / tuning hook)
     double zrec_lz = 0.0;
     int zrec_e = 0;               // points per thread (0: nz does not fit any compiled form)
+    // Single-rank recurrence as two thread-per-line sweeps (carry-in from the planes that can still matter, then the
+    // solve): ~1 + end_fraction passes, any nz.  Taken when the tile kernel does not fit nz or runs one CTA per SM
+    // (nz >= 1024), provided the decay keeps the first sweep short.
+    bool zrec_line = false;
+    double end_fraction = 1.0;    // share of the array the first sweep reads (mean over lines of min(M, nz) / nz)
+    int zline_mode = -1;          // tuning hook: 1 force the line form, 0 never, -1 choose
+    double2 *zcarry = nullptr;    // [nx ny] carry into plane 0 (single-rank line form)
     int stagger = 0;              // start offset (cycles) of every SM's second resident CTA (tuning hook)
     int nzl = 1, z0 = 0;          // local z slab
     int nyl = 1, y0 = 0;          // local y range in the transposed distribution
@@ -270,6 +277,7 @@ template <typename T> struct PlanT : PlanBase {
         }
         if (sendbuf) cudaFree(sendbuf);
         if (ebuf) cudaFree(ebuf);
+        if (zcarry) cudaFree(zcarry);
         if (gbuf) cudaFree(gbuf);
         if (zinbuf) cudaFree(zinbuf);
         if (tbuf) cudaFree(tbuf);
@@ -345,6 +353,7 @@ template <typename T> struct PlanT : PlanBase {
         if (const char *sg = tune("CPC_STAGGER")) stagger = atoi(sg);
         if (const char *zl = tune("CPC_ZSLAB_LINE")) zslab_line = atoi(zl) != 0;
         if (const char *et = tune("CPC_END_TRUNC")) end_trunc = atoi(et) != 0;
+        if (const char *zm = tune("CPC_ZLINE")) zline_mode = atoi(zm);
         CPC_TRACE("got smem attribute");
 
         // multi-rank plans whose ny is not divisible by the ranks can only run the transpose-free z-slab schedule:
@@ -688,6 +697,22 @@ template <typename T> struct PlanT : PlanBase {
         long long off = 0;
         // middle pass of a transport symbol: cyclic recurrence along z (zsolve.cuh), 128-byte rows as lanes.
         // Multi-rank pushes need power-of-two chunks (shift / mask addressing), as for the FFT kernels.
+        // Line form (single rank): carry into plane 0 from the planes that can still matter, then one thread per line
+        // marches along z (zsolve.cuh); chosen by set_symbol_tables when the tile kernel does not fit or is slow.
+        if (axis == 2 && mode == MODE_FUSED_SEP && zrec && !zrec_off && zrec_line && split == 0 && layout == 0 &&
+            desc.nranks == 1 && zb == 0 && zc == n[2]) {
+            const long long L = (long long)n[0] * n[1];
+            if (!zcarry) CPC_CUDA(cudaMalloc(&zcarry, sizeof(double2) * (size_t)L));
+            ZSolveArgs za = zsolve_args();
+            za.nline = n[2];
+            za.zin = zcarry;
+            const int egrid = (int)((L + 255) / 256);
+            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(in, L, n[0], 0, n[2], 0, end_trunc ? 1 : 0, zcarry, za, -2, 1, ZCarryPeers{});
+            zs_dist_line_kernel<T><<<egrid, 256, 0, st>>>(in, out, L, n[0], n[2], za);
+            launches += 2;
+            CPC_CUDA(cudaGetLastError());
+            return CPC_OK;
+        }
         const bool zs = axis == 2 && mode == MODE_FUSED_SEP && zrec && !zrec_off && zrec_e > 0 && nc == 1 &&
                         (split == 0 || (nzl & (nzl - 1)) == 0);
         PassGeom g = make_geom(axis, zs ? 128 / (int)sizeof(C) : c.tx, zb, zc, layout, &off);
@@ -837,7 +862,28 @@ template <typename T> struct PlanT : PlanBase {
         }
         if (!(mn[0] + mn[1] >= 0.5)) zrec = false;
         zrec_lz = lz;
+        // how much of a line the end-value sweep has to read: planes whose weight |c|^m can reach 1e-17
+        end_fraction = 1.0;
+        if (zrec && n[2] > 1) {
+            double acc = 0.0;
+            for (int j = 0; j < n[1]; ++j)
+                for (int i = 0; i < n[0]; ++i) {
+                    const double ar = h[0][i].x + h[1][j].x + lz, ai = h[0][i].y + h[1][j].y;
+                    const double c2 = lz * lz / (ar * ar + ai * ai);
+                    double m = c2 > 0.0 ? -78.3 / std::log(c2) + 1.0 : 1.0;
+                    if (!(m < (double)n[2])) m = (double)n[2];
+                    acc += m;
+                }
+            end_fraction = acc / ((double)n[0] * n[1] * n[2]);
+        }
+        update_zrec_line();
         return CPC_OK;
+    }
+
+    void update_zrec_line()
+    {
+        zrec_line = zrec && desc.nranks == 1 && nc == 1 && !real && n[2] > 1 &&
+                    (zline_mode == 1 || (zline_mode != 0 && end_trunc && end_fraction < 0.25 && (zrec_e == 0 || n[2] >= 1024)));
     }
 
     int set_symbol_separable(const double *cx, const double *cy, const double *cz, double lx, double ly,
@@ -1103,6 +1149,7 @@ template <typename T> struct PlanT : PlanBase {
         case CPC_OPT_Z_RECURRENCE: zrec_off = (value == 0); return CPC_OK;
         case CPC_OPT_L2_CHUNK_BYTES: l2_chunk_bytes = value < 0 ? 0 : value; return CPC_OK;
         case CPC_OPT_CHAIN_STREAMS: chain_streams = value >= 2 ? 2 : 1; return CPC_OK;
+        case CPC_OPT_Z_LINE_FORM: zline_mode = value < 0 ? -1 : (value ? 1 : 0); update_zrec_line(); return CPC_OK;
         default: set_error("cpc_set_option: unknown option %d", option); return CPC_ERR_ARG;
         }
     }
@@ -1319,7 +1366,7 @@ template <typename T> struct PlanT : PlanBase {
             const PassGeom g = make_geom(2, 128 / (int)sizeof(C), 0, nzl, 0, &off);
             launch_zsolve_e(zslab_e, ZS_DIST, false, nzl, g.ntiles, stream, x, x, g);
         } else {
-            zs_dist_line_kernel<T><<<egrid, 256, 0, stream>>>(x, L, n[0], nzl, za);
+            zs_dist_line_kernel<T><<<egrid, 256, 0, stream>>>(x, x, L, n[0], nzl, za);
         }
         ++launches;
         CPC_CUDA(cudaGetLastError());
@@ -1667,7 +1714,7 @@ template <typename T> struct PlanT : PlanBase {
         info->dist_mode = desc.nranks == 1 ? 0 : (use_zslab() ? 3 : ((tbuf_tried ? p2p : want_p2p) ? 2 : 1));
         for (int a = 0; a < 3; ++a) info->fast_path[a] = cfg[a].fast ? 1 : 0;
         if (desc.nranks > 1 ? use_zslab()
-                            : (symbol_kind == CPC_SYMBOL_SEPARABLE && zrec && !zrec_off && zrec_e > 0 && nc == 1))
+                            : (symbol_kind == CPC_SYMBOL_SEPARABLE && zrec && !zrec_off && (zrec_e > 0 || zrec_line) && nc == 1))
             info->fast_path[2] = 2;
         info->local_elems = nloc;
         info->bytes_per_apply_alg = 5ll * 2 * nloc * (long long)(real ? sizeof(T) : sizeof(C));

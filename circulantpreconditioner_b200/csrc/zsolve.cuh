@@ -240,6 +240,8 @@ struct ZCarryPeers {
 // eight have |c| < 0.54 and need fewer than 64 planes -- the planes the forward y pass wrote last, still in L2.
 // With push_rank >= 0 (the last chunk, peers mapped) the result is stored straight into the gather buffer of the
 // rank q = line / lsub that owns the line, G_q[push_rank][line - q lsub], over NVLink.
+// push_rank == -2 (single rank, the planes are the whole line): the cycle is closed on the spot and e receives the
+// carry into plane 0,  e / (1 - c^nz)  -- what zs_carry_owner_kernel computes for one rank.
 template <typename T>
 __global__ void __launch_bounds__(256)
 zs_end_accum_kernel(const cplx_t<T> *__restrict__ x, long long lines, int nx, int zb, int zc, int carry_in, int trunc,
@@ -277,6 +279,9 @@ zs_end_accum_kernel(const cplx_t<T> *__restrict__ x, long long lines, int nx, in
     if (push_rank >= 0) {
         const int q = (int)(line / lsub);
         gpeer.p[q][(long long)push_rank * lsub + (line - (long long)q * lsub)] = acc;
+    } else if (push_rank == -2) {
+        const double2 cn = cpow_rt(c, zc);
+        e[line] = cmul(acc, crecip_scaled<double>(make_double2(1.0 - cn.x, -cn.y), 1.0));
     } else {
         e[line] = acc;
     }
@@ -284,10 +289,11 @@ zs_end_accum_kernel(const cplx_t<T> *__restrict__ x, long long lines, int nx, in
 
 // Second sweep for slabs whose plane count fits no tile form of zsolve_kernel (nz / P = 8 planes at 8 ranks of a 64^3
 // grid, odd counts ...): one thread per (kx, ky) line marches over the local planes from the exchanged carry-in,
-//   y_k = c y_{k-1} + b_k,  x_k = r y_k / (nx ny),   in place, 8 planes in flight per thread.
+//   y_k = c y_{k-1} + b_k,  x_k = r y_k / (nx ny),   8 planes in flight per thread (in == x allowed: a thread only
+// touches its own line and reads a plane before it writes it).  Also the second sweep of the single-rank line form.
 template <typename T>
 __global__ void __launch_bounds__(256)
-zs_dist_line_kernel(cplx_t<T> *x, long long lines, int nx, int nzl, const ZSolveArgs a)
+zs_dist_line_kernel(const cplx_t<T> *in, cplx_t<T> *x, long long lines, int nx, int nzl, const ZSolveArgs a)
 {
     using CS = cplx_t<T>;
     const long long line = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -296,12 +302,13 @@ zs_dist_line_kernel(cplx_t<T> *x, long long lines, int nx, int nzl, const ZSolve
     zs_coeffs(a, (int)(line % nx), (int)(line / nx), r, c);
     const double2 rs = make_double2(r.x * a.scale, r.y * a.scale);
     double2 acc = a.zin[line];
+    const CS *pi = in + line;
     CS *p = x + line;
     int k = 0;
     for (; k + 8 <= nzl; k += 8) {
         double2 v[8];
 #pragma unroll
-        for (int m = 0; m < 8; ++m) v[m] = to_d2(p[(long long)(k + m) * lines]);
+        for (int m = 0; m < 8; ++m) v[m] = to_d2(pi[(long long)(k + m) * lines]);
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
             const double2 t = acc;
@@ -313,7 +320,7 @@ zs_dist_line_kernel(cplx_t<T> *x, long long lines, int nx, int nzl, const ZSolve
         for (int m = 0; m < 8; ++m) p[(long long)(k + m) * lines] = from_d2<CS>(v[m]);
     }
     for (; k < nzl; ++k) {
-        const double2 v = to_d2(p[(long long)k * lines]), t = acc;
+        const double2 v = to_d2(pi[(long long)k * lines]), t = acc;
         acc.x = fma(c.x, t.x, fma(-c.y, t.y, v.x));
         acc.y = fma(c.x, t.y, fma(c.y, t.x, v.y));
         p[(long long)k * lines] = from_d2<CS>(cmul(acc, rs));

@@ -115,7 +115,11 @@ enum cpc_option {
     CPC_OPT_L2_CHUNK_BYTES = 2, /* > 0: run the x / y passes z-chunk by z-chunk with this many bytes of x per chunk (Fx and
                                    Fy, By and Bx back to back on each chunk, so the second pass reads it from L2);
                                    0 (default) = whole-array passes, which measured faster at 512^3 */
-    CPC_OPT_CHAIN_STREAMS = 3   /* 1 (default) or 2: alternate the chunks' chains between two streams */
+    CPC_OPT_CHAIN_STREAMS = 3,  /* 1 (default) or 2: alternate the chunks' chains between two streams */
+    CPC_OPT_Z_LINE_FORM = 4     /* single-rank recurrence as two thread-per-line sweeps (carry-in from the planes whose
+                                   weight |c|^m can reach 1e-17, then the solve) instead of the tile kernel:
+                                   1 always, 0 never, -1 (default) when the tile kernel does not fit nz or nz >= 1024
+                                   and the first sweep reads less than a quarter of the array */
 };
 int cpc_set_option(cpc_plan plan, int option, long long value);
 

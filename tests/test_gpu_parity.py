@@ -174,6 +174,29 @@ def test_middle_pass_recurrence_matches_fft_form(shape):
     assert rel_l2(rec, fft) < TOL64
 
 
+@pytest.mark.parametrize("shape", [(64, 32, 512), (24, 16, 384), (8, 8, 100), (40, 3, 1024), (8, 5, 200), (12, 7, 63), (16, 16, 2)])
+@pytest.mark.parametrize("lam", [(55.5556, 55.5556, 55.5556), (0.6, 0.15, 3000.0)])
+def test_middle_pass_line_form(shape, lam):
+    """The thread-per-line form of the recurrence (carry-in from the planes that can still matter, then one thread per
+    line along z; any nz) against the oracle and the tile-kernel / FFT forms; lambda_z = 3000 makes every plane matter."""
+    nx, ny, nz = shape
+    rng = np.random.default_rng(nx + 3 * ny + 7 * nz)
+    b = rand_c(rng, nx * ny * nz)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b)
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        p.set_symbol_transport(*lam)
+        p.set_option("z_line_form", 1)
+        assert p.info()["fast_path"][2] == 2
+        line = host(p.apply(dev(b)))
+        x = dev(b)
+        p.apply(x, x)                                    # in place
+        p.set_option("z_line_form", 0)
+        other = host(p.apply(dev(b)))
+    assert rel_l2(line, want) < TOL64
+    assert rel_l2(host(x), want) < TOL64
+    assert rel_l2(line, other) < TOL64
+
+
 def test_middle_pass_recurrence_gating():
     nx, ny, nz = 32, 16, 64
     rng = np.random.default_rng(5)
