@@ -189,8 +189,8 @@ template <typename T> struct PlanT : PlanBase {
     double zrec_lz = 0.0;
     int zrec_e = 0;               // points per thread (0: nz does not fit any compiled form)
     // Single-rank recurrence as two thread-per-line sweeps (carry-in from the planes that can still matter, then the
-    // solve): ~1 + end_fraction passes, any nz.  Taken when the tile kernel does not fit nz or runs one CTA per SM
-    // (nz >= 1024), provided the decay keeps the first sweep short.
+    // solve): ~1 + end_fraction passes, any nz.  Taken when the tile kernel does not fit nz, or when it is slow there
+    // (see update_zrec_line) and the decay keeps the first sweep short.
     bool zrec_line = false;
     double end_fraction = 1.0;    // share of the array the first sweep reads (mean over lines of min(M, nz) / nz)
     int zline_mode = -1;          // tuning hook: 1 force the line form, 0 never, -1 choose
@@ -882,8 +882,15 @@ template <typename T> struct PlanT : PlanBase {
 
     void update_zrec_line()
     {
+        // Measured (profiles/r02_notes.md): the tile kernel wins with 16 points per thread and two CTAs per SM (512^3:
+        // 0.70 against 0.82 ms); the line form wins when the tile kernel runs one CTA per SM (1024^3: 8.2 -> 6.0 ms) or
+        // with fewer points per thread (500^3: 1.57 -> 0.78 ms, 1000^3: 9.1 -> 5.5 ms).  It needs enough lines to fill
+        // the GPU with one thread each.
+        const bool fills = (long long)n[0] * n[1] >= 131072;
         zrec_line = zrec && desc.nranks == 1 && nc == 1 && !real && n[2] > 1 &&
-                    (zline_mode == 1 || (zline_mode != 0 && end_trunc && end_fraction < 0.25 && (zrec_e == 0 || n[2] >= 1024)));
+                    (zline_mode == 1 ||
+                     (zline_mode != 0 && (zrec_e == 0 || (end_trunc && end_fraction < 0.25 && fills &&
+                                                         (zrec_e != 16 || n[2] >= 1024)))));
     }
 
     int set_symbol_separable(const double *cx, const double *cy, const double *cz, double lx, double ly,
