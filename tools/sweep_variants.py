@@ -3,6 +3,7 @@
 Variant ids (csrc/plan_impl.cuh enum Variant): 0 wide, 1 narrow, 2 xmap (scalar x pass), 3 wide2, 4 small.
 Usage: python tools/sweep_variants.py N  vx,vy,vz[,prefetch_waves] ...   (env NCOMP=4 for the wave block)"""
 import os
+os.environ["CPC_TUNING"] = "1"      # the library reads its tuning hooks only then
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
