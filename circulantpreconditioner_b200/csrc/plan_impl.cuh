@@ -885,12 +885,14 @@ template <typename T> struct PlanT : PlanBase {
         // Measured (profiles/r02_notes.md): the tile kernel wins with 16 points per thread and two CTAs per SM (512^3:
         // 0.70 against 0.82 ms); the line form wins when the tile kernel runs one CTA per SM (1024^3: 8.2 -> 6.0 ms) or
         // with fewer points per thread (500^3: 1.57 -> 0.78 ms, 1000^3: 9.1 -> 5.5 ms).  It needs enough lines to fill
-        // the GPU with one thread each.
-        const bool fills = (long long)n[0] * n[1] >= 131072;
+        // the GPU with one thread each (400^3, 160 k lines: 0.44 ms against 0.33 for the tile kernel).  complex64
+        // storage: the tile kernel computes in fp64 on 16-lane rows, 512 threads at 128 registers -- one CTA per SM,
+        // 0.70 ms at 512^3 where the line form streams the 1 GB array at full rate.
+        const bool fills = (long long)n[0] * n[1] >= 200000;
         zrec_line = zrec && desc.nranks == 1 && nc == 1 && !real && n[2] > 1 &&
                     (zline_mode == 1 ||
                      (zline_mode != 0 && (zrec_e == 0 || (end_trunc && end_fraction < 0.25 && fills &&
-                                                         (zrec_e != 16 || n[2] >= 1024)))));
+                                                         (zrec_e != 16 || n[2] >= 1024 || sizeof(T) == 4)))));
     }
 
     int set_symbol_separable(const double *cx, const double *cy, const double *cz, double lx, double ly,
