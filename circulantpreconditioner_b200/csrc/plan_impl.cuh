@@ -701,14 +701,14 @@ template <typename T> struct PlanT : PlanBase {
         // marches along z (zsolve.cuh); chosen by set_symbol_tables when the tile kernel does not fit or is slow.
         if (axis == 2 && mode == MODE_FUSED_SEP && zrec && !zrec_off && zrec_line && split == 0 && layout == 0 &&
             desc.nranks == 1 && zb == 0 && zc == n[2]) {
-            const long long L = (long long)n[0] * n[1];
+            const long long L = wx * n[1];       // wx = nx, or the padded half-spectrum row of a real plan
             if (!zcarry) CPC_CUDA(cudaMalloc(&zcarry, sizeof(double2) * (size_t)L));
             ZSolveArgs za = zsolve_args();
             za.nline = n[2];
             za.zin = zcarry;
             const int egrid = (int)((L + 255) / 256);
-            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(in, L, n[0], 0, n[2], 0, end_trunc ? 1 : 0, zcarry, za, -2, 1, ZCarryPeers{});
-            zs_dist_line_kernel<T><<<egrid, 256, 0, st>>>(in, out, L, n[0], n[2], za);
+            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(in, L, (int)wx, 0, n[2], 0, end_trunc ? 1 : 0, zcarry, za, -2, 1, ZCarryPeers{});
+            zs_dist_line_kernel<T><<<egrid, 256, 0, st>>>(in, out, L, (int)wx, n[2], za);
             launches += 2;
             CPC_CUDA(cudaGetLastError());
             return CPC_OK;
@@ -888,8 +888,8 @@ template <typename T> struct PlanT : PlanBase {
         // the GPU with one thread each (400^3, 160 k lines: 0.44 ms against 0.33 for the tile kernel).  complex64
         // storage: the tile kernel computes in fp64 on 16-lane rows, 512 threads at 128 registers -- one CTA per SM,
         // 0.70 ms at 512^3 where the line form streams the 1 GB array at full rate.
-        const bool fills = (long long)n[0] * n[1] >= 200000;
-        zrec_line = zrec && desc.nranks == 1 && nc == 1 && !real && n[2] > 1 &&
+        const bool fills = wx * n[1] >= 200000;
+        zrec_line = zrec && desc.nranks == 1 && nc == 1 && !real_promote && n[2] > 1 &&
                     (zline_mode == 1 ||
                      (zline_mode != 0 && (zrec_e == 0 || (end_trunc && end_fraction < 0.25 && fills &&
                                                          (zrec_e != 16 || n[2] >= 1024 || sizeof(T) == 4)))));
