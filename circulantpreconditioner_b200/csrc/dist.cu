@@ -234,8 +234,8 @@ int dist_flag_barrier_init(DistState &d, int device, cudaStream_t stream)
 {
     if (d.nranks == 1 || d.nranks > CPC_DIST_MAX_PEERS) return CPC_OK;
     CPC_CUDA(cudaSetDevice(device));
-    CPC_CUDA(cudaMalloc(&d.flags, sizeof(unsigned long long) * CPC_DIST_MAX_PEERS));
-    CPC_CUDA(cudaMemset(d.flags, 0, sizeof(unsigned long long) * CPC_DIST_MAX_PEERS));
+    CPC_CUDA(cudaMalloc(&d.flags, sizeof(unsigned long long) * 2 * CPC_DIST_MAX_PEERS));
+    CPC_CUDA(cudaMemset(d.flags, 0, sizeof(unsigned long long) * 2 * CPC_DIST_MAX_PEERS));
     CPC_CUDA(cudaMalloc(&d.timeout_flag, sizeof(int)));
     CPC_CUDA(cudaMemset(d.timeout_flag, 0, sizeof(int)));
     int rc = dist_map_peers(d, d.flags, d.peer_flags, device, stream);
@@ -244,13 +244,15 @@ int dist_flag_barrier_init(DistState &d, int device, cudaStream_t stream)
     return CPC_OK;
 }
 
-int dist_barrier(DistState &d, cudaStream_t stream)
+int dist_barrier(DistState &d, cudaStream_t stream, int group)
 {
     if (d.nranks == 1) return CPC_OK;
     if (d.flag_barrier) {
         FlagPeers fp{};
-        for (int q = 0; q < d.nranks; ++q) fp.p[q] = (unsigned long long *)d.peer_flags[q];
-        flag_barrier_kernel<<<1, 32, 0, stream>>>(fp, d.flags, d.nranks, d.rank, ++d.epoch, d.timeout_flag);
+        const int go = (group ? 1 : 0) * CPC_DIST_MAX_PEERS;
+        for (int q = 0; q < d.nranks; ++q) fp.p[q] = (unsigned long long *)d.peer_flags[q] + go;
+        flag_barrier_kernel<<<1, 32, 0, stream>>>(fp, d.flags + go, d.nranks, d.rank, ++d.epoch[group ? 1 : 0],
+                                                  d.timeout_flag);
         CPC_CUDA(cudaGetLastError());
         return CPC_OK;
     }

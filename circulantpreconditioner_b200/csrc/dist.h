@@ -14,10 +14,11 @@ struct DistState {
     int nranks = 1, rank = 0;
     void *comm = nullptr;        // ncclComm_t
     float *barrier_buf = nullptr;
-    // flag barrier over peer-mapped memory (dist_flag_barrier_init): flags[s] = last epoch rank s signalled to this rank
+    // flag barrier over peer-mapped memory (dist_flag_barrier_init): flags[g][s] = last epoch rank s signalled to this
+    // rank in barrier group g.  Two groups: barriers issued on two different streams must not share epochs.
     unsigned long long *flags = nullptr;
     void *peer_flags[CPC_DIST_MAX_PEERS] = {};
-    unsigned long long epoch = 0;
+    unsigned long long epoch[2] = { 0, 0 };
     int *timeout_flag = nullptr; // device int, set by a barrier kernel that gave up waiting (a peer died)
     bool flag_barrier = false;
 };
@@ -33,8 +34,10 @@ int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes
 int dist_allgather(DistState &d, const void *send, void *recv, size_t bytes, cudaStream_t stream);
 // In-place sum over ranks of `count` floats (agreement flags of collective set-up steps).
 int dist_allreduce_sum_f32(DistState &d, float *buf, size_t count, cudaStream_t stream);
-// Stream-ordered barrier across ranks (1-element all-reduce).
-int dist_barrier(DistState &d, cudaStream_t stream);
+// Stream-ordered barrier across ranks (peer flags, or a 1-element all-reduce).  Every rank must issue the barriers of
+// one group in the same order; group 1 is for a second stream (NCCL fallback: group is ignored, so callers that use
+// two streams must check d.flag_barrier first).
+int dist_barrier(DistState &d, cudaStream_t stream, int group = 0);
 // Barrier through peer-mapped flags instead of an NCCL all-reduce (a 1-CTA kernel: every rank writes its epoch into
 // every peer's flag array over NVLink and waits for the peers' epochs in its own; ~5 us instead of ~20 at 8 GPUs).
 // The wait gives up after ~2 s and raises timeout_flag, so a dead peer cannot hang the GPU.  dist_barrier() uses it

@@ -53,8 +53,10 @@ zs_carry_owner_kernel(const double2 *__restrict__ gbuf, long long gstride, long 
     for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < count;
          j += (long long)gridDim.x * blockDim.x) {
         const long long line = line0 + j;
+        const int lx = (int)(line % nx);
+        if (lx < a.xs0 || lx >= a.xs0 + a.xsn) continue;          // this launch serves the other half of the columns
         double2 r, c;
-        zs_coeffs(a, (int)(line % nx), (int)(line / nx), r, c);
+        zs_coeffs(a, lx, (int)(line / nx), r, c);
         const double2 cL = cpow_rt(c, nzl);
         double2 e[CPC_MAX_PEERS];
 #pragma unroll

@@ -243,6 +243,12 @@ template <typename T> struct PlanT : PlanBase {
     long long lsub = 0;           // lines owned per rank
     bool carry_p2p = false;
     void *peer_g[CPC_MAX_PEERS] = {}, *peer_z[CPC_MAX_PEERS] = {};
+    // The carry exchange of one half of the columns (kx) runs on xstream -- barrier, owner kernel, barrier: ~40 us of
+    // latency -- while the main stream does the forward y pass and the end-value sweep of the other half, and then
+    // the solve of the first half.  Needs the flag barrier (two barrier groups) and nx divisible by two tile widths.
+    bool xsplit = true;
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t xs_ev[4] = {};
     int zslab_e = 0;              // points per thread for nz / P point lines (0: no tile form fits -> one thread per line)
     bool zslab_line = false;      // tuning hook: always take the thread-per-line form of the second sweep
     bool end_trunc = true;        // end values summed over the planes that can still matter (zs_end_accum_kernel)
@@ -283,6 +289,9 @@ template <typename T> struct PlanT : PlanBase {
         if (tbuf) cudaFree(tbuf);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (side_stream) cudaStreamDestroy(side_stream);
+        if (xstream) cudaStreamDestroy(xstream);
+        for (auto e : xs_ev)
+            if (e) cudaEventDestroy(e);
         if (fork_ev) cudaEventDestroy(fork_ev);
         if (join_ev) cudaEventDestroy(join_ev);
         for (auto e : chunk_ev) cudaEventDestroy(e);
@@ -354,6 +363,7 @@ template <typename T> struct PlanT : PlanBase {
         if (const char *zl = tune("CPC_ZSLAB_LINE")) zslab_line = atoi(zl) != 0;
         if (const char *et = tune("CPC_END_TRUNC")) end_trunc = atoi(et) != 0;
         if (const char *zm = tune("CPC_ZLINE")) zline_mode = atoi(zm);
+        if (const char *xs = tune("CPC_XSPLIT")) xsplit = atoi(xs) != 0;
         CPC_TRACE("got smem attribute");
 
         // multi-rank plans whose ny is not divisible by the ranks can only run the transpose-free z-slab schedule:
@@ -542,6 +552,12 @@ template <typename T> struct PlanT : PlanBase {
                     carry_p2p = (r1 == CPC_OK && r2 == CPC_OK);
                     if (!carry_p2p && r1 != CPC_ERR_UNSUPPORTED && r2 != CPC_ERR_UNSUPPORTED) return r1 ? r1 : r2;
                 }
+                if (carry_p2p && dist.flag_barrier) {
+                    int lo = 0, hi = 0;
+                    CPC_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                    CPC_CUDA(cudaStreamCreateWithPriority(&xstream, cudaStreamNonBlocking, hi));
+                    for (auto &e : xs_ev) CPC_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                }
                 if (!carry_p2p) {                 // all-gather fallback: every rank holds every rank's end values
                     cudaFree(gbuf);
                     gbuf = nullptr;
@@ -691,7 +707,9 @@ template <typename T> struct PlanT : PlanBase {
     // split: 0 = none, 1 = store side chunked (forward y of a multi-rank plan), 2 = load side chunked (backward y)
     // split: 0 = none, 1 = store side chunked, 2 = load side chunked, 3 = stores pushed to the peers' transposed
     // buffers (forward y), 4 = stores pushed to the peers' chunked buffers (fused z)
-    int run_pass(int axis, int mode, const C *in, C *out, int zb, int zc, int layout, cudaStream_t st, int split = 0)
+    // xs0 / xsn (y passes only): restrict the pass to columns [xs0, xs0 + xsn) of every row, a multiple of the tile width
+    int run_pass(int axis, int mode, const C *in, C *out, int zb, int zc, int layout, cudaStream_t st, int split = 0,
+                 int xs0 = 0, int xsn = 0)
     {
         const AxisCfg &c = cfg[axis];
         long long off = 0;
@@ -716,6 +734,12 @@ template <typename T> struct PlanT : PlanBase {
         const bool zs = axis == 2 && mode == MODE_FUSED_SEP && zrec && !zrec_off && zrec_e > 0 && nc == 1 &&
                         (split == 0 || (nzl & (nzl - 1)) == 0);
         PassGeom g = make_geom(axis, zs ? 128 / (int)sizeof(C) : c.tx, zb, zc, layout, &off);
+        if (axis == 1 && xsn > 0) {
+            g.tiles_inner = xsn / c.tx;
+            g.lines_inner = xsn;
+            g.ntiles = g.tiles_inner * zc;
+            off += xs0;
+        }
         if (split == 1 || split == 2) make_split(g, split == 1);
         if (split == 3 || split == 4) {
             const long long W = (long long)n[0] * nc;
@@ -940,6 +964,8 @@ template <typename T> struct PlanT : PlanBase {
         a.scale = (double)n[2] / (double)ntot;
         a.n = n[2];
         a.zin = zinbuf;
+        a.xs0 = 0;
+        a.xsn = (int)wx;
         return a;
     }
 
@@ -1323,9 +1349,67 @@ template <typename T> struct PlanT : PlanBase {
     // Multi-rank apply for a transport symbol: no transposes.  [Fx, Fy, end-value accumulation] z-chunk by z-chunk
     // (L2-chained), the carry exchange (zsolve.cuh), the z solve on the local slab from the exchanged carry-in,
     // [By, Bx] z-chunk by z-chunk.  Pass kinds: Fx, Fy, end values, carry exchange, z solve, By, Bx.
+    // Can the carry exchange be pipelined over two halves of the columns?  (peer flags for two barrier groups, both
+    // x and y transformed, the halves whole tiles of the y pass)
+    bool xsplit_ok() const
+    {
+        return xsplit && xstream && carry_p2p && dist.flag_barrier && n[0] > 1 && n[1] > 1 && l2_chunk_bytes <= 0 &&
+               cfg[1].tx > 0 && n[0] % (2 * cfg[1].tx) == 0 && (long long)n[0] * n[1] >= 65536;
+    }
+
+    // The z-slab schedule with the carry exchange of one half of the columns hidden behind the work on the other:
+    //   main stream:  Fx | Fy(A) END(A) | Fy(B) END(B) | wait A: solve(A) | wait B: solve(B) | By | Bx
+    //   xstream:             wait END(A): barrier, owner(A), barrier | wait END(B): barrier, owner(B), barrier
+    // A = columns [0, nx/2), B = the rest; END pushes its end values straight to the line owners.  The second sweep is
+    // the thread-per-line kernel (it takes a column range as it is).  Barriers of xstream use their own flag group.
+    int apply_device_zslab_xsplit(const C *b, C *x)
+    {
+        int rc;
+        const long long L = (long long)n[0] * n[1];
+        const int nxh = n[0] / 2;
+        ZCarryPeers gp{}, zp{};
+        for (int q = 0; q < desc.nranks; ++q) { gp.p[q] = (double2 *)peer_g[q]; zp.p[q] = (double2 *)peer_z[q]; }
+        const int hgrid = (int)(((long long)nxh * n[1] + 255) / 256);
+        const long long line0 = lsub * desc.rank;
+        const long long cnt = line0 >= L ? 0 : (L - line0 < lsub ? L - line0 : lsub);
+        if ((rc = run_pass(0, MODE_FWD, b, x, 0, nzl, 0, stream))) return rc;
+        ZSolveArgs za[2];
+        for (int h = 0; h < 2; ++h) {
+            za[h] = zsolve_args();
+            za[h].nline = nzl;
+            za[h].xs0 = h * nxh;
+            za[h].xsn = nxh;
+            if ((rc = run_pass(1, MODE_FWD, x, x, 0, nzl, 0, stream, 0, h * nxh, nxh))) return rc;
+            zs_end_accum_kernel<T><<<hgrid, 256, 0, stream>>>(x, L, n[0], 0, nzl, 0, end_trunc ? 1 : 0, ebuf, za[h], desc.rank, lsub, gp);
+            ++launches;
+            CPC_CUDA(cudaGetLastError());
+            CPC_CUDA(cudaEventRecord(xs_ev[h], stream));
+            CPC_CUDA(cudaStreamWaitEvent(xstream, xs_ev[h], 0));
+            if ((rc = dist_barrier(dist, xstream, 1))) return rc;         // every rank's end values of this half have landed
+            if (cnt > 0) {
+                zs_carry_owner_kernel<<<(int)((cnt + 255) / 256), 256, 0, xstream>>>(gbuf, lsub, line0, cnt, n[0], nzl, desc.nranks,
+                                                                                  desc.rank, 0, zp, za[h]);
+                ++launches;
+                CPC_CUDA(cudaGetLastError());
+            }
+            if ((rc = dist_barrier(dist, xstream, 1))) return rc;         // every carry-in of this half has landed
+            CPC_CUDA(cudaEventRecord(xs_ev[2 + h], xstream));
+        }
+        for (int h = 0; h < 2; ++h) {
+            CPC_CUDA(cudaStreamWaitEvent(stream, xs_ev[2 + h], 0));
+            zs_dist_line_kernel<T><<<hgrid, 256, 0, stream>>>(x, x, L, n[0], nzl, za[h]);
+            ++launches;
+            CPC_CUDA(cudaGetLastError());
+        }
+        if ((rc = run_pass(1, MODE_INV, x, x, 0, nzl, 0, stream))) return rc;
+        return run_pass(0, MODE_INV, x, x, 0, nzl, 0, stream);
+    }
+
     int apply_device_zslab(const C *b, C *x, float *pass_ms, int *npasses)
     {
         int rc;
+        // (per-pass profiling keeps the serial schedule: its pass kinds would overlap in the pipelined one)
+        if (!pass_ms && xsplit_ok()) return apply_device_zslab_xsplit(b, x);
         if ((rc = prof_begin(pass_ms))) return rc;
         const long long L = (long long)n[0] * n[1];
         ZSolveArgs za = zsolve_args();

@@ -44,7 +44,18 @@ struct ZSolveArgs {
     int n;                        // nz
     int nline;                    // points of the line a tile holds: nz, or nz / P in the z-slab sweep
     const double2 *zin;           // ZS_DIST: carry into the first local plane of every (kx, ky) line, [nx ny]
+    // thread-per-line kernels: the launch covers columns [xs0, xs0 + xsn) of every row (the whole row by default);
+    // the z-slab schedule pipelines the carry exchange of one half of the columns behind the work on the other
+    int xs0, xsn;
 };
+
+// line index (x + nx y) of the t-th line of a launch that covers columns [xs0, xs0 + xsn)
+__device__ __forceinline__ long long zs_line_of(const ZSolveArgs &a, long long t, int nx, int &x, int &y)
+{
+    y = (int)(t / a.xsn);
+    x = a.xs0 + (int)(t - (long long)y * a.xsn);
+    return x + (long long)nx * y;
+}
 
 enum ZSolveKind {
     ZS_CYCLIC = 0,    // the whole z line is in the tile: close the cycle inside the kernel (single GPU, transposed slabs)
@@ -247,10 +258,12 @@ __global__ void __launch_bounds__(256)
 zs_end_accum_kernel(const cplx_t<T> *__restrict__ x, long long lines, int nx, int zb, int zc, int carry_in, int trunc,
                     double2 *__restrict__ e, const ZSolveArgs a, int push_rank, long long lsub, ZCarryPeers gpeer)
 {
-    const long long line = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (line >= lines) return;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= lines / nx * a.xsn) return;
+    int lx, ly;
+    const long long line = zs_line_of(a, t, nx, lx, ly);
     double2 r, c;
-    zs_coeffs(a, (int)(line % nx), (int)(line / nx), r, c);
+    zs_coeffs(a, lx, ly, r, c);
     int k = 0;
     if (trunc) {
         const double c2 = c.x * c.x + c.y * c.y;                  // |c|^2 < 1
@@ -301,10 +314,12 @@ __global__ void __launch_bounds__(256)
 zs_dist_line_kernel(const cplx_t<T> *in, cplx_t<T> *x, long long lines, int nx, int nzl, const ZSolveArgs a)
 {
     using CS = cplx_t<T>;
-    const long long line = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (line >= lines) return;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= lines / nx * a.xsn) return;
+    int lx, ly;
+    const long long line = zs_line_of(a, t, nx, lx, ly);
     double2 r, c;
-    zs_coeffs(a, (int)(line % nx), (int)(line / nx), r, c);
+    zs_coeffs(a, lx, ly, r, c);
     const double2 rs = make_double2(r.x * a.scale, r.y * a.scale);
     double2 acc = a.zin[line];
     const CS *pi = in + line;
