@@ -243,10 +243,12 @@ template <typename T> struct PlanT : PlanBase {
     long long lsub = 0;           // lines owned per rank
     bool carry_p2p = false;
     void *peer_g[CPC_MAX_PEERS] = {}, *peer_z[CPC_MAX_PEERS] = {};
-    // The carry exchange of one half of the columns (kx) runs on xstream -- barrier, owner kernel, barrier: ~40 us of
-    // latency -- while the main stream does the forward y pass and the end-value sweep of the other half, and then
-    // the solve of the first half.  Needs the flag barrier (two barrier groups) and nx divisible by two tile widths.
-    bool xsplit = true;
+    // Optional (tuning hook CPC_XSPLIT=1, off by default): the carry exchange of one half of the columns (kx) runs on
+    // xstream -- barrier, owner kernel, barrier: ~40 us of latency -- while the main stream does the forward y pass
+    // and the end-value sweep of the other half, and then the solve of the first half.  Needs the flag barrier (two
+    // barrier groups) and nx divisible by two tile widths.  Measured at 512^3 on 2 GPUs: 1.80 ms against 1.73 ms for
+    // the serial schedule -- the three extra kernel tails cost more than the hidden exchange saves; kept for larger grids.
+    bool xsplit = false;
     cudaStream_t xstream = nullptr;
     cudaEvent_t xs_ev[4] = {};
     int zslab_e = 0;              // points per thread for nz / P point lines (0: no tile form fits -> one thread per line)

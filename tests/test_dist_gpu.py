@@ -82,7 +82,7 @@ def _run(shape, lam, ncomp=1, wave=False, P=2, opts=None):
     return dict(errs)
 
 
-# (256, 256, 32): enough lines (>= 65536) for the schedule that pipelines the carry exchange over two halves of the columns
+# (256, 256, 32): 65536 lines, 16 planes per rank
 @pytest.mark.parametrize("shape", [(64, 64, 64), (128, 32, 16), (32, 16, 256), (20, 12, 10), (96, 48, 24), (16, 32, 1024),
                                    (256, 256, 32)])
 def test_two_rank_transport(shape):
@@ -155,8 +155,8 @@ def test_four_rank_transport():
 # ---- 8 ranks (one 8 x B200 node: `gpurun --gpus 8 -- python -m pytest tests/test_dist_gpu.py -m gpu -k eight`) ----
 @pytest.mark.parametrize("shape", [(64, 64, 64), (256, 256, 64), (40, 24, 128)])
 def test_eight_rank_transport(shape):
-    """The transpose-free z-slab schedule at 8 ranks (8 / 16 planes per rank; (256, 256, 64) takes the pipelined carry
-    exchange; the (40, 24, 128) grid has generic x / y lengths): every rank's slab against the single-process oracle."""
+    """The transpose-free z-slab schedule at 8 ranks (8 / 16 planes per rank; the (40, 24, 128) grid has generic x / y
+    lengths): every rank's slab against the single-process oracle."""
     errs = _run(shape, (55.5556, 55.5556, 55.5556), P=8, opts={"expect_dist_mode": 3})
     assert len(errs) == 8
     for r, (e1, e2, e3) in errs.items():
