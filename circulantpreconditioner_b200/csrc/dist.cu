@@ -118,6 +118,8 @@ void dist_destroy(DistState &d)
     }
     if (d.flags) cudaFree(d.flags);
     if (d.timeout_flag) cudaFree(d.timeout_flag);
+    if (d.sync_counters) cudaFree(d.sync_counters);
+    d.sync_counters = nullptr;
     d.flags = nullptr;
     d.timeout_flag = nullptr;
     if (d.barrier_buf) cudaFree(d.barrier_buf);
@@ -238,6 +240,8 @@ int dist_flag_barrier_init(DistState &d, int device, cudaStream_t stream)
     CPC_CUDA(cudaMemset(d.flags, 0, sizeof(unsigned long long) * 2 * CPC_DIST_MAX_PEERS));
     CPC_CUDA(cudaMalloc(&d.timeout_flag, sizeof(int)));
     CPC_CUDA(cudaMemset(d.timeout_flag, 0, sizeof(int)));
+    CPC_CUDA(cudaMalloc(&d.sync_counters, 2 * sizeof(int)));
+    CPC_CUDA(cudaMemset(d.sync_counters, 0, 2 * sizeof(int)));
     int rc = dist_map_peers(d, d.flags, d.peer_flags, device, stream);
     if (rc == CPC_OK) d.flag_barrier = true;
     else if (rc != CPC_ERR_UNSUPPORTED) return rc;

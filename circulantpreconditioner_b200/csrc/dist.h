@@ -20,6 +20,7 @@ struct DistState {
     void *peer_flags[CPC_DIST_MAX_PEERS] = {};
     unsigned long long epoch[2] = { 0, 0 };
     int *timeout_flag = nullptr; // device int, set by a barrier kernel that gave up waiting (a peer died)
+    int *sync_counters = nullptr; // 2 device ints: finished-block counters of kernels that signal at their end (zsolve.cuh)
     bool flag_barrier = false;
 };
 

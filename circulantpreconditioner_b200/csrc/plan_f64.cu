@@ -48,8 +48,10 @@ __global__ void diag_check_separable_kernel(const double2 *__restrict__ diag, co
 
 __global__ void __launch_bounds__(256)
 zs_carry_owner_kernel(const double2 *__restrict__ gbuf, long long gstride, long long line0, long long count, int nx,
-                      int nzl, int nranks, int rank, int self_only, ZCarryPeers zpeer, const ZSolveArgs a)
+                      int nzl, int nranks, int rank, int self_only, ZCarryPeers zpeer, const ZSolveArgs a,
+                      const FlagSync wait, const FlagSync done)
 {
+    zs_wait_for_peers(wait);                       // every rank's end values of the lines owned here have landed
     for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < count;
          j += (long long)gridDim.x * blockDim.x) {
         const long long line = line0 + j;
@@ -78,6 +80,7 @@ zs_carry_owner_kernel(const double2 *__restrict__ gbuf, long long gstride, long 
                 Z = cadd(e[q], cmul(cL, Z));                        // Zin_{q+1} = e_q + cL Zin_q
             }
     }
+    zs_signal_when_grid_done(done);                // "the carry-ins computed here have landed on every rank"
 }
 
 int build_diag_separable(int nx, int ny, int nz, const double *cx, const double *cy, const double *cz, double lx, double ly,

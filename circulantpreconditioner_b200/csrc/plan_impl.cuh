@@ -249,6 +249,9 @@ template <typename T> struct PlanT : PlanBase {
     // barrier groups) and nx divisible by two tile widths.  Measured at 512^3 on 2 GPUs: 1.80 ms against 1.73 ms for
     // the serial schedule -- the three extra kernel tails cost more than the hidden exchange saves; kept for larger grids.
     bool xsplit = false;
+    // The kernels of the carry exchange signal and wait themselves (zsolve.cuh FlagSync) instead of separate barrier
+    // launches between them: END -> owner -> solve is three launches, not five.
+    bool fused_sync = true;
     cudaStream_t xstream = nullptr;
     cudaEvent_t xs_ev[4] = {};
     int zslab_e = 0;              // points per thread for nz / P point lines (0: no tile form fits -> one thread per line)
@@ -366,6 +369,7 @@ template <typename T> struct PlanT : PlanBase {
         if (const char *et = tune("CPC_END_TRUNC")) end_trunc = atoi(et) != 0;
         if (const char *zm = tune("CPC_ZLINE")) zline_mode = atoi(zm);
         if (const char *xs = tune("CPC_XSPLIT")) xsplit = atoi(xs) != 0;
+        if (const char *fs = tune("CPC_FUSED_SYNC")) fused_sync = atoi(fs) != 0;
         CPC_TRACE("got smem attribute");
 
         // multi-rank plans whose ny is not divisible by the ranks can only run the transpose-free z-slab schedule:
@@ -727,8 +731,9 @@ template <typename T> struct PlanT : PlanBase {
             za.nline = n[2];
             za.zin = zcarry;
             const int egrid = (int)((L + 255) / 256);
-            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(in, L, (int)wx, 0, n[2], 0, end_trunc ? 1 : 0, zcarry, za, -2, 1, ZCarryPeers{});
-            zs_dist_line_kernel<T><<<egrid, 256, 0, st>>>(in, out, L, (int)wx, n[2], za);
+            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(in, L, (int)wx, 0, n[2], 0, end_trunc ? 1 : 0, zcarry, za, -2, 1, ZCarryPeers{},
+                                                          FlagSync{});
+            zs_dist_line_kernel<T><<<egrid, 256, 0, st>>>(in, out, L, (int)wx, n[2], za, FlagSync{});
             launches += 2;
             CPC_CUDA(cudaGetLastError());
             return CPC_OK;
@@ -972,8 +977,21 @@ template <typename T> struct PlanT : PlanBase {
     }
 
     // nline = points of the z line a tile holds (nz, or nz / P for the z-slab sweeps)
+    FlagSync make_sync(int group, unsigned long long epoch) const
+    {
+        FlagSync f{};
+        for (int q = 0; q < desc.nranks; ++q) f.peer[q] = (unsigned long long *)dist.peer_flags[q] + group * CPC_DIST_MAX_PEERS;
+        f.mine = dist.flags + group * CPC_DIST_MAX_PEERS;
+        f.epoch = epoch;
+        f.counter = dist.sync_counters + group;
+        f.timeout = dist.timeout_flag;
+        f.nranks = desc.nranks;
+        f.rank = desc.rank;
+        return f;
+    }
+
     template <int E> void launch_zsolve(int kind, bool gen, int nline, int grid, cudaStream_t st, const C *in, C *out,
-                                        const PassGeom &g)
+                                        const PassGeom &g, const FlagSync &wait = FlagSync{})
     {
         constexpr int TX = 128 / (int)sizeof(C);
         ZSolveArgs a = zsolve_args();
@@ -983,19 +1001,19 @@ template <typename T> struct PlanT : PlanBase {
         const int gpc = tpt >= 128 ? 1 : 128 / tpt;
         const int threads = tpt * gpc;
         grid = (grid + gpc - 1) / gpc;
-        if (kind == ZS_DIST) zsolve_kernel<T, E, false, ZS_DIST><<<grid, threads, 0, st>>>(in, out, g, a);
-        else if (gen) zsolve_kernel<T, E, true><<<grid, threads, 0, st>>>(in, out, g, a);
-        else zsolve_kernel<T, E, false><<<grid, threads, 0, st>>>(in, out, g, a);
+        if (kind == ZS_DIST) zsolve_kernel<T, E, false, ZS_DIST><<<grid, threads, 0, st>>>(in, out, g, a, wait);
+        else if (gen) zsolve_kernel<T, E, true><<<grid, threads, 0, st>>>(in, out, g, a, wait);
+        else zsolve_kernel<T, E, false><<<grid, threads, 0, st>>>(in, out, g, a, wait);
     }
     void launch_zsolve_e(int e, int kind, bool gen, int nline, int grid, cudaStream_t st, const C *in, C *out,
-                         const PassGeom &g)
+                         const PassGeom &g, const FlagSync &wait = FlagSync{})
     {
         switch (e) {
-        case 16: launch_zsolve<16>(kind, gen, nline, grid, st, in, out, g); break;
-        case 8: launch_zsolve<8>(kind, gen, nline, grid, st, in, out, g); break;
-        case 10: launch_zsolve<10>(kind, gen, nline, grid, st, in, out, g); break;
-        case 5: launch_zsolve<5>(kind, gen, nline, grid, st, in, out, g); break;
-        default: launch_zsolve<4>(kind, gen, nline, grid, st, in, out, g); break;
+        case 16: launch_zsolve<16>(kind, gen, nline, grid, st, in, out, g, wait); break;
+        case 8: launch_zsolve<8>(kind, gen, nline, grid, st, in, out, g, wait); break;
+        case 10: launch_zsolve<10>(kind, gen, nline, grid, st, in, out, g, wait); break;
+        case 5: launch_zsolve<5>(kind, gen, nline, grid, st, in, out, g, wait); break;
+        default: launch_zsolve<4>(kind, gen, nline, grid, st, in, out, g, wait); break;
         }
     }
 
@@ -1382,7 +1400,8 @@ template <typename T> struct PlanT : PlanBase {
             za[h].xs0 = h * nxh;
             za[h].xsn = nxh;
             if ((rc = run_pass(1, MODE_FWD, x, x, 0, nzl, 0, stream, 0, h * nxh, nxh))) return rc;
-            zs_end_accum_kernel<T><<<hgrid, 256, 0, stream>>>(x, L, n[0], 0, nzl, 0, end_trunc ? 1 : 0, ebuf, za[h], desc.rank, lsub, gp);
+            zs_end_accum_kernel<T><<<hgrid, 256, 0, stream>>>(x, L, n[0], 0, nzl, 0, end_trunc ? 1 : 0, ebuf, za[h], desc.rank, lsub, gp,
+                                                              FlagSync{});
             ++launches;
             CPC_CUDA(cudaGetLastError());
             CPC_CUDA(cudaEventRecord(xs_ev[h], stream));
@@ -1390,7 +1409,7 @@ template <typename T> struct PlanT : PlanBase {
             if ((rc = dist_barrier(dist, xstream, 1))) return rc;         // every rank's end values of this half have landed
             if (cnt > 0) {
                 zs_carry_owner_kernel<<<(int)((cnt + 255) / 256), 256, 0, xstream>>>(gbuf, lsub, line0, cnt, n[0], nzl, desc.nranks,
-                                                                                  desc.rank, 0, zp, za[h]);
+                                                                                  desc.rank, 0, zp, za[h], FlagSync{}, FlagSync{});
                 ++launches;
                 CPC_CUDA(cudaGetLastError());
             }
@@ -1399,7 +1418,7 @@ template <typename T> struct PlanT : PlanBase {
         }
         for (int h = 0; h < 2; ++h) {
             CPC_CUDA(cudaStreamWaitEvent(stream, xs_ev[2 + h], 0));
-            zs_dist_line_kernel<T><<<hgrid, 256, 0, stream>>>(x, x, L, n[0], nzl, za[h]);
+            zs_dist_line_kernel<T><<<hgrid, 256, 0, stream>>>(x, x, L, n[0], nzl, za[h], FlagSync{});
             ++launches;
             CPC_CUDA(cudaGetLastError());
         }
@@ -1420,11 +1439,18 @@ template <typename T> struct PlanT : PlanBase {
         const int egrid = (int)((L + 255) / 256);
         ZCarryPeers gp{}, zp{};
         for (int q = 0; q < desc.nranks; ++q) { gp.p[q] = (double2 *)peer_g[q]; zp.p[q] = (double2 *)peer_z[q]; }
+        // With peers mapped the exchange needs no separate barrier launches: the end-value sweep signals "landed at the
+        // owners" when its last block finishes, the owner kernel waits for every rank's signal, pushes the carry-ins and
+        // signals in turn, and the second sweep waits for that (FlagSync, zsolve.cuh).
+        const bool fused = carry_p2p && dist.flag_barrier && fused_sync;
+        const FlagSync none{};
+        const FlagSync s_end = fused ? make_sync(0, ++dist.epoch[0]) : none;
+        const FlagSync s_own = fused ? make_sync(1, ++dist.epoch[1]) : none;
         // the end values of the last chunk go straight to the ranks that own the lines (peer stores) when peers are mapped
         auto end_acc = [&](int zb, int zc, cudaStream_t st) -> int {
             const bool last = zb + zc >= nzl;
             zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(x, L, n[0], zb, zc, zb > 0 ? 1 : 0, end_trunc ? 1 : 0, ebuf, za,
-                                                          (carry_p2p && last) ? desc.rank : -1, lsub, gp);
+                                                          (carry_p2p && last) ? desc.rank : -1, lsub, gp, last ? s_end : none);
             ++launches;
             CPC_CUDA(cudaGetLastError());
             return prof_mark(2);
@@ -1437,21 +1463,20 @@ template <typename T> struct PlanT : PlanBase {
         if (rc) return rc;
         const int cgrid = 148 * 8;
         if (carry_p2p) {
-            if ((rc = dist_barrier(dist, stream))) return rc;            // every rank's end values have landed
+            if (!fused && (rc = dist_barrier(dist, stream))) return rc;  // every rank's end values have landed
             const long long line0 = lsub * desc.rank;
             const long long cnt = line0 >= L ? 0 : (L - line0 < lsub ? L - line0 : lsub);
-            if (cnt > 0) {
-                zs_carry_owner_kernel<<<(int)((cnt + 255) / 256), 256, 0, stream>>>(gbuf, lsub, line0, cnt, n[0], nzl, desc.nranks,
-                                                                                 desc.rank, 0, zp, za);
-                ++launches;
-                CPC_CUDA(cudaGetLastError());
-            }
-            if ((rc = dist_barrier(dist, stream))) return rc;            // every line's carry-in has landed
+            // (launched even without lines of its own: the peers wait for this rank's signal)
+            zs_carry_owner_kernel<<<(int)((cnt + 255) / 256 > 0 ? (cnt + 255) / 256 : 1), 256, 0, stream>>>(
+                gbuf, lsub, line0, cnt, n[0], nzl, desc.nranks, desc.rank, 0, zp, za, s_end, s_own);
+            ++launches;
+            CPC_CUDA(cudaGetLastError());
+            if (!fused && (rc = dist_barrier(dist, stream))) return rc;  // every line's carry-in has landed
         } else {
             if ((rc = dist_allgather(dist, ebuf, gbuf, sizeof(double2) * (size_t)L, stream))) return rc;
             ZCarryPeers zl{};
             zl.p[0] = zinbuf;
-            zs_carry_owner_kernel<<<cgrid, 256, 0, stream>>>(gbuf, L, 0, L, n[0], nzl, desc.nranks, desc.rank, 1, zl, za);
+            zs_carry_owner_kernel<<<cgrid, 256, 0, stream>>>(gbuf, L, 0, L, n[0], nzl, desc.nranks, desc.rank, 1, zl, za, none, none);
             ++launches;
             CPC_CUDA(cudaGetLastError());
         }
@@ -1459,9 +1484,9 @@ template <typename T> struct PlanT : PlanBase {
         if (zslab_e > 0 && !zslab_line) {
             long long off = 0;
             const PassGeom g = make_geom(2, 128 / (int)sizeof(C), 0, nzl, 0, &off);
-            launch_zsolve_e(zslab_e, ZS_DIST, false, nzl, g.ntiles, stream, x, x, g);
+            launch_zsolve_e(zslab_e, ZS_DIST, false, nzl, g.ntiles, stream, x, x, g, s_own);
         } else {
-            zs_dist_line_kernel<T><<<egrid, 256, 0, stream>>>(x, x, L, n[0], nzl, za);
+            zs_dist_line_kernel<T><<<egrid, 256, 0, stream>>>(x, x, L, n[0], nzl, za, s_own);
         }
         ++launches;
         CPC_CUDA(cudaGetLastError());

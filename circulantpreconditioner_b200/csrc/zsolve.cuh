@@ -57,6 +57,52 @@ __device__ __forceinline__ long long zs_line_of(const ZSolveArgs &a, long long t
     return x + (long long)nx * y;
 }
 
+// Signals between the ranks of a z-slab plan, carried by the kernels themselves instead of separate barrier launches
+// (dist.cu keeps the flag arrays: flags[s] = last epoch rank s signalled to this rank, written over NVLink).
+//   zs_signal_when_grid_done: every block fences its (peer) stores and counts itself; the last one to finish stores the
+//                             epoch into every peer's flag array -- "this kernel's output has landed everywhere".
+//   zs_wait_for_peers:        the first warp of every block waits until every rank's flag has reached the epoch.
+// A wait gives up after ~2 s and raises *timeout (a dead peer must not hang the GPU); nranks == 0 disables both.
+struct FlagSync {
+    unsigned long long *peer[CPC_MAX_PEERS];      // every rank's flag array (IPC-mapped), this group
+    unsigned long long *mine;                     // this rank's flag array
+    unsigned long long epoch;
+    int *counter;                                 // blocks of the signalling kernel that have finished
+    int *timeout;
+    int nranks, rank;
+};
+
+__device__ __forceinline__ void zs_wait_for_peers(const FlagSync &f)
+{
+    if (f.nranks == 0) return;
+    if (threadIdx.x < (unsigned)f.nranks) {
+        const long long t0 = clock64();
+        unsigned long long seen = 0;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(f.mine + threadIdx.x) : "memory");
+            if (seen >= f.epoch) break;
+            if (clock64() - t0 > 4000000000ll) { *f.timeout = 1; break; }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void zs_signal_when_grid_done(const FlagSync &f)
+{
+    if (f.nranks == 0) return;
+    __threadfence_system();                       // this thread's stores (to peers too) before the block counts itself
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(f.counter, 1);
+        if (done == (int)gridDim.x - 1) {
+            __threadfence_system();               // ... and every other block's, before the flags
+            *f.counter = 0;
+            for (int q = 0; q < f.nranks; ++q)
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.peer[q] + f.rank), "l"(f.epoch) : "memory");
+        }
+    }
+}
+
 enum ZSolveKind {
     ZS_CYCLIC = 0,    // the whole z line is in the tile: close the cycle inside the kernel (single GPU, transposed slabs)
     ZS_DIST = 2       // z-slab plans: the local part of the line with the carry-in computed by zs_carry_owner_kernel
@@ -100,9 +146,10 @@ template <int E> struct ZSolveMaxThreads { static constexpr int v = (E >= 16) ? 
 
 template <typename T, int E, bool GEN, int KIND = ZS_CYCLIC>
 __global__ void __launch_bounds__((ZSolveMaxThreads<E>::v), 1)
-zsolve_kernel(const cplx_t<T> *in, cplx_t<T> *out, const PassGeom g, const ZSolveArgs a)
+zsolve_kernel(const cplx_t<T> *in, cplx_t<T> *out, const PassGeom g, const ZSolveArgs a, const FlagSync wait)
 {
     using CS = cplx_t<T>;                           // storage type
+    if constexpr (KIND == ZS_DIST) zs_wait_for_peers(wait);       // the carry-ins have landed (zs_carry_owner_kernel)
     using C = double2;                              // arithmetic type
     constexpr int TX = 128 / (int)sizeof(CS);       // lanes = lines per tile
     constexpr int QW = 32 / TX;                     // segments per warp
@@ -256,53 +303,56 @@ struct ZCarryPeers {
 template <typename T>
 __global__ void __launch_bounds__(256)
 zs_end_accum_kernel(const cplx_t<T> *__restrict__ x, long long lines, int nx, int zb, int zc, int carry_in, int trunc,
-                    double2 *__restrict__ e, const ZSolveArgs a, int push_rank, long long lsub, ZCarryPeers gpeer)
+                    double2 *__restrict__ e, const ZSolveArgs a, int push_rank, long long lsub, ZCarryPeers gpeer,
+                    const FlagSync done)
 {
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= lines / nx * a.xsn) return;
-    int lx, ly;
-    const long long line = zs_line_of(a, t, nx, lx, ly);
-    double2 r, c;
-    zs_coeffs(a, lx, ly, r, c);
-    int k = 0;
-    if (trunc) {
-        const double c2 = c.x * c.x + c.y * c.y;                  // |c|^2 < 1
-        // |c|^m <= 1e-17  <=>  m >= ln(1e-17) / ln|c| = -78.3 / ln(|c|^2)
-        const double m = c2 > 0.0 ? -78.3 / log(c2) + 1.0 : 1.0;
-        if (m < (double)zc) k = zc - (int)m;
-        // whole groups of 16 planes (the extra planes only carry less weight): no one-plane-at-a-time remainder
-        k = zc - ((zc - k + 15) & ~15);
-        if (k < 0) k = 0;
-    }
-    double2 acc = (carry_in && k == 0) ? e[line] : make_double2(0.0, 0.0);
-    const cplx_t<T> *p = x + (long long)zb * lines + line;
-    // 16 planes in flight per thread: the kernel's duration is the longest line's (the few low-frequency lines that
-    // need every plane), i.e. (planes / planes in flight) DRAM latencies (ncu: 221 us for 1024 planes with 8 in flight)
-    for (; k + 16 <= zc; k += 16) {
-        double2 v[16];
+    if (t < lines / nx * a.xsn) {
+        int lx, ly;
+        const long long line = zs_line_of(a, t, nx, lx, ly);
+        double2 r, c;
+        zs_coeffs(a, lx, ly, r, c);
+        int k = 0;
+        if (trunc) {
+            const double c2 = c.x * c.x + c.y * c.y;                  // |c|^2 < 1
+            // |c|^m <= 1e-17  <=>  m >= ln(1e-17) / ln|c| = -78.3 / ln(|c|^2)
+            const double m = c2 > 0.0 ? -78.3 / log(c2) + 1.0 : 1.0;
+            if (m < (double)zc) k = zc - (int)m;
+            // whole groups of 16 planes (the extra planes only carry less weight): no one-plane-at-a-time remainder
+            k = zc - ((zc - k + 15) & ~15);
+            if (k < 0) k = 0;
+        }
+        double2 acc = (carry_in && k == 0) ? e[line] : make_double2(0.0, 0.0);
+        const cplx_t<T> *p = x + (long long)zb * lines + line;
+        // 16 planes in flight per thread: the kernel's duration is the longest line's (the few low-frequency lines that
+        // need every plane), i.e. (planes / planes in flight) DRAM latencies (ncu: 221 us for 1024 planes with 8 in flight)
+        for (; k + 16 <= zc; k += 16) {
+            double2 v[16];
 #pragma unroll
-        for (int m = 0; m < 16; ++m) v[m] = to_d2(p[(long long)(k + m) * lines]);
+            for (int m = 0; m < 16; ++m) v[m] = to_d2(p[(long long)(k + m) * lines]);
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            const double2 t = acc;
-            acc.x = fma(c.x, t.x, fma(-c.y, t.y, v[m].x));
-            acc.y = fma(c.x, t.y, fma(c.y, t.x, v[m].y));
+            for (int m = 0; m < 16; ++m) {
+                const double2 tt = acc;
+                acc.x = fma(c.x, tt.x, fma(-c.y, tt.y, v[m].x));
+                acc.y = fma(c.x, tt.y, fma(c.y, tt.x, v[m].y));
+            }
+        }
+        for (; k < zc; ++k) {
+            const double2 v = to_d2(p[(long long)k * lines]), tt = acc;
+            acc.x = fma(c.x, tt.x, fma(-c.y, tt.y, v.x));
+            acc.y = fma(c.x, tt.y, fma(c.y, tt.x, v.y));
+        }
+        if (push_rank >= 0) {
+            const int q = (int)(line / lsub);
+            gpeer.p[q][(long long)push_rank * lsub + (line - (long long)q * lsub)] = acc;
+        } else if (push_rank == -2) {
+            const double2 cn = cpow_rt(c, zc);
+            e[line] = cmul(acc, crecip_scaled<double>(make_double2(1.0 - cn.x, -cn.y), 1.0));
+        } else {
+            e[line] = acc;
         }
     }
-    for (; k < zc; ++k) {
-        const double2 v = to_d2(p[(long long)k * lines]), t = acc;
-        acc.x = fma(c.x, t.x, fma(-c.y, t.y, v.x));
-        acc.y = fma(c.x, t.y, fma(c.y, t.x, v.y));
-    }
-    if (push_rank >= 0) {
-        const int q = (int)(line / lsub);
-        gpeer.p[q][(long long)push_rank * lsub + (line - (long long)q * lsub)] = acc;
-    } else if (push_rank == -2) {
-        const double2 cn = cpow_rt(c, zc);
-        e[line] = cmul(acc, crecip_scaled<double>(make_double2(1.0 - cn.x, -cn.y), 1.0));
-    } else {
-        e[line] = acc;
-    }
+    zs_signal_when_grid_done(done);                // "this rank's end values have landed at their owners"
 }
 
 // Second sweep for slabs whose plane count fits no tile form of zsolve_kernel (nz / P = 8 planes at 8 ranks of a 64^3
@@ -311,9 +361,11 @@ zs_end_accum_kernel(const cplx_t<T> *__restrict__ x, long long lines, int nx, in
 // touches its own line and reads a plane before it writes it).  Also the second sweep of the single-rank line form.
 template <typename T>
 __global__ void __launch_bounds__(256)
-zs_dist_line_kernel(const cplx_t<T> *in, cplx_t<T> *x, long long lines, int nx, int nzl, const ZSolveArgs a)
+zs_dist_line_kernel(const cplx_t<T> *in, cplx_t<T> *x, long long lines, int nx, int nzl, const ZSolveArgs a,
+                    const FlagSync wait)
 {
     using CS = cplx_t<T>;
+    zs_wait_for_peers(wait);                       // the carry-ins have landed (zs_carry_owner_kernel)
     const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= lines / nx * a.xsn) return;
     int lx, ly;
@@ -353,6 +405,7 @@ zs_dist_line_kernel(const cplx_t<T> *in, cplx_t<T> *x, long long lines, int nx, 
 // only into this rank's when self_only (fallback without peer mapping: every rank owns all lines).
 __global__ void __launch_bounds__(256)
 zs_carry_owner_kernel(const double2 *__restrict__ gbuf, long long gstride, long long line0, long long count, int nx,
-                      int nzl, int nranks, int rank, int self_only, ZCarryPeers zpeer, const ZSolveArgs a);
+                      int nzl, int nranks, int rank, int self_only, ZCarryPeers zpeer, const ZSolveArgs a,
+                      const FlagSync wait, const FlagSync done);
 
 }  // namespace cpc

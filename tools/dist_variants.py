@@ -15,9 +15,9 @@ nzl = n // world
 b = torch.randn(n * n * nzl, dtype=torch.float64, device="cuda").to(torch.complex128)
 x = torch.empty_like(b)
 os.environ["CPC_TUNING"] = "1"
-VARIANTS = [{}, {"CPC_XSPLIT": "1"}, {"CPC_FLAG_BARRIER": "0"}, {"CPC_END_TRUNC": "0"}]
+VARIANTS = [{}, {"CPC_FUSED_SYNC": "0"}, {"CPC_XSPLIT": "1"}, {"CPC_FLAG_BARRIER": "0"}]
 for var in VARIANTS:
-    for k in ("CPC_ZSLAB_LINE", "CPC_END_TRUNC", "CPC_FLAG_BARRIER", "CPC_XSPLIT"):
+    for k in ("CPC_ZSLAB_LINE", "CPC_END_TRUNC", "CPC_FLAG_BARRIER", "CPC_XSPLIT", "CPC_FUSED_SYNC"):
         os.environ.pop(k, None)
     os.environ.update(var)
     idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
