@@ -249,9 +249,12 @@ template <typename T> struct PlanT : PlanBase {
     // barrier groups) and nx divisible by two tile widths.  Measured at 512^3 on 2 GPUs: 1.80 ms against 1.73 ms for
     // the serial schedule -- the three extra kernel tails cost more than the hidden exchange saves; kept for larger grids.
     bool xsplit = false;
-    // The kernels of the carry exchange signal and wait themselves (zsolve.cuh FlagSync) instead of separate barrier
-    // launches between them: END -> owner -> solve is three launches, not five.
-    bool fused_sync = true;
+    // Optional (tuning hook CPC_FUSED_SYNC=1, off by default): the kernels of the carry exchange signal and wait
+    // themselves (zsolve.cuh FlagSync) instead of separate barrier launches between them: END -> owner -> solve is
+    // three launches, not five.  Measured at 512^3: no gain on 2 GPUs (1.75 vs 1.73 ms) and a loss on 8 (0.536 vs
+    // 0.508 ms): every block of the signalling kernels pays a system-scope fence behind its NVLink stores, which costs
+    // more than the two 1-CTA barrier launches it replaces (profiles/r02_variants_n8.log).
+    bool fused_sync = false;
     cudaStream_t xstream = nullptr;
     cudaEvent_t xs_ev[4] = {};
     int zslab_e = 0;              // points per thread for nz / P point lines (0: no tile form fits -> one thread per line)
