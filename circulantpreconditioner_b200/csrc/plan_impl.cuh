@@ -326,7 +326,6 @@ template <typename T> struct PlanT : PlanBase {
         real = (desc.dtype == CPC_F64 || desc.dtype == CPC_F32);
         if (real) {
             if (nc != 1) { set_error("real-scalar plans need ncomp == 1"); return CPC_ERR_ARG; }
-            if (desc.nranks != 1) { set_error("real-scalar plans are single-rank in this version"); return CPC_ERR_UNSUPPORTED; }
         }
         // z-slabs need nz divisible by the ranks; ny too only for the transposing schedule (checked when it is chosen)
         if (desc.nranks > 1 && n[2] % desc.nranks != 0) {
@@ -340,9 +339,10 @@ template <typename T> struct PlanT : PlanBase {
             if (n[0] % 2 == 0 && reg.find(FastKey<T>(n2, VAR_XMAP, MODE_R2C)) != reg.end()) {
                 nxp = (n2 + 1 + 7) / 8 * 8;
                 wx = nxp;
-                CPC_CUDA(cudaMalloc(&work, sizeof(C) * (size_t)nxp * n[1] * n[2]));
-                CPC_CUDA(cudaMemset(work, 0, sizeof(C) * (size_t)nxp * n[1] * n[2]));
+                CPC_CUDA(cudaMalloc(&work, sizeof(C) * (size_t)nxp * n[1] * nzl));        // this rank's planes
+                CPC_CUDA(cudaMemset(work, 0, sizeof(C) * (size_t)nxp * n[1] * nzl));
             } else {
+                if (desc.nranks != 1) { set_error("multi-rank real-scalar plans need an even nx with an r2c kernel (nx=%d)", n[0]); return CPC_ERR_UNSUPPORTED; }
                 real_promote = true;         // odd or unsupported nx: run the complex path on a promoted copy
                 CPC_CUDA(cudaMalloc(&work, sizeof(C) * (size_t)nloc));
             }
@@ -547,9 +547,9 @@ template <typename T> struct PlanT : PlanBase {
             want_p2p = !(mode && strcmp(mode, "nccl") == 0) && desc.nranks <= CPC_MAX_PEERS;
             const char *fb = tune("CPC_FLAG_BARRIER");
             if (want_p2p && !(fb && atoi(fb) == 0) && (rc = dist_flag_barrier_init(dist, device, stream))) return rc;
-            if (!real && nc == 1) {
+            if (nc == 1) {
                 zslab_e = zsolve_points_per_thread(nzl);
-                const long long L = (long long)n[0] * n[1];
+                const long long L = wx * n[1];        // (kx, ky) lines: nx ny, or the padded half spectrum of a real plan
                 lsub = (L + desc.nranks - 1) / desc.nranks;
                 CPC_CUDA(cudaMalloc(&ebuf, sizeof(double2) * (size_t)L));
                 CPC_CUDA(cudaMalloc(&zinbuf, sizeof(double2) * (size_t)L));
@@ -1376,7 +1376,7 @@ template <typename T> struct PlanT : PlanBase {
     // x and y transformed, the halves whole tiles of the y pass)
     bool xsplit_ok() const
     {
-        return xsplit && xstream && carry_p2p && dist.flag_barrier && n[0] > 1 && n[1] > 1 && l2_chunk_bytes <= 0 &&
+        return xsplit && xstream && !real && carry_p2p && dist.flag_barrier && n[0] > 1 && n[1] > 1 && l2_chunk_bytes <= 0 &&
                cfg[1].tx > 0 && n[0] % (2 * cfg[1].tx) == 0 && (long long)n[0] * n[1] >= 65536;
     }
 
@@ -1429,49 +1429,39 @@ template <typename T> struct PlanT : PlanBase {
         return run_pass(0, MODE_INV, x, x, 0, nzl, 0, stream);
     }
 
-    int apply_device_zslab(const C *b, C *x, float *pass_ms, int *npasses)
+    // The z part of the z-slab schedule on array x (rows of wx complex numbers: nx, or the padded half spectrum of a
+    // real plan), behind the forward y pass: end-value sweep, carry exchange, second sweep.  Profile kinds 2, 3, 4.
+    int zslab_middle(C *x)
     {
         int rc;
-        // (per-pass profiling keeps the serial schedule: its pass kinds would overlap in the pipelined one)
-        if (!pass_ms && xsplit_ok()) return apply_device_zslab_xsplit(b, x);
-        if ((rc = prof_begin(pass_ms))) return rc;
-        const long long L = (long long)n[0] * n[1];
+        const long long L = wx * n[1];
+        const int nxw = (int)wx;
         ZSolveArgs za = zsolve_args();
         za.nline = nzl;
-        const int kf[2] = { 0, 1 }, kb[2] = { 5, 6 };
         const int egrid = (int)((L + 255) / 256);
         ZCarryPeers gp{}, zp{};
         for (int q = 0; q < desc.nranks; ++q) { gp.p[q] = (double2 *)peer_g[q]; zp.p[q] = (double2 *)peer_z[q]; }
-        // With peers mapped the exchange needs no separate barrier launches: the end-value sweep signals "landed at the
-        // owners" when its last block finishes, the owner kernel waits for every rank's signal, pushes the carry-ins and
-        // signals in turn, and the second sweep waits for that (FlagSync, zsolve.cuh).
+        // With peers mapped and CPC_FUSED_SYNC the exchange needs no separate barrier launches: the end-value sweep
+        // signals "landed at the owners" when its last block finishes, the owner kernel waits for every rank's signal,
+        // pushes the carry-ins and signals in turn, and the second sweep waits for that (FlagSync, zsolve.cuh).
         const bool fused = carry_p2p && dist.flag_barrier && fused_sync;
         const FlagSync none{};
         const FlagSync s_end = fused ? make_sync(0, ++dist.epoch[0]) : none;
         const FlagSync s_own = fused ? make_sync(1, ++dist.epoch[1]) : none;
-        // the end values of the last chunk go straight to the ranks that own the lines (peer stores) when peers are mapped
-        auto end_acc = [&](int zb, int zc, cudaStream_t st) -> int {
-            const bool last = zb + zc >= nzl;
-            zs_end_accum_kernel<T><<<egrid, 256, 0, st>>>(x, L, n[0], zb, zc, zb > 0 ? 1 : 0, end_trunc ? 1 : 0, ebuf, za,
-                                                          (carry_p2p && last) ? desc.rank : -1, lsub, gp, last ? s_end : none);
-            ++launches;
-            CPC_CUDA(cudaGetLastError());
-            return prof_mark(2);
-        };
-        // the end values chain from chunk to chunk, so the chunks stay on one stream
-        const int cs = chain_streams;
-        chain_streams = 1;
-        rc = run_xy(true, b, x, kf, end_acc);
-        chain_streams = cs;
-        if (rc) return rc;
+        // the end values go straight to the ranks that own the lines (peer stores) when peers are mapped
+        zs_end_accum_kernel<T><<<egrid, 256, 0, stream>>>(x, L, nxw, 0, nzl, 0, end_trunc ? 1 : 0, ebuf, za,
+                                                          carry_p2p ? desc.rank : -1, lsub, gp, s_end);
+        ++launches;
+        CPC_CUDA(cudaGetLastError());
+        if ((rc = prof_mark(2))) return rc;
         const int cgrid = 148 * 8;
         if (carry_p2p) {
             if (!fused && (rc = dist_barrier(dist, stream))) return rc;  // every rank's end values have landed
             const long long line0 = lsub * desc.rank;
             const long long cnt = line0 >= L ? 0 : (L - line0 < lsub ? L - line0 : lsub);
-            // (launched even without lines of its own: the peers wait for this rank's signal)
+            // (launched even without lines of its own: with fused signals the peers wait for this rank's)
             zs_carry_owner_kernel<<<(int)((cnt + 255) / 256 > 0 ? (cnt + 255) / 256 : 1), 256, 0, stream>>>(
-                gbuf, lsub, line0, cnt, n[0], nzl, desc.nranks, desc.rank, 0, zp, za, s_end, s_own);
+                gbuf, lsub, line0, cnt, nxw, nzl, desc.nranks, desc.rank, 0, zp, za, s_end, s_own);
             ++launches;
             CPC_CUDA(cudaGetLastError());
             if (!fused && (rc = dist_barrier(dist, stream))) return rc;  // every line's carry-in has landed
@@ -1479,7 +1469,7 @@ template <typename T> struct PlanT : PlanBase {
             if ((rc = dist_allgather(dist, ebuf, gbuf, sizeof(double2) * (size_t)L, stream))) return rc;
             ZCarryPeers zl{};
             zl.p[0] = zinbuf;
-            zs_carry_owner_kernel<<<cgrid, 256, 0, stream>>>(gbuf, L, 0, L, n[0], nzl, desc.nranks, desc.rank, 1, zl, za, none, none);
+            zs_carry_owner_kernel<<<cgrid, 256, 0, stream>>>(gbuf, L, 0, L, nxw, nzl, desc.nranks, desc.rank, 1, zl, za, none, none);
             ++launches;
             CPC_CUDA(cudaGetLastError());
         }
@@ -1489,11 +1479,22 @@ template <typename T> struct PlanT : PlanBase {
             const PassGeom g = make_geom(2, 128 / (int)sizeof(C), 0, nzl, 0, &off);
             launch_zsolve_e(zslab_e, ZS_DIST, false, nzl, g.ntiles, stream, x, x, g, s_own);
         } else {
-            zs_dist_line_kernel<T><<<egrid, 256, 0, stream>>>(x, x, L, n[0], nzl, za, s_own);
+            zs_dist_line_kernel<T><<<egrid, 256, 0, stream>>>(x, x, L, nxw, nzl, za, s_own);
         }
         ++launches;
         CPC_CUDA(cudaGetLastError());
-        if ((rc = prof_mark(4))) return rc;
+        return prof_mark(4);
+    }
+
+    int apply_device_zslab(const C *b, C *x, float *pass_ms, int *npasses)
+    {
+        int rc;
+        // (per-pass profiling keeps the serial schedule: its pass kinds would overlap in the pipelined one)
+        if (!pass_ms && xsplit_ok()) return apply_device_zslab_xsplit(b, x);
+        if ((rc = prof_begin(pass_ms))) return rc;
+        const int kf[2] = { 0, 1 }, kb[2] = { 5, 6 };
+        if ((rc = run_xy(true, b, x, kf, no_after))) return rc;
+        if ((rc = zslab_middle(x))) return rc;
         if ((rc = run_xy(false, x, x, kb, no_after))) return rc;
         return prof_end(pass_ms, npasses, 7);
     }
@@ -1613,7 +1614,11 @@ template <typename T> struct PlanT : PlanBase {
     {
         int rc;
         if ((rc = prof_begin(pass_ms))) return rc;
-        const long long N = (long long)n[0] * n[1] * n[2];
+        const long long N = (long long)n[0] * n[1] * nzl;
+        if (desc.nranks > 1 && !use_zslab()) {
+            set_error("multi-rank real-scalar plans run the transpose-free z-slab schedule only (transport / upwind-z separable symbol)");
+            return CPC_ERR_UNSUPPORTED;
+        }
         if (real_promote) {
             real_to_complex_kernel<T><<<1184, 256, 0, stream>>>(b, work, N);
             ++launches;
@@ -1629,11 +1634,13 @@ template <typename T> struct PlanT : PlanBase {
             return prof_end(pass_ms, npasses, 1);
         }
         int k = 0;
+        const bool multi = desc.nranks > 1;
+        if (multi && prof_on) { prof_on = false; set_error("profiled apply: single-rank real plans only"); return CPC_ERR_UNSUPPORTED; }
         const int kx0 = k++, ky0 = n[1] > 1 ? k++ : -1, kz = k++, ky1 = n[1] > 1 ? k++ : -1, kx1 = k++;
         const int cp = chain_planes();
-        const int step = cp > 0 ? cp : n[2];
-        for (int zb = 0; zb < n[2]; zb += step) {
-            const int zc = n[2] - zb < step ? n[2] - zb : step;
+        const int step = cp > 0 ? cp : nzl;
+        for (int zb = 0; zb < nzl; zb += step) {
+            const int zc = nzl - zb < step ? nzl - zb : step;
             if ((rc = run_real_x(true, b, work, zb, zc, stream))) return rc;
             if ((rc = prof_mark(kx0))) return rc;
             if (n[1] > 1) {
@@ -1641,10 +1648,14 @@ template <typename T> struct PlanT : PlanBase {
                 if ((rc = prof_mark(ky0))) return rc;
             }
         }
-        if ((rc = run_pass(2, fused_mode(), work, work, 0, n[2], 0, stream))) return rc;
-        if ((rc = prof_mark(kz))) return rc;
-        for (int zb = 0; zb < n[2]; zb += step) {
-            const int zc = n[2] - zb < step ? n[2] - zb : step;
+        if (multi) {
+            if ((rc = zslab_middle(work))) return rc;        // half-spectrum lines: carries exchanged between the slabs
+        } else {
+            if ((rc = run_pass(2, fused_mode(), work, work, 0, n[2], 0, stream))) return rc;
+            if ((rc = prof_mark(kz))) return rc;
+        }
+        for (int zb = 0; zb < nzl; zb += step) {
+            const int zc = nzl - zb < step ? nzl - zb : step;
             if (n[1] > 1) {
                 if ((rc = run_pass(1, MODE_INV, work, work, zb, zc, 0, stream))) return rc;
                 if ((rc = prof_mark(ky1))) return rc;
@@ -1657,7 +1668,7 @@ template <typename T> struct PlanT : PlanBase {
 
     int apply_real(const void *b, void *x, int mem_kind, float *pass_ms, int *npasses)
     {
-        const size_t bytes = sizeof(T) * (size_t)n[0] * n[1] * n[2];
+        const size_t bytes = sizeof(T) * (size_t)n[0] * n[1] * nzl;
         if (mem_kind == CPC_MEM_DEVICE) return apply_device_real((const T *)b, (T *)x, pass_ms, npasses);
         int rc = ensure_dbuf();        // nloc complex >= N reals
         if (rc) return rc;

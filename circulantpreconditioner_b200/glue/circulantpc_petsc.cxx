@@ -137,13 +137,14 @@ PetscErrorCode CPCMatAttachPlan(Mat A, MPI_Comm comm, PetscInt n_x, PetscInt n_y
         (void)id;
 #endif
     }
-    // PetscScalar of a complex build is complex128; a real build takes the r2c / c2r plan
-#if defined(PETSC_USE_COMPLEX)
-    const int dtype = CPC_C128;
-#else
-    const int dtype = CPC_F64;
+    // The glue follows the complex-scalar branch of the reference (FftLinearSolver_3D.c:173-175,183-184), the one whose
+    // semantics are defined: PetscScalar = complex128.  A real-scalar PETSc build is served by CPC_F64 / CPC_F32 plans
+    // at the C-ABI level (r2c / c2r inside the x pass); the reference's own real branch (:7-78,176,186) is unfinished
+    // and its eigenvalue Vecs have no defined layout there, so this file refuses to pretend.
+#if !defined(PETSC_USE_COMPLEX)
+#error "circulantpc_petsc.cxx needs a complex-scalar PETSc build; real builds use the CPC_F64 plans of include/circulantpc.h directly"
 #endif
-    cpc_plan_desc d = { (int)n_x, (int)n_y, (int)n_z, 1, dtype, size, rank, idp, nullptr, -1 };
+    cpc_plan_desc d = { (int)n_x, (int)n_y, (int)n_z, 1, CPC_C128, size, rank, idp, nullptr, -1 };
     cpc_plan plan = nullptr;
     PetscCallCPC(cpc_plan_create(&plan, &d));
     CpcMatData *data = (CpcMatData *)calloc(1, sizeof(CpcMatData));

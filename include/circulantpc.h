@@ -47,7 +47,8 @@ enum cpc_dtype {
     CPC_C64 = 1,              /* fp32 option: complex64 in/out */
     CPC_F64 = 2,              /* PetscScalar of a real PETSc build: float64 in, float64 out; r2c / c2r inside, half
                                  the bytes per pass (the reference's unfinished real branch, FftLinearSolver_3D.c:7-78,
-                                 176,186).  ncomp == 1, single rank, transport / separable symbol. */
+                                 176,186).  ncomp == 1, transport / separable symbol; multi-rank plans (z-slabs, even
+                                 nx) run the transpose-free recurrence schedule only. */
     CPC_F32 = 3               /* float32 in/out */
 };
 

@@ -254,3 +254,51 @@ def test_multi_rank_pcshell_boundary(P):
     assert len(errs) == P
     for r, (e, nranks, mode, kind) in dict(errs).items():
         assert e < 1e-12 and nranks == P and mode == 3 and kind == 1, (r, e, nranks, mode, kind)
+
+
+# ---- real-scalar plans on z-slabs (PetscScalar of a real PETSc build; r2c / c2r inside the x pass, the carry exchange on
+# the half spectrum) ----
+def _worker_real(rank, P, port, shape, lam, b_full, want, dtype, errs):
+    import circulantpreconditioner_b200 as cpc
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=P, device_id=torch.device("cuda", rank))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.frombuffer(bytearray(cpc.nccl_unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(idt, 0)
+    nx, ny, nz = shape
+    z0, nzl = cpc.slab_range(nz, P, rank)
+    plane = nx * ny
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    loc = torch.from_numpy(b_full[z0 * plane:(z0 + nzl) * plane].copy()).to(tdt).cuda()
+    with cpc.CirculantPlan(nx, ny, nz, dtype=dtype, nranks=P, rank=rank, nccl_id=idt.cpu().numpy().tobytes()) as p:
+        p.set_symbol_transport(*lam)
+        assert p.info()["dist_mode"] == 3
+        out = p.apply(loc)
+        e1 = np.linalg.norm(out.cpu().numpy() - want[z0 * plane:(z0 + nzl) * plane]) / np.linalg.norm(want)
+        hb = loc.cpu().numpy()
+        hx = np.empty_like(hb)
+        p.apply(hb, hx)                                   # host pointers
+        e2 = np.linalg.norm(hx - want[z0 * plane:(z0 + nzl) * plane]) / np.linalg.norm(want)
+    errs[rank] = (float(e1), float(e2))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-12), ("f32", 1e-5)])
+def test_two_rank_real_scalar_plan(dtype, tol):
+    from oracle import circulant_oracle as O
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    shape, lam = (64, 32, 128), (55.5556, 0.3, 2.5)
+    nx, ny, nz = shape
+    rng = np.random.default_rng(31)
+    b = rng.standard_normal(nx * ny * nz)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b.astype(np.complex128)).real
+    mgr = mp.Manager()
+    errs = mgr.dict()
+    mp.spawn(_worker_real, args=(2, 29900 + (os.getpid() % 2000), shape, lam, b, want, dtype, errs), nprocs=2, join=True)
+    assert len(errs) == 2
+    for r, (e1, e2) in dict(errs).items():
+        assert e1 < tol and e2 < tol, (r, e1, e2)
