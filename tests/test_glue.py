@@ -42,6 +42,28 @@ def test_glue_exports_reference_names():
         assert any(line.split(" T ")[-1].startswith(n + "(") for line in syms.splitlines() if " T " in line), n
 
 
+def test_glue_fails_loudly_without_a_gpu():
+    """No CPU fallback anywhere on the product path: on a box without a CUDA device MatCreateFFT (the plan behind the
+    reference's FFT Mat) must return a PETSc error that says so -- not a Mat that computes on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    ensure_built()
+    from circulantpreconditioner_b200 import glue_binding as G
+    L = G.lib()
+    L.MatCreateFFT.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p,
+                               ctypes.POINTER(ctypes.c_void_p)]
+    mat = ctypes.c_void_p()
+    dims = (ctypes.c_int * 3)(8, 8, 8)
+    ierr = L.MatCreateFFT(0, 3, dims, b"fftw", ctypes.byref(mat))
+    assert ierr != 0 and not mat.value
+    assert b"no CPU fallback" in L.ShimLastError() or b"CUDA" in L.ShimLastError()
+    # the host-side object model of the stand-in works without a GPU (Vecs, views)
+    v = G.Vec.create_host(6)
+    v.numpy()[:] = np.arange(6) * (1 + 1j)
+    assert v.local_size() == 6 and v.numpy()[5] == 5 + 5j
+
+
 def test_forwarding_headers_carry_reference_file_names():
     for h in ("FftLinearSolver_3D.h", "PCSHELLFft_3D.hxx"):
         assert "circulantpc_petsc.h" in open(os.path.join(GLUE, h)).read()
