@@ -203,6 +203,57 @@ def FftTransportSolver_z_recurrence(n_x, n_y, n_z, lambda_x, lambda_y, lambda_z,
     return X.reshape(-1)
 
 
+def FftTransportSolver_z_line_form(n_x, n_y, n_z, lambda_x, lambda_y, lambda_z, b, weight_floor=1e-17, slabs=1):
+    """The recurrence form as the CUDA line kernels evaluate it (csrc/zsolve.cuh: zs_end_accum_kernel,
+    zs_carry_owner_kernel, zs_dist_line_kernel), restated so that its one approximation is pinned on the CPU:
+
+    * the carry into the first plane of a slab is summed only over the planes whose weight ``|c|^m`` can still reach
+      ``weight_floor`` (in whole groups of 16 planes, like the kernel), the rest being below the rounding of the sum;
+    * with ``slabs = P`` the line is cut into P z-slabs: every slab's end value from a zero carry-in, the cycle closed
+      over the slabs by the line's owner (``Zin_0`` by Horner, ``Zin_{r+1} = e_r + c^(nz/P) Zin_r``), then every slab
+      solved from its carry-in -- the multi-rank schedule; ``slabs = 1`` is the single-GPU line form.
+    Same operator as solve_3D (FftLinearSolver_3D.c:166-190) to rounding."""
+    b3 = np.asarray(b, dtype=np.complex128).reshape(n_z, n_y, n_x)
+    cx = np.fft.fft(build_transport_col(n_x))
+    cy = np.fft.fft(build_transport_col(n_y))
+    alpha = (1.0 + lambda_x * cx[None, :] + lambda_y * cy[:, None]).reshape(-1)
+    if lambda_z < 0 or alpha.real.min() < 0.5:
+        raise ValueError("the recurrence form needs lambda_z >= 0 and Re(alpha) >= 1/2")
+    if n_z % slabs:
+        raise ValueError("n_z must be divisible by the number of slabs")
+    bh = np.fft.fft(np.fft.fft(b3, axis=2), axis=1).reshape(n_z, -1)
+    r = 1.0 / (alpha + lambda_z)
+    c = lambda_z * r
+    nzl = n_z // slabs
+    # planes of a slab that still matter, per line
+    c2 = np.abs(c) ** 2
+    with np.errstate(divide="ignore"):
+        m = np.where(c2 > 0, np.log(weight_floor ** 2) / np.log(np.where(c2 > 0, c2, 0.5)) + 1.0, 1.0)
+    start = np.where(m < nzl, nzl - m.astype(np.int64), 0)
+    start = np.maximum(nzl - ((nzl - start + 15) // 16) * 16, 0)
+    ends = np.zeros((slabs, alpha.size), dtype=np.complex128)
+    for s_ in range(slabs):                   # end value of every slab from a zero carry-in, truncated sum
+        acc = np.zeros(alpha.size, dtype=np.complex128)
+        for k in range(nzl):
+            live = k >= start
+            acc = np.where(live, c * acc + bh[s_ * nzl + k], 0.0)
+        ends[s_] = acc
+    cL = c ** nzl
+    acc = np.zeros(alpha.size, dtype=np.complex128)
+    for s_ in range(slabs):                   # owner: Zin_0 by Horner over e_0 .. e_{P-1}, closed cyclically
+        acc = cL * acc + ends[s_]
+    Z = acc / (1.0 - cL ** slabs)
+    y = np.empty_like(bh)
+    for s_ in range(slabs):                   # second sweep of every slab from its carry-in
+        acc = Z.copy()
+        for k in range(nzl):
+            acc = c * acc + bh[s_ * nzl + k]
+            y[s_ * nzl + k] = acc * r
+        Z = ends[s_] + cL * Z                 # Zin_{r+1} = e_r + cL Zin_r
+    X = np.fft.ifft(np.fft.ifft(y.reshape(n_z, n_y, n_x), axis=1), axis=2)
+    return X.reshape(-1)
+
+
 def Fft3DTransportSolver(n_x, n_y, n_z, a_x, a_y, a_z, dt, delta_x, delta_y, delta_z, b, workers=1, naive=False):
     """``lambda_d = a_d * dt / delta_d`` (FftLinearSolver_3D.c:266-281)."""
     return FftTransportSolver(n_x, n_y, n_z, a_x * dt / delta_x, a_y * dt / delta_y, a_z * dt / delta_z,

@@ -201,3 +201,24 @@ def test_oracle_properties_random_shapes():
         assert rel_l2(CO.transport_solve_z_recurrence(nx, ny, nz, lx, ly, lz, b1), s1) < tol
 
     check()
+
+
+# the line form of the middle pass (one thread per z line, carry-in summed over the planes that can still matter) and the
+# multi-rank owner scheme, restated in numpy: the truncation is below rounding, the slab closure is exact
+@pytest.mark.parametrize("shape", [(6, 5, 64), (4, 4, 200), (8, 3, 96)])
+@pytest.mark.parametrize("lam", [(55.5556, 55.5556, 55.5556), (0.6, 0.15, 3000.0), (2.0, 0.5, 0.0)])
+@pytest.mark.parametrize("slabs", [1, 2, 4])
+def test_z_line_form_equals_fft_form(shape, lam, slabs):
+    nx, ny, nz = shape
+    rng = np.random.default_rng(nx + ny + nz + slabs)
+    b = rng.standard_normal(nx * ny * nz) + 1j * rng.standard_normal(nx * ny * nz)
+    want = O.FftTransportSolver(nx, ny, nz, *lam, b)
+    got = O.FftTransportSolver_z_line_form(nx, ny, nz, *lam, b, slabs=slabs)
+    assert rel_l2(got, want) < 1e-12
+    # the truncation itself: against the untruncated sum (weight_floor = 0) the difference is at rounding level
+    full = O.FftTransportSolver_z_line_form(nx, ny, nz, *lam, b, weight_floor=1e-300, slabs=slabs)
+    assert rel_l2(got, full) < 1e-15
+    # a careless floor would be visible: the check has teeth
+    sloppy = O.FftTransportSolver_z_line_form(nx, ny, nz, *lam, b, weight_floor=1e-3, slabs=slabs)
+    if lam[0] > 50.0 and nz >= 96 and slabs == 1:
+        assert rel_l2(sloppy, full) > 1e-9
