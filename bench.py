@@ -36,7 +36,6 @@ if int(os.environ.get("RANK", "0")) == 0 and os.environ.get("OMP_NUM_THREADS") =
     os.environ.pop("OMP_NUM_THREADS", None)
 
 import argparse
-import ctypes
 import json
 import statistics
 import subprocess
