@@ -558,3 +558,29 @@ def test_wave_block_256cube_config3():
         x = p.apply(b)
     err = (torch.linalg.vector_norm(x - y) / torch.linalg.vector_norm(y)).item()
     assert err < TOL64, err
+
+
+def test_pageable_host_arrays_go_through_the_bounce_buffers():
+    """numpy arrays are pageable memory (what a CPU-only PETSc Vec hands over): above 4 MB they are copied by several host
+    threads through pinned bounce buffers; the result must equal the device-pointer result bit for bit, in place too."""
+    nx, ny, nz = 256, 256, 96                    # 100 MB per array: several 64 MB pieces per z-chunk boundary case
+    rng = np.random.default_rng(8)
+    b = rand_c(rng, nx * ny * nz)
+    lam = (55.5556, 0.3, 2.5)
+    with cpc.CirculantPlan(nx, ny, nz) as p:
+        p.set_symbol_transport(*lam)
+        want = host(p.apply(dev(b)))
+        xh = np.empty_like(b)
+        i0 = p.info()
+        p.apply(b, xh)                             # pageable in, pageable out
+        i1 = p.info()
+        assert np.array_equal(xh, want)
+        assert i1["h2d_bytes"] - i0["h2d_bytes"] == 16 * b.size and i1["d2h_bytes"] - i0["d2h_bytes"] == 16 * b.size
+        inplace = b.copy()
+        p.apply(inplace, inplace)
+        assert np.array_equal(inplace, want)
+        pb = torch.from_numpy(b).pin_memory()      # pinned in, pageable out
+        xh2 = np.empty_like(b)
+        with pytest.raises(ValueError):
+            p.apply(pb, xh2.astype(np.complex64))
+    assert rel_l2(want, O.FftTransportSolver(nx, ny, nz, *lam, b)) < TOL64
