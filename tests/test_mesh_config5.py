@@ -139,3 +139,26 @@ def test_config5_kershaw_tetrahedra_gpu_vs_oracle():
         x_g, its_g, reason_g, hist_g = K.gmres(MS.torch_operator(A, "cuda"), torch.from_numpy(b).cuda(), M)
     assert reason_c in (2, 3) and its_g == its_c and reason_g == reason_c, (its_g, its_c, reason_g, reason_c)
     assert np.allclose(hist_g, hist_c, rtol=1e-5, atol=1e-8)
+
+
+def test_fixtures_regenerate_from_the_reference_meshes():
+    """The committed fixtures are what tests/golden/make_mesh_fixtures.py derives from the reference's own mesh files
+    (only possible where /root/reference exists: this container, not the GPU box)."""
+    import importlib.util
+    import os
+    ref = "/root/reference/meshes/3DTetrahedra_Kershaw/3DKershawTetra1.msh"
+    if not os.path.exists(ref):
+        pytest.skip("/root/reference is not available here")
+    spec = importlib.util.spec_from_file_location("make_mesh_fixtures", os.path.join(MS.GOLDEN, "make_mesh_fixtures.py"))
+    M = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(M)
+    for name, path in (("kershaw_tetra1", ref), ("hexa_3", "/root/reference/meshes/3DHexaèdres/mesh_hexa_3.msh")):
+        xyz, cells, kind = M.read_msh(path)
+        xyz, cells = M.merge_duplicate_nodes(xyz, cells)
+        centre, vol, surf, fc, fa, nborder = M.fv_geometry(xyz, cells, kind)
+        fix = MS.load_fixture(name)
+        assert np.array_equal(fc, fix["face_cells"])
+        assert np.allclose(centre, fix["centre"], rtol=0, atol=1e-15)
+        assert np.allclose(vol, fix["volume"], rtol=1e-14, atol=0)
+        assert np.allclose(surf, fix["surface"], rtol=1e-14, atol=0)
+        assert np.allclose(fa, fix["face_area"], rtol=0, atol=1e-15)
