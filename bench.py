@@ -385,6 +385,15 @@ def run_gpu(args):
         except Exception as exc:      # the glue is optional for the headline; say why it is missing
             pcshell = {"unavailable": f"{type(exc).__name__}: {exc}"}
 
+    # side reference only (north_star: "cuFFT is timed only as a side reference"): the same three steps with
+    # torch.fft (cuFFT Z2Z) + a pointwise division, device-resident; nothing of it is on the product path
+    side = None
+    if world == 1 and not args.no_side_reference:
+        try:
+            side = cufft_side_reference(torch, b, x_ref, max(3, min(args.steps, 10)))
+        except Exception as exc:
+            side = {"unavailable": f"{type(exc).__name__}: {exc}"}
+
     ksp = None
     if not args.no_ksp:
         del x_ref, b, x
@@ -453,6 +462,8 @@ def run_gpu(args):
             line["pcshell"] = pcshell
         if ksp is not None:
             line["ksp"] = ksp
+        if side is not None:
+            line["side_reference"] = side
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
@@ -463,6 +474,37 @@ def run_gpu(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# cuFFT side reference (not product code): fftn -> divide by Diag -> ifftn with torch.fft on the same b
+# ---------------------------------------------------------------------------------------------------------------
+def cufft_side_reference(torch, b, x_ref, steps):
+    n = N_GRID
+    k = torch.arange(n, device="cuda", dtype=torch.float64)
+    chat = 1.0 - torch.exp(-2j * torch.pi * k / n)                     # DFT of the upwind column [1, -1, 0, ...]
+    diag = (1.0 + LAMBDA[0] * chat[None, None, :] + LAMBDA[1] * chat[None, :, None] + LAMBDA[2] * chat[:, None, None])
+    b3 = b.reshape(n, n, n)
+
+    def apply():
+        return torch.fft.ifftn(torch.fft.fftn(b3) / diag)
+
+    for _ in range(2):
+        xs = apply()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        xs = apply()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    err = float((torch.linalg.vector_norm(xs.reshape(-1) - x_ref) / torch.linalg.vector_norm(x_ref)).item())
+    del xs, diag
+    torch.cuda.empty_cache()
+    return {"what": "torch.fft.fftn (cuFFT Z2Z) -> / Diag (N-entry table) -> torch.fft.ifftn, device-resident, same b",
+            "value": 1e3 / ms, "ms_per_step": ms, "steps": steps, "rel_l2_vs_x_ref": err,
+            "note": "side reference only; cuFFT is not linked into libcirculantpc.so"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -583,6 +625,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pcshell", action="store_true")
     ap.add_argument("--no-ksp", action="store_true")
+    ap.add_argument("--no-side-reference", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 200 and args.warmup == 20:      # defaults sized for the GPU arm; keep the CPU arm to minutes
