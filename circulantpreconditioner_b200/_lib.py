@@ -62,6 +62,7 @@ ABI = {
     "cpc_slab_range": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "cpc_slab_send_chunk": (_i, [_i, _i, _i, _i, _i, _i, _i, _i64p, _i64p]),
     "cpc_slab_recv_chunk": (_i, [_i, _i, _i, _i, _i, _i, _i, _i64p, _i64p]),
+    "cpc_symbol_recurrence_lambda": (_i, [_i, _i, _i, _dp, _dp, _dp, _dp]),
     "cpc_nccl_unique_id": (_i, [_vp]),
 }
 

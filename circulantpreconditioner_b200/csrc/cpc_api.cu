@@ -27,6 +27,30 @@ int cuda_fail(cudaError_t e, const char *what)
     return e == cudaErrorMemoryAllocation ? CPC_ERR_NOMEM : CPC_ERR_CUDA;
 }
 
+int symbol_recurrence_lambda(int nx, int ny, int nz, const double2 *ax, const double2 *ay, const double2 *az, double *lambda_z)
+{
+    double lz = 0.0;
+    if (nz > 1) {
+        double re, im;
+        exact_root(1, nz, &re, &im);
+        lz = az[1].x / (1.0 - re);
+    }
+    if (lambda_z) *lambda_z = lz;
+    bool ok = std::isfinite(lz) && lz >= 0.0 && lz <= 4096.0;
+    const double tol = 1e-13 * (lz > 1.0 ? lz : 1.0);
+    for (int m = 0; ok && m < nz; ++m) {
+        double re = 1.0, im = 0.0;
+        if (nz > 1) exact_root(m, nz, &re, &im);
+        const double wr = nz > 1 ? lz * (1.0 - re) : 0.0, wi = nz > 1 ? -lz * im : 0.0;
+        if (std::fabs(az[m].x - wr) > tol || std::fabs(az[m].y - wi) > tol) ok = false;
+    }
+    double mnx = ax[0].x, mny = ay[0].x;
+    for (int m = 1; m < nx; ++m) mnx = ax[m].x < mnx ? ax[m].x : mnx;
+    for (int m = 1; m < ny; ++m) mny = ay[m].x < mny ? ay[m].x : mny;
+    if (!(mnx + mny >= 0.5)) ok = false;
+    return ok ? 1 : 0;
+}
+
 SlabRange slab_range(int n, int nranks, int rank)
 {
     const int base = n / nranks, rem = n % nranks;
@@ -285,6 +309,12 @@ int cpc_slab_recv_chunk(int nx, int ny, int nz, int ncomp, int nranks, int rank,
     *offset = (long long)zs.start * yr.count * W;
     *count = (long long)zs.count * yr.count * W;
     return CPC_OK;
+}
+
+int cpc_symbol_recurrence_lambda(int nx, int ny, int nz, const double *ax, const double *ay, const double *az, double *lambda_z)
+{
+    if (nx < 1 || ny < 1 || nz < 1 || !ax || !ay || !az) return -1;
+    return symbol_recurrence_lambda(nx, ny, nz, (const double2 *)ax, (const double2 *)ay, (const double2 *)az, lambda_z);
 }
 
 int cpc_nccl_unique_id(void *out_bytes)

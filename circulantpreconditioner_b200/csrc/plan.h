@@ -19,6 +19,29 @@ int cuda_fail(cudaError_t e, const char *what);
         if (_e != cudaSuccess) return ::cpc::cuda_fail(_e, #call);      \
     } while (0)
 
+#include <cmath>
+
+// exp(-2 pi i m / n) rounded from long double
+inline void exact_root(long long m, long long n, double *re, double *im)
+{
+    m %= n;
+    const long double a = 2.0L * 3.141592653589793238462643383279502884L * (long double)m / (long double)n;
+    // use symmetries so that the classic points are exact
+    if (4 * m == n) { *re = 0.0; *im = -1.0; return; }
+    if (2 * m == n) { *re = -1.0; *im = 0.0; return; }
+    if (4 * m == 3 * n) { *re = 0.0; *im = 1.0; return; }
+    *re = (double)cosl(a);
+    *im = (double)(-sinl(a));
+}
+
+
+// Does a separable symbol (three 1-D tables already multiplied by their lambdas, the "+1" riding on y) admit the
+// recurrence form of the middle pass (zsolve.cuh)?  The z table must be lambda_z (1 - exp(-2 pi i k / nz)) -- the DFT of
+// the reference's upwind column [1, -1, 0, ...] (build_transport_col, FftLinearSolver_3D.c:80-90) -- for some
+// 0 <= lambda_z <= 4096, entry by entry to 1e-13 max(1, lambda_z), and Re(ax[i] + ay[j]) >= 1/2 everywhere, so that
+// |lambda_z / (alpha + lambda_z)| < 1.  Pure host code (cpc_symbol_recurrence_lambda exposes it).
+int symbol_recurrence_lambda(int nx, int ny, int nz, const double2 *ax, const double2 *ay, const double2 *az, double *lambda_z);
+
 // Slab bookkeeping shared by the multi-rank code and the pure-host ABI helpers.
 struct SlabRange { int start, count; };
 SlabRange slab_range(int n, int nranks, int rank);

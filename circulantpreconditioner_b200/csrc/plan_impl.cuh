@@ -136,19 +136,6 @@ __global__ void csr_spmv_kernel(long long rows, const long long *__restrict__ ro
     }
 }
 
-// exp(-2 pi i m / n) rounded from long double
-static inline void exact_root(long long m, long long n, double *re, double *im)
-{
-    m %= n;
-    const long double a = 2.0L * 3.141592653589793238462643383279502884L * (long double)m / (long double)n;
-    // use symmetries so that the classic points are exact
-    if (4 * m == n) { *re = 0.0; *im = -1.0; return; }
-    if (2 * m == n) { *re = -1.0; *im = 0.0; return; }
-    if (4 * m == 3 * n) { *re = 0.0; *im = 1.0; return; }
-    *re = (double)cosl(a);
-    *im = (double)(-sinl(a));
-}
-
 // ------------------------------------------------------------------------------------------------
 // PlanT
 // ------------------------------------------------------------------------------------------------
@@ -887,25 +874,7 @@ template <typename T> struct PlanT : PlanBase {
         if (rc) return rc;
         symbol_kind = CPC_SYMBOL_SEPARABLE;
         double lz = 0.0;
-        if (n[2] > 1) {
-            double re, im;
-            exact_root(1, n[2], &re, &im);
-            lz = h[2][1].x / (1.0 - re);
-        }
-        zrec = std::isfinite(lz) && lz >= 0.0 && lz <= 4096.0;
-        const double tol = 1e-13 * (lz > 1.0 ? lz : 1.0);
-        for (int m = 0; zrec && m < n[2]; ++m) {
-            double re = 1.0, im = 0.0;
-            if (n[2] > 1) exact_root(m, n[2], &re, &im);
-            const double wr = n[2] > 1 ? lz * (1.0 - re) : 0.0, wi = n[2] > 1 ? -lz * im : 0.0;
-            if (std::fabs(h[2][m].x - wr) > tol || std::fabs(h[2][m].y - wi) > tol) zrec = false;
-        }
-        double mn[2] = { 0.0, 0.0 };
-        for (int a = 0; a < 2; ++a) {
-            mn[a] = h[a][0].x;
-            for (int m = 1; m < n[a]; ++m) mn[a] = h[a][m].x < mn[a] ? h[a][m].x : mn[a];
-        }
-        if (!(mn[0] + mn[1] >= 0.5)) zrec = false;
+        zrec = symbol_recurrence_lambda(n[0], n[1], n[2], h[0].data(), h[1].data(), h[2].data(), &lz) != 0;
         zrec_lz = lz;
         // how much of a line the end-value sweep has to read: planes whose weight |c|^m can reach 1e-17
         end_fraction = 1.0;

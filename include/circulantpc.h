@@ -204,6 +204,13 @@ int cpc_slab_send_chunk(int nx, int ny, int nz, int ncomp, int nranks, int rank,
 /* Same for the chunk received from rank `s` into the transposed buffer [z_glob][y_loc][x]. */
 int cpc_slab_recv_chunk(int nx, int ny, int nz, int ncomp, int nranks, int rank, int s,
                         int64_t *offset, int64_t *count);
+/* The test the library applies to a separable symbol before it takes the recurrence form of the middle pass (see
+ * cpc_apply): tables ax[nx], ay[ny], az[nz] as HOST complex128 arrays, already multiplied by their lambdas, the "+1"
+ * of build_diag_mat_vec_3D (FftLinearSolver_3D.c:155) riding on ay.  Returns 1 and *lambda_z when az is
+ * lambda_z (1 - exp(-2 pi i k / nz)) -- the DFT of build_transport_col's [1, -1, 0, ...] (:80-90) -- for some
+ * 0 <= lambda_z <= 4096 and Re(ax[i] + ay[j]) >= 1/2 everywhere; 0 otherwise (the FFT form runs); -1 on bad arguments. */
+int cpc_symbol_recurrence_lambda(int nx, int ny, int nz, const double *ax, const double *ay, const double *az,
+                                 double *lambda_z);
 /* NCCL bootstrap: fills CPC_NCCL_UNIQUE_ID_BYTES bytes (call on rank 0, broadcast out of band). */
 int cpc_nccl_unique_id(void *out_bytes);
 

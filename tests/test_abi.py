@@ -4,6 +4,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 import circulantpreconditioner_b200 as cpc
@@ -84,3 +85,47 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cxx", ".hxx", ".cpp", "Makefile")):
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 assert not pat.search(txt), f"{os.path.join(dp, f)} reaches into oracle/"
+
+
+# ---- pure-host logic: when does a separable symbol take the recurrence form of the middle pass? ----
+def _tables(n, lam, shift_y=True):
+    from oracle import circulant_oracle as O
+    t = [lam[a] * np.fft.fft(O.build_transport_col(n[a])) for a in range(3)]
+    if shift_y:
+        t[1] = t[1] + 1.0                      # the "+1" (VecShift, FftLinearSolver_3D.c:155) rides on the y table
+    return [np.ascontiguousarray(v, dtype=np.complex128) for v in t]
+
+
+def _recurrence(n, tabs):
+    L = cpc.lib()
+    lz = ctypes.c_double(-1.0)
+    p = [v.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) for v in tabs]
+    ok = L.cpc_symbol_recurrence_lambda(n[0], n[1], n[2], p[0], p[1], p[2], ctypes.byref(lz))
+    return ok, lz.value
+
+
+@pytest.mark.parametrize("n", [(8, 4, 16), (5, 3, 7), (16, 16, 512), (4, 4, 2), (6, 1, 1), (1, 1, 9)])
+@pytest.mark.parametrize("lam", [(55.5556, 55.5556, 55.5556), (0.6, 0.15, 0.02), (1.0, 1.0, 4096.0), (2.0, 0.0, 0.0)])
+def test_recurrence_gate_accepts_the_reference_symbol(n, lam):
+    ok, lz = _recurrence(n, _tables(n, lam))
+    assert ok == 1
+    assert lz == pytest.approx(lam[2] if n[2] > 1 else 0.0, rel=1e-12, abs=1e-12)
+
+
+def test_recurrence_gate_rejects_everything_else():
+    n = (8, 6, 32)
+    base = (2.0, 0.5, 3.0)
+    assert _recurrence(n, _tables(n, base))[0] == 1
+    assert _recurrence(n, _tables(n, (2.0, 0.5, -0.2)))[0] == 0                # lambda_z < 0
+    assert _recurrence(n, _tables(n, (2.0, 0.5, 5000.0)))[0] == 0              # beyond the validated range
+    assert _recurrence(n, _tables(n, (-0.3, 0.5, 3.0)))[0] == 0                # Re(alpha) can drop below 1/2
+    assert _recurrence(n, _tables(n, (-0.2, 0.5, 3.0)))[0] == 1                # ... here it cannot (min 0.6)
+    t = _tables(n, base)
+    t[2][5] += 1e-9                                                            # one z entry off: not the upwind column
+    assert _recurrence(n, t)[0] == 0
+    t = _tables(n, base)
+    t[2] = np.conj(t[2])                                                       # downwind column [1, 0, ..., -1]
+    assert _recurrence(n, t)[0] == 0
+    t = _tables(n, base, shift_y=False)                                        # no "+1" anywhere: alpha can vanish
+    assert _recurrence(n, t)[0] == 0
+    assert cpc.lib().cpc_symbol_recurrence_lambda(0, 1, 1, None, None, None, None) == -1
