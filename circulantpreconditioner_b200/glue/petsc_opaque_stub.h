@@ -33,6 +33,12 @@ typedef struct _p_PetscContainer *PetscContainer;
 typedef struct _p_Vec *Vec;
 typedef struct _p_Mat *Mat;
 typedef struct _p_PC *PC;
+typedef struct _p_KSP *KSP;
+typedef const char *KSPType;
+typedef const char *PCType;
+#define KSPGMRES "gmres"
+#define PCSHELL "shell"
+#define PETSC_DEFAULT (-2)
 
 #define PETSC_USE_COMPLEX 1
 #define PETSC_SUCCESS 0
@@ -100,6 +106,14 @@ PetscErrorCode MatSeqAIJRestoreArrayRead(Mat, const PetscScalar **);
 PetscErrorCode MatDestroy(Mat *);
 PetscErrorCode MatMult(Mat, Vec, Vec);
 
+PetscErrorCode KSPCreate(MPI_Comm, KSP *);
+PetscErrorCode KSPSetType(KSP, KSPType);
+PetscErrorCode KSPSetTolerances(KSP, PetscReal, PetscReal, PetscReal, PetscInt);
+PetscErrorCode KSPGetPC(KSP, PC *);
+PetscErrorCode KSPSetOperators(KSP, Mat, Mat);
+PetscErrorCode KSPSolve(KSP, Vec, Vec);
+PetscErrorCode KSPDestroy(KSP *);
+PetscErrorCode PCSetType(PC, PCType);
 PetscErrorCode PCShellSetContext(PC, void *);
 PetscErrorCode PCShellGetContext(PC, void *);
 PetscErrorCode PCShellSetApply(PC, PetscErrorCode (*)(PC, Vec, Vec));

@@ -114,8 +114,9 @@ def test_petsc_fft3d_transport_solver_by_value_context():
 
 
 def test_glue_sources_are_petsc_clean():
-    """circulantpc_petsc.cxx / circulantpc_pcshell.cxx compile with -DCPC_WITH_PETSC against a header in which Vec, Mat
-    and PC are opaque pointers (glue/petsc_opaque_stub.h): they use public PETSc functions only."""
+    """circulantpc_petsc.cxx / circulantpc_pcshell.cxx (and the example of the reference-side driver changes,
+    example_petsc_driver.cxx) compile with -DCPC_WITH_PETSC against a header in which Vec, Mat and PC are opaque pointers
+    (glue/petsc_opaque_stub.h): they use public PETSc functions only."""
     subprocess.check_call(["make", "-s", "-B", "-C", GLUE, "check-petsc-clean"])
     for src in ("circulantpc_petsc.cxx", "circulantpc_pcshell.cxx"):
         text = open(os.path.join(GLUE, src)).read()
