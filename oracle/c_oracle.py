@@ -28,6 +28,9 @@ def lib():
         L.oracle_Fft3DTransportSolver.argtypes = [ctypes.c_int] * 3 + [ctypes.c_double] * 7 + [dp, dp]
         L.oracle_transport_solve_z_recurrence.argtypes = [dp, dp] + [ctypes.c_int] * 3 + [ctypes.c_double] * 3
         L.oracle_transport_solve_z_recurrence.restype = ctypes.c_int
+        L.oracle_transport_solve_z_line_form.argtypes = [dp, dp] + [ctypes.c_int] * 3 + [ctypes.c_double] * 3 + [ctypes.c_int,
+                                                                                                           ctypes.c_double]
+        L.oracle_transport_solve_z_line_form.restype = ctypes.c_int
         L.oracle_num_threads.restype = ctypes.c_int
         _LIB = L
     return _LIB
@@ -73,3 +76,13 @@ def transport_solve_z_recurrence(nx, ny, nz, lx, ly, lz, b):
         raise ValueError("the recurrence form needs non-negative lambdas")
     return x
 
+
+
+def transport_solve_z_line_form(nx, ny, nz, lx, ly, lz, b, slabs=1, weight_floor=1e-17):
+    """The line form / multi-rank owner scheme of the recurrence (csrc/zsolve.cuh) in plain C."""
+    b = np.ascontiguousarray(b, dtype=np.complex128)
+    x = np.empty_like(b)
+    rc = lib().oracle_transport_solve_z_line_form(_p(x), _p(b), nx, ny, nz, lx, ly, lz, slabs, weight_floor)
+    if rc != 0:
+        raise ValueError("bad lambdas or slab count")
+    return x

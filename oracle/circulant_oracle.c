@@ -243,6 +243,76 @@ int oracle_transport_solve_z_recurrence(double *X, const double *b, int nx, int 
     return 0;
 }
 
+/* The recurrence form as the CUDA line kernels and the multi-rank owner scheme evaluate it (csrc/zsolve.cuh:
+ * zs_end_accum_kernel, zs_carry_owner_kernel, zs_dist_line_kernel): the z line is cut into `slabs` equal parts; the end
+ * value of every part from a zero carry-in is summed only over the planes whose weight |c|^m can still reach
+ * `weight_floor` (whole groups of 16 planes, as the kernel does); the line's owner closes the cycle over the parts --
+ * Zin_0 by Horner, Zin_{r+1} = e_r + c^(nz/slabs) Zin_r -- and every part is solved from its carry-in.  slabs = 1 is the
+ * single-GPU line form.  Same operator as oracle_solve_3D (FftLinearSolver_3D.c:166-190) to rounding.
+ * Returns 0, -1 on bad lambdas, -2 if nz is not divisible by slabs (or slabs > 64). */
+int oracle_transport_solve_z_line_form(double *X, const double *b, int nx, int ny, int nz, double lx, double ly, double lz,
+                                       int slabs, double weight_floor)
+{
+    if (lx < 0 || ly < 0 || lz < 0) return -1;
+    if (slabs < 1 || slabs > 64 || nz % slabs) return -2;
+    size_t N = (size_t)nx * ny * nz;
+    long sxy = (long)nx * ny;
+    const int nzl = nz / slabs;
+    cplx *a = (cplx *)malloc(sizeof(cplx) * N);
+    memcpy(a, b, sizeof(cplx) * N);
+    dft_axis(a, nx, 1, nz, sxy, ny, nx, -1);          /* Fx */
+    dft_axis(a, ny, nx, nz, sxy, nx, 1, -1);          /* Fy */
+#pragma omp parallel for schedule(static)
+    for (long line = 0; line < sxy; ++line) {
+        const int i = (int)(line % nx), j = (int)(line / nx);
+        cplx wx = root(i, nx, -1), wy = root(j, ny, -1);
+        double are = 1.0 + (nx > 1 ? lx * (1.0 - wx.re) : 0.0) + (ny > 1 ? ly * (1.0 - wy.re) : 0.0) + lz;
+        double aim = (nx > 1 ? -lx * wx.im : 0.0) + (ny > 1 ? -ly * wy.im : 0.0);
+        if (nz == 1) are -= lz;
+        double d2 = are * are + aim * aim;
+        cplx r = { are / d2, -aim / d2 };
+        cplx c = { (nz > 1 ? lz : 0.0) * r.re, (nz > 1 ? lz : 0.0) * r.im };
+        /* first plane of a part that still matters */
+        double c2 = c.re * c.re + c.im * c.im;
+        double m = c2 > 0.0 ? log(weight_floor * weight_floor) / log(c2) + 1.0 : 1.0;
+        int start = (m < (double)nzl) ? nzl - (int)m : 0;
+        start = nzl - ((nzl - start + 15) / 16) * 16;
+        if (start < 0) start = 0;
+        cplx e[64];
+        for (int s_ = 0; s_ < slabs; ++s_) {           /* end value of part s_, zero carry-in, truncated sum */
+            cplx acc = { 0.0, 0.0 };
+            for (int k = start; k < nzl; ++k) acc = cadd(cmul(c, acc), a[line + (long)(s_ * nzl + k) * sxy]);
+            e[s_] = acc;
+        }
+        cplx cL = { 1.0, 0.0 };
+        for (int k = 0; k < nzl; ++k) cL = cmul(cL, c);
+        cplx acc = { 0.0, 0.0 }, cLp = { 1.0, 0.0 };
+        for (int s_ = 0; s_ < slabs; ++s_) {           /* owner: Horner over e_0 .. e_{P-1}, closed cyclically */
+            acc = cadd(cmul(cL, acc), e[s_]);
+            cLp = cmul(cLp, cL);
+        }
+        double e2 = (1.0 - cLp.re) * (1.0 - cLp.re) + cLp.im * cLp.im;
+        cplx inv = { (1.0 - cLp.re) / e2, cLp.im / e2 };
+        cplx Z = cmul(acc, inv);
+        for (int s_ = 0; s_ < slabs; ++s_) {           /* second sweep of every part from its carry-in */
+            cplx y = Z;
+            for (int k = 0; k < nzl; ++k) {
+                long idx = line + (long)(s_ * nzl + k) * sxy;
+                y = cadd(cmul(c, y), a[idx]);
+                a[idx] = cmul(y, r);
+            }
+            Z = cadd(e[s_], cmul(cL, Z));              /* Zin_{r+1} = e_r + cL Zin_r */
+        }
+    }
+    dft_axis(a, ny, nx, nz, sxy, nx, 1, +1);          /* By */
+    dft_axis(a, nx, 1, nz, sxy, ny, nx, +1);          /* Bx */
+    double s = 1.0 / ((double)nx * ny);
+    cplx *x = (cplx *)X;
+    for (size_t mm = 0; mm < N; ++mm) { x[mm].re = a[mm].re * s; x[mm].im = a[mm].im * s; }
+    free(a);
+    return 0;
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -229,7 +229,7 @@ def FftTransportSolver_z_line_form(n_x, n_y, n_z, lambda_x, lambda_y, lambda_z, 
     c2 = np.abs(c) ** 2
     with np.errstate(divide="ignore"):
         m = np.where(c2 > 0, np.log(weight_floor ** 2) / np.log(np.where(c2 > 0, c2, 0.5)) + 1.0, 1.0)
-    start = np.where(m < nzl, nzl - m.astype(np.int64), 0)
+    start = np.where(m < nzl, nzl - np.minimum(m, nzl).astype(np.int64), 0)
     start = np.maximum(nzl - ((nzl - start + 15) // 16) * 16, 0)
     ends = np.zeros((slabs, alpha.size), dtype=np.complex128)
     for s_ in range(slabs):                   # end value of every slab from a zero carry-in, truncated sum

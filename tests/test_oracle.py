@@ -215,6 +215,9 @@ def test_z_line_form_equals_fft_form(shape, lam, slabs):
     want = O.FftTransportSolver(nx, ny, nz, *lam, b)
     got = O.FftTransportSolver_z_line_form(nx, ny, nz, *lam, b, slabs=slabs)
     assert rel_l2(got, want) < 1e-12
+    got_c = CO.transport_solve_z_line_form(nx, ny, nz, *lam, b, slabs=slabs)       # the plain-C restatement
+    # (at lambda_z = 3000 the closure 1/(1 - c^nz) amplifies rounding to ~3e-13 in either restatement)
+    assert rel_l2(got_c, want) < 1e-12 and rel_l2(got_c, got) < 1e-12
     # the truncation itself: against the untruncated sum (weight_floor = 0) the difference is at rounding level
     full = O.FftTransportSolver_z_line_form(nx, ny, nz, *lam, b, weight_floor=1e-300, slabs=slabs)
     assert rel_l2(got, full) < 1e-15
