@@ -1,0 +1,529 @@
+"""A minimal read-only HDF5 reader, enough for the reference's MED mesh files (meshes/**/*.med, MED 4.x on HDF5 1.10).
+
+Harness code for BASELINE config 5: no HDF5 library exists in this image, and the polyhedral
+Kershaw meshes (meshes/3DKershaw/Kershaw{1,2}.med) ship as .med only.  Written from the published HDF5 file-format
+specification (version 3.0); covers exactly what those files use:
+
+  superblock        versions 0-3
+  groups            new style: link messages in the object header (compact) or fractal heap (dense), and old style:
+                    symbol table (B-tree v1 + local heap)
+  object headers    version 1 and version 2 ("OHDR"), with continuation blocks
+  datasets          contiguous, compact, and chunked (B-tree v1 index; deflate / shuffle filters) layouts; fixed-point,
+                    floating-point and fixed-length string types
+  attributes        versions 1-3, scalar or simple dataspaces of the same types
+
+Anything else raises NotImplementedError instead of guessing.
+"""
+from __future__ import annotations
+
+import struct
+import zlib
+
+import numpy as np
+
+_SIG = b"\x89HDF\r\n\x1a\n"
+_UNDEF = 0xFFFFFFFFFFFFFFFF
+
+
+class Hdf5Error(Exception):
+    pass
+
+
+class _Reader:
+    def __init__(self, buf, pos=0):
+        self.b, self.p = buf, pos
+
+    def u(self, n):
+        v = int.from_bytes(self.b[self.p:self.p + n], "little")
+        self.p += n
+        return v
+
+    def raw(self, n):
+        v = self.b[self.p:self.p + n]
+        self.p += n
+        return v
+
+    def skip(self, n):
+        self.p += n
+
+    def align(self, base, k):
+        self.p = base + ((self.p - base + k - 1) // k) * k
+
+
+class Dataset:
+    def __init__(self, f, msgs, attrs):
+        self._f, self._msgs, self.attrs = f, msgs, attrs
+        self.shape = f._dataspace(msgs[0x01][0]) if 0x01 in msgs else ()
+        try:
+            self.dtype, self._strlen = f._datatype(msgs[0x03][0])
+        except NotImplementedError:                     # e.g. the array-of-char names of MED families: listed, not read
+            self.dtype, self._strlen = None, None
+
+    def read(self):
+        if self.dtype is None:
+            raise NotImplementedError("datatype of this dataset")
+        return self._f._read_layout(self._msgs, self.shape, self.dtype, self._strlen)
+
+
+class Group:
+    def __init__(self, f, links, attrs):
+        self._f, self.links, self.attrs = f, links, attrs
+
+    def keys(self):
+        return sorted(self.links)
+
+    def __contains__(self, name):
+        return name in self.links
+
+    def __getitem__(self, path):
+        node = self
+        for part in [p for p in path.split("/") if p]:
+            if not isinstance(node, Group) or part not in node.links:
+                raise KeyError(path)
+            node = node._f._object(node.links[part])
+        return node
+
+
+class File:
+    def __init__(self, path):
+        with open(path, "rb") as fh:
+            self.b = fh.read()
+        self._superblock()
+        self._cache = {}
+        self.root = self._object(self.root_addr)
+
+    def __getitem__(self, path):
+        return self.root[path]
+
+    def walk(self, group=None, prefix=""):
+        """Yield (path, object) for everything below `group`, depth first in name order."""
+        group = self.root if group is None else group
+        for name in group.keys():
+            obj = group[name]
+            yield prefix + "/" + name, obj
+            if isinstance(obj, Group):
+                yield from self.walk(obj, prefix + "/" + name)
+
+    # ------------------------------------------------------------------ superblock
+    def _superblock(self):
+        base = self.b.find(_SIG)
+        if base != 0:
+            raise Hdf5Error("not an HDF5 file (or a user block precedes the superblock)")
+        r = _Reader(self.b, 8)
+        ver = r.u(1)
+        if ver in (0, 1):
+            r.skip(4)                                   # free-space, root group, reserved, shared header versions
+            self.O, self.L = r.u(1), r.u(1)
+            r.skip(1)
+            r.skip(4)                                   # group leaf node K, group internal node K
+            r.skip(4)                                   # consistency flags
+            if ver == 1:
+                r.skip(4)
+            r.skip(4 * self.O)                          # base, free-space info, end of file, driver info
+            r.skip(self.O)                              # root symbol table entry: link name offset
+            self.root_addr = r.u(self.O)
+        elif ver in (2, 3):
+            self.O, self.L = r.u(1), r.u(1)
+            r.skip(1)
+            r.skip(3 * self.O)                          # base, superblock extension, end of file
+            self.root_addr = r.u(self.O)
+        else:
+            raise NotImplementedError(f"superblock version {ver}")
+
+    # ------------------------------------------------------------------ object headers
+    def _messages(self, addr):
+        """[(type, flags, body bytes)] of the object header at addr, continuation blocks followed."""
+        b = self.b
+        out = []
+        if b[addr:addr + 4] == b"OHDR":
+            r = _Reader(b, addr + 4)
+            if r.u(1) != 2:
+                raise NotImplementedError("object header version")
+            flags = r.u(1)
+            if flags & 0x20:
+                r.skip(16)
+            if flags & 0x10:
+                r.skip(4)
+            size0 = r.u(1 << (flags & 3))
+            blocks = [(r.p, size0)]
+            tracked = bool(flags & 0x04)
+            while blocks:
+                start, size = blocks.pop(0)
+                r = _Reader(b, start)
+                end = start + size
+                while r.p + 4 <= end:
+                    mtype, msize, mflags = r.u(1), r.u(2), r.u(1)
+                    if tracked:
+                        r.skip(2)
+                    body = r.raw(msize)
+                    if mtype == 0x10:                   # continuation: "OCHK" + messages + checksum
+                        c = _Reader(body)
+                        caddr, clen = c.u(self.O), c.u(self.L)
+                        if b[caddr:caddr + 4] != b"OCHK":
+                            raise Hdf5Error("bad continuation block")
+                        blocks.append((caddr + 4, clen - 8))
+                    elif mtype != 0:
+                        out.append((mtype, mflags, body))
+            return out
+        # version 1
+        r = _Reader(b, addr)
+        if r.u(1) != 1:
+            raise Hdf5Error(f"no object header at {addr:#x}")
+        r.skip(1)
+        nmsg = r.u(2)
+        r.skip(4)
+        size0 = r.u(4)
+        r.align(addr, 8)
+        blocks = [(r.p, size0)]
+        while blocks and nmsg > 0:
+            start, size = blocks.pop(0)
+            r = _Reader(b, start)
+            while r.p + 8 <= start + size and nmsg > 0:
+                mtype, msize, mflags = r.u(2), r.u(2), r.u(1)
+                r.skip(3)
+                body = r.raw(msize)
+                nmsg -= 1
+                if mtype == 0x10:
+                    c = _Reader(body)
+                    blocks.append((c.u(self.O), c.u(self.L)))
+                elif mtype != 0:
+                    out.append((mtype, mflags, body))
+        return out
+
+    def _object(self, addr):
+        if addr in self._cache:
+            return self._cache[addr]
+        by_type = {}
+        for mtype, mflags, body in self._messages(addr):
+            if mflags & 0x02 and mtype in (0x01, 0x03, 0x0B, 0x0C):
+                raise NotImplementedError("shared header messages")
+            by_type.setdefault(mtype, []).append(body)
+        attrs = {}
+        for body in by_type.get(0x0C, []):
+            name, val = self._attribute(body)
+            attrs[name] = val
+        if 0x15 in by_type:
+            ai = _Reader(by_type[0x15][0])
+            ai.skip(1)
+            fl = ai.u(1)
+            if fl & 1:
+                ai.skip(2)
+            heap = ai.u(self.O)
+            if heap != _UNDEF & ((1 << (8 * self.O)) - 1):
+                for blob in self._heap_objects(heap):
+                    name, val = self._attribute(blob)
+                    attrs[name] = val
+        if 0x08 in by_type:                             # data layout -> dataset
+            obj = Dataset(self, by_type, attrs)
+        else:
+            links = {}
+            for body in by_type.get(0x06, []):
+                name, target = self._link(_Reader(body))
+                if target is not None:
+                    links[name] = target
+            if 0x02 in by_type:                         # link info: dense storage
+                li = _Reader(by_type[0x02][0])
+                li.skip(1)
+                fl = li.u(1)
+                if fl & 1:
+                    li.skip(8)
+                heap = li.u(self.O)
+                if heap != _UNDEF & ((1 << (8 * self.O)) - 1):
+                    for blob in self._heap_objects(heap):
+                        name, target = self._link(_Reader(blob))
+                        if target is not None:
+                            links[name] = target
+            if 0x11 in by_type:                         # symbol table message: old-style group
+                st = _Reader(by_type[0x11][0])
+                links.update(self._symbol_table(st.u(self.O), st.u(self.O)))
+            obj = Group(self, links, attrs)
+        self._cache[addr] = obj
+        return obj
+
+    # ------------------------------------------------------------------ links
+    def _link(self, r):
+        if r.u(1) != 1:
+            raise Hdf5Error("link message version")
+        fl = r.u(1)
+        ltype = r.u(1) if fl & 0x08 else 0
+        if fl & 0x04:
+            r.skip(8)
+        if fl & 0x10:
+            r.skip(1)
+        n = r.u(1 << (fl & 3))
+        name = r.raw(n).decode("utf-8", "replace")
+        return name, (r.u(self.O) if ltype == 0 else None)   # soft / external links are not followed
+
+    def _heap_objects(self, addr):
+        """The managed objects of the fractal heap at addr, in storage order.  Objects are self-delimiting messages
+        (links, attributes) written back to back from the start of every direct block; the block is zero-filled behind
+        them.  The object count is checked against the heap header."""
+        b = self.b
+        if b[addr:addr + 4] != b"FRHP":
+            raise Hdf5Error("no fractal heap")
+        r = _Reader(b, addr + 5)
+        r.skip(2)                                       # heap ID length
+        filt_len = r.u(2)
+        hflags = r.u(1)
+        r.skip(4)                                       # max managed object size
+        r.skip(self.L + self.O + self.L + self.O)       # huge ID, huge B-tree, free space, free-space manager
+        r.skip(3 * self.L)                              # managed space, allocated space, iterator offset
+        n_managed = r.u(self.L)
+        r.skip(self.L)
+        n_huge = r.u(self.L)
+        r.skip(self.L)
+        n_tiny = r.u(self.L)
+        width = r.u(2)
+        start_size = r.u(self.L)
+        max_direct = r.u(self.L)
+        max_heap_bits = r.u(2)
+        r.skip(2)
+        root = r.u(self.O)
+        cur_rows = r.u(2)
+        if filt_len or n_huge or n_tiny:
+            raise NotImplementedError("filtered fractal heap, huge or tiny objects")
+        off_bytes = (max_heap_bits + 7) // 8
+        hdr = 5 + self.O + off_bytes + (4 if hflags & 2 else 0)
+        blocks = []
+        if cur_rows == 0:
+            blocks.append((root, start_size))
+        else:
+            if b[root:root + 4] != b"FHIB":
+                raise Hdf5Error("no indirect block")
+            q = _Reader(b, root + 5 + self.O + off_bytes)
+            max_direct_rows = (max_direct // start_size).bit_length() + 1     # log2(max/start) + 2
+            for row in range(cur_rows):
+                if row >= max_direct_rows:
+                    raise NotImplementedError("nested indirect blocks")
+                size = start_size if row < 2 else start_size << (row - 1)
+                for _ in range(width):
+                    a = q.u(self.O)
+                    if a != _UNDEF & ((1 << (8 * self.O)) - 1):
+                        blocks.append((a, size))
+        objs = []
+        for a, size in blocks:
+            if b[a:a + 4] != b"FHDB":
+                raise Hdf5Error("no direct block")
+            p, end = a + hdr, a + size
+            while p < end and b[p] != 0:
+                n = self._message_length(b, p)
+                objs.append(b[p:p + n])
+                p += n
+        if len(objs) != n_managed:
+            raise Hdf5Error(f"fractal heap: found {len(objs)} objects, header says {n_managed}")
+        return objs
+
+    def _message_length(self, b, p):
+        """Length of the link (version 1) or attribute (version 3) message that starts at p."""
+        ver = b[p]
+        r = _Reader(b, p + 1)
+        if ver == 1:                                    # link
+            fl = r.u(1)
+            ltype = r.u(1) if fl & 0x08 else 0
+            if fl & 0x04:
+                r.skip(8)
+            if fl & 0x10:
+                r.skip(1)
+            r.skip(r.u(1 << (fl & 3)))
+            if ltype == 0:
+                r.skip(self.O)
+            elif ltype == 1:
+                r.skip(r.u(2))
+            else:
+                r.skip(r.u(2))
+            return r.p - p
+        if ver == 3:                                    # attribute
+            r.skip(1)
+            nn, nt, ns = r.u(2), r.u(2), r.u(2)
+            r.skip(1)
+            name_end = r.p + nn
+            dt, _ = self._datatype(b[name_end:name_end + nt])
+            shape = self._dataspace(b[name_end + nt:name_end + nt + ns])
+            count = int(np.prod(shape)) if shape else 1
+            itemsize = _Reader(b, name_end + 4).u(4)
+            return name_end + nt + ns + count * itemsize - p
+        raise NotImplementedError(f"heap object version {ver}")
+
+    def _symbol_table(self, btree, heap):
+        b = self.b
+        if b[heap:heap + 4] != b"HEAP":
+            raise Hdf5Error("no local heap")
+        r = _Reader(b, heap + 8)
+        r.skip(2 * self.L)
+        data = r.u(self.O)
+        links = {}
+
+        def node(addr):
+            if b[addr:addr + 4] == b"TREE":
+                q = _Reader(b, addr + 4)
+                q.skip(1)
+                level, used = q.u(1), q.u(2)
+                q.skip(2 * self.O)
+                q.skip(self.L)                          # key 0
+                for _ in range(used):
+                    child = q.u(self.O)
+                    q.skip(self.L)
+                    node(child)
+            elif b[addr:addr + 4] == b"SNOD":
+                q = _Reader(b, addr + 6)
+                for _ in range(q.u(2)):
+                    name_off, target = q.u(self.O), q.u(self.O)
+                    q.skip(4 + 4 + 16)
+                    e = b.index(b"\0", data + name_off)
+                    links[b[data + name_off:e].decode()] = target
+            else:
+                raise Hdf5Error("bad group B-tree node")
+
+        node(btree)
+        return links
+
+    # ------------------------------------------------------------------ dataspace / datatype / attribute
+    def _dataspace(self, body):
+        r = _Reader(body)
+        ver = r.u(1)
+        rank, fl = r.u(1), r.u(1)
+        if ver == 1:
+            r.skip(5)
+        elif ver == 2:
+            if r.u(1) == 2:
+                return (0,)                             # null dataspace
+        else:
+            raise NotImplementedError("dataspace version")
+        return tuple(r.u(self.L) for _ in range(rank))
+
+    def _datatype(self, body):
+        """(numpy dtype, string length or None)."""
+        r = _Reader(body)
+        cv = r.u(1)
+        cls = cv & 0x0F
+        bits = r.u(3)
+        size = r.u(4)
+        order = ">" if bits & 1 else "<"
+        if cls == 0:
+            return np.dtype(f"{order}{'i' if bits & 0x08 else 'u'}{size}"), None
+        if cls == 1:
+            return np.dtype(f"{order}f{size}"), None
+        if cls == 3:
+            return np.dtype(f"S{size}"), size
+        raise NotImplementedError(f"datatype class {cls}")
+
+    def _attribute(self, body):
+        r = _Reader(body)
+        ver = r.u(1)
+        if ver == 1:
+            r.skip(1)
+            nn, nt, ns = r.u(2), r.u(2), r.u(2)
+            pad = lambda n: (n + 7) // 8 * 8
+            name = r.raw(pad(nn))[:nn]
+            t = r.raw(pad(nt))
+            s = r.raw(pad(ns))
+        elif ver in (2, 3):
+            fl = r.u(1)
+            if fl & 3:
+                raise NotImplementedError("shared attribute datatype / dataspace")
+            nn, nt, ns = r.u(2), r.u(2), r.u(2)
+            if ver == 3:
+                r.skip(1)
+            name, t, s = r.raw(nn), r.raw(nt), r.raw(ns)
+        else:
+            raise NotImplementedError("attribute version")
+        dt, strlen = self._datatype(t)
+        shape = self._dataspace(s)
+        count = int(np.prod(shape)) if shape else 1
+        val = np.frombuffer(r.raw(count * dt.itemsize), dtype=dt, count=count)
+        name = name.rstrip(b"\0").decode()
+        if strlen is not None:
+            val = [v.split(b"\0")[0].decode("latin-1") for v in val]
+            return name, (val[0] if not shape else val)
+        return name, (val[0].item() if not shape else val.reshape(shape).copy())
+
+    # ------------------------------------------------------------------ raw data
+    def _read_layout(self, msgs, shape, dtype, strlen):
+        r = _Reader(msgs[0x08][0])
+        ver = r.u(1)
+        if ver != 3:
+            raise NotImplementedError(f"data layout version {ver}")
+        cls = r.u(1)
+        count = int(np.prod(shape)) if shape else 1
+        nbytes = count * dtype.itemsize
+        if cls == 0:
+            n = r.u(2)
+            raw = r.raw(n)[:nbytes]
+        elif cls == 1:
+            addr = r.u(self.O)
+            r.u(self.L)
+            raw = self.b[addr:addr + nbytes] if addr != _UNDEF & ((1 << (8 * self.O)) - 1) else bytes(nbytes)
+        elif cls == 2:
+            ndim = r.u(1)
+            btree = r.u(self.O)
+            cdims = [r.u(4) for _ in range(ndim)]
+            raw = self._read_chunked(btree, cdims[:-1], shape, dtype, msgs.get(0x0B))
+        else:
+            raise NotImplementedError("data layout class")
+        a = np.frombuffer(raw, dtype=dtype, count=count).reshape(shape if shape else ())
+        if strlen is not None:
+            return a
+        return a.astype(dtype.newbyteorder("="))
+
+    def _filters(self, body):
+        if body is None:
+            return []
+        r = _Reader(body[0])
+        ver, n = r.u(1), r.u(1)
+        if ver == 1:
+            r.skip(6)
+        out = []
+        for _ in range(n):
+            fid = r.u(2)
+            nlen = r.u(2) if (ver == 1 or fid >= 256) else 0
+            r.skip(2)
+            ncd = r.u(2)
+            if nlen:
+                r.skip((nlen + 7) // 8 * 8 if ver == 1 else nlen)
+            cd = [r.u(4) for _ in range(ncd)]
+            if ver == 1 and ncd % 2:
+                r.skip(4)
+            out.append((fid, cd))
+        return out
+
+    def _read_chunked(self, btree, cdims, shape, dtype, filt_body):
+        filters = self._filters(filt_body)
+        out = np.zeros(shape, dtype=dtype)
+        rank = len(shape)
+        b = self.b
+
+        def node(addr):
+            if b[addr:addr + 4] != b"TREE":
+                raise Hdf5Error("bad chunk B-tree node")
+            q = _Reader(b, addr + 4)
+            if q.u(1) != 1:
+                raise Hdf5Error("chunk B-tree type")
+            level, used = q.u(1), q.u(2)
+            q.skip(2 * self.O)
+            for _ in range(used):
+                csize, mask = q.u(4), q.u(4)
+                offs = [q.u(8) for _ in range(rank + 1)][:rank]
+                child = q.u(self.O)
+                if level > 0:
+                    node(child)
+                    continue
+                raw = b[child:child + csize]
+                for i, (fid, cd) in reversed(list(enumerate(filters))):
+                    if mask & (1 << i):
+                        continue
+                    if fid == 1:
+                        raw = zlib.decompress(raw)
+                    elif fid == 2:
+                        es = cd[0]
+                        raw = np.frombuffer(raw, np.uint8).reshape(es, -1).T.tobytes()
+                    elif fid == 3:
+                        raw = raw[:-4]                  # fletcher32 checksum
+                    else:
+                        raise NotImplementedError(f"filter {fid}")
+                chunk = np.frombuffer(raw, dtype=dtype, count=int(np.prod(cdims))).reshape(cdims)
+                sl = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, cdims, shape))
+                out[sl] = chunk[tuple(slice(0, s.stop - s.start) for s in sl)]
+
+        if btree != _UNDEF & ((1 << (8 * self.O)) - 1):
+            node(btree)
+        return out.tobytes()

@@ -4,8 +4,11 @@ Run HERE (the container that has /root/reference); the GPU box does not.  Reads 
 mesh files -- Gmsh 4.1 `.msh` of `meshes/3DTetrahedra_Kershaw/3DKershawTetra1` (the Kershaw family, tetrahedrised) and of
 `meshes/3DHexaèdres/mesh_hexa_3`, `mesh_hexa_4` -- and stores what a cell-centred upwind finite-volume assembly needs
 (what SOLVERLAB's Mesh/Cell/Face give reference src/TransportEquation.cxx:75-133): cell centres and volumes, and per
-interior face the two cells and the area vector pointing from the first to the second.  `meshes/3DKershaw/*.med`
-(polyhedral Kershaw cells) is HDF5 and cannot be read in this image (no HDF5 / MEDfile): it stays blocked.
+interior face the two cells and the area vector pointing from the first to the second.  The polyhedral Kershaw meshes
+of BASELINE config 5 proper, `meshes/3DKershaw/Kershaw{1,2}.med`, exist as MED (HDF5) only: they are read with the
+package's own minimal HDF5 reader (circulantpreconditioner_b200/hdf5_min.py, med.py -- no HDF5 / MEDfile library in this
+image); the same reader applied to `mesh_hexa_3.med` / `3DKershawTetra1.med` reproduces the Gmsh-derived fixtures
+(tests/test_med_reader.py).
 
     python tests/golden/make_mesh_fixtures.py          -> tests/golden/mesh_*.npz
 """
@@ -13,6 +16,8 @@ import os
 import sys
 
 import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 REF = "/root/reference/meshes"
 OUT = os.path.dirname(os.path.abspath(__file__))
@@ -111,7 +116,22 @@ def fv_geometry(xyz, cells, kind):
     return centre, vol, surf, np.asarray(fc, dtype=np.int32), np.asarray(fa), len(seen)
 
 
+def med_fixtures():
+    from circulantpreconditioner_b200 import med
+    for name, rel in (("kershaw1", "3DKershaw/Kershaw1.med"), ("kershaw2", "3DKershaw/Kershaw2.med")):
+        path = os.path.join(REF, rel)
+        xyz, cells = med.read_med_mesh(path)
+        centre, vol, surf, fc, fa, nborder = med.fv_geometry(xyz, cells)
+        lo, hi = xyz.min(axis=0), xyz.max(axis=0)
+        assert abs(vol.sum() - np.prod(hi - lo)) < 1e-12 * np.prod(hi - lo), (name, vol.sum())
+        np.savez_compressed(os.path.join(OUT, f"mesh_{name}.npz"), centre=centre, volume=vol, surface=surf, face_cells=fc,
+                            face_area=fa, bbox=np.stack([lo, hi]), source=os.path.relpath(path, "/root/reference"))
+        print(f"{name}: {len(xyz)} nodes, {len(cells)} polyhedra, {len(fc)} interior faces, {nborder} border faces, "
+              f"volume {vol.sum():.6f}, cell volumes {vol.min():.3e} .. {vol.max():.3e}, bbox {lo} .. {hi}")
+
+
 def main():
+    med_fixtures()
     jobs = [("kershaw_tetra1", os.path.join(REF, "3DTetrahedra_Kershaw", "3DKershawTetra1.msh")),
             ("hexa_3", os.path.join(REF, "3DHexaèdres", "mesh_hexa_3.msh")),
             ("hexa_4", os.path.join(REF, "3DHexaèdres", "mesh_hexa_4.msh"))]
