@@ -9,6 +9,8 @@ There is no CPU fallback: importing works without a GPU (so the ABI can be inspe
 raises ``CpcError`` when no CUDA device is present, and importing raises if the shared library was not built.
 """
 from ._lib import CpcError, lib, library_path, build_library  # noqa: F401
-from .plan import CirculantPlan, nccl_unique_id, slab_range  # noqa: F401
+from .plan import (CirculantPlan, nccl_unique_id, slab_range, pencil_layout, pencil_steps, pencil_group,  # noqa: F401
+                   pencil_apply_lockstep)
 
-__all__ = ["CirculantPlan", "CpcError", "lib", "library_path", "build_library", "nccl_unique_id", "slab_range"]
+__all__ = ["CirculantPlan", "CpcError", "lib", "library_path", "build_library", "nccl_unique_id", "slab_range",
+           "pencil_layout", "pencil_steps", "pencil_group", "pencil_apply_lockstep"]

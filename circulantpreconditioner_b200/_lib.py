@@ -32,12 +32,25 @@ class PlanInfo(ctypes.Structure):
                 ("kernel_launches", ctypes.c_uint64), ("h2d_bytes", ctypes.c_uint64), ("d2h_bytes", ctypes.c_uint64)]
 
 
+class PencilLayout(ctypes.Structure):
+    _fields_ = [("r", ctypes.c_int), ("c", ctypes.c_int), ("nxl", ctypes.c_int), ("x0", ctypes.c_int),
+                ("nyl", ctypes.c_int), ("y0", ctypes.c_int), ("nyl2", ctypes.c_int), ("y02", ctypes.c_int),
+                ("nzl", ctypes.c_int), ("z0", ctypes.c_int), ("local_elems", ctypes.c_int64)]
+
+
+class PencilStep(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("dir", ctypes.c_int), ("a", ctypes.c_int64), ("b", ctypes.c_int64),
+                ("inner", ctypes.c_int64), ("scale", ctypes.c_double)]
+
+
 # every symbol include/circulantpc.h declares: name -> (restype, argtypes)
 _vp, _i, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
 _dp = ctypes.POINTER(ctypes.c_double)
 _i64p = ctypes.POINTER(ctypes.c_int64)
 ABI = {
     "cpc_plan_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(PlanDesc)]),
+    "cpc_plan_create_pencil": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(PlanDesc), _i, _i]),
+    "cpc_pencil_apply_lockstep": (_i, [ctypes.POINTER(_vp), _i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i]),
     "cpc_destroy": (_i, [_vp]),
     "cpc_set_stream": (_i, [_vp, _vp]),
     "cpc_sync": (_i, [_vp]),
@@ -62,6 +75,10 @@ ABI = {
     "cpc_slab_range": (_i, [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     "cpc_slab_send_chunk": (_i, [_i, _i, _i, _i, _i, _i, _i, _i64p, _i64p]),
     "cpc_slab_recv_chunk": (_i, [_i, _i, _i, _i, _i, _i, _i, _i64p, _i64p]),
+    "cpc_pencil_layout": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(PencilLayout)]),
+    "cpc_pencil_steps": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(PencilStep), _i, ctypes.POINTER(_i)]),
+    "cpc_pencil_group": (_i, [_i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
+    "cpc_pencil_swap_source": (ctypes.c_int64, [ctypes.c_int64] * 4),
     "cpc_symbol_recurrence_lambda": (_i, [_i, _i, _i, _dp, _dp, _dp, _dp]),
     "cpc_nccl_unique_id": (_i, [_vp]),
 }
@@ -70,6 +87,7 @@ CPC_MAX_PASSES = 16
 CPC_NCCL_UNIQUE_ID_BYTES = 128
 DTYPES = {"c128": 0, "c64": 1, "f64": 2, "f32": 3}
 MEM_DEVICE, MEM_HOST = 0, 1
+PSTEP_PASS_X, PSTEP_PASS_Y, PSTEP_MIDDLE, PSTEP_SWAP, PSTEP_A2A_ROW, PSTEP_A2A_COL = range(6)
 OPTIONS = {"z_recurrence": 1, "l2_chunk_bytes": 2, "chain_streams": 3, "z_line_form": 4}
 
 

@@ -5,7 +5,10 @@
 #include <cstring>
 #include <new>
 
+#include <vector>
+
 #include "dist.h"
+#include "pencil.h"
 #include "plan.h"
 
 namespace cpc {
@@ -79,7 +82,10 @@ int cpc_device_count(void)
     return n;
 }
 
-int cpc_plan_create(cpc_plan *plan, const cpc_plan_desc *d)
+static int check_alignment(const void *a, const void *b, int mem_kind, const char *who);
+
+// p_rows == 0: the z-slab / single-rank plan of cpc_plan_create; otherwise a pencil plan on a p_rows x p_cols grid
+static int create_plan(cpc_plan *plan, const cpc_plan_desc *d, int p_rows, int p_cols)
 {
     if (!plan || !d) { set_error("cpc_plan_create: null argument"); return CPC_ERR_ARG; }
     *plan = nullptr;
@@ -103,7 +109,9 @@ int cpc_plan_create(cpc_plan *plan, const cpc_plan_desc *d)
     if (dev < 0) CPC_CUDA(cudaGetDevice(&dev));
     if (dev >= ndev) { set_error("cpc_plan_create: device %d out of range (%d visible)", dev, ndev); return CPC_ERR_ARG; }
     CPC_CUDA(cudaSetDevice(dev));
-    PlanBase *impl = (d->dtype == CPC_C128 || d->dtype == CPC_F64) ? make_plan_f64() : make_plan_f32();
+    const bool f64 = (d->dtype == CPC_C128 || d->dtype == CPC_F64);
+    PlanBase *impl = p_rows > 0 ? (f64 ? make_pencil_plan_f64(p_rows, p_cols) : make_pencil_plan_f32(p_rows, p_cols))
+                                : (f64 ? make_plan_f64() : make_plan_f32());
     if (!impl) { set_error("out of host memory"); return CPC_ERR_NOMEM; }
     impl->desc = *d;
     impl->device = dev;
@@ -114,6 +122,74 @@ int cpc_plan_create(cpc_plan *plan, const cpc_plan_desc *d)
     if (!p) { delete impl; set_error("out of host memory"); return CPC_ERR_NOMEM; }
     p->impl = impl;
     *plan = p;
+    return CPC_OK;
+}
+
+int cpc_plan_create(cpc_plan *plan, const cpc_plan_desc *d) { return create_plan(plan, d, 0, 0); }
+
+int cpc_plan_create_pencil(cpc_plan *plan, const cpc_plan_desc *d, int p_rows, int p_cols)
+{
+    if (p_rows < 1 || p_cols < 1) { set_error("cpc_plan_create_pencil: the grid must be at least 1 x 1 (got %d x %d)", p_rows, p_cols); return CPC_ERR_ARG; }
+    return create_plan(plan, d, p_rows, p_cols);
+}
+
+// One apply on all ranks of a pencil grid whose plans live in this process (created without an NCCL id): the local steps
+// run on every plan's own device and stream, the all-to-alls are peer copies between the plans' buffers.
+int cpc_pencil_apply_lockstep(cpc_plan *plans, int nplans, const void *const *b, void *const *x, int mem_kind)
+{
+    if (!plans || nplans < 1 || !b || !x) { set_error("cpc_pencil_apply_lockstep: null argument"); return CPC_ERR_ARG; }
+    std::vector<PencilIface *> pp((size_t)nplans);
+    for (int i = 0; i < nplans; ++i) {
+        CHECK_PLAN(plans[i]);
+        pp[i] = dynamic_cast<PencilIface *>(plans[i]->impl);
+        if (!pp[i]) { set_error("cpc_pencil_apply_lockstep: plan %d is not a pencil plan", i); return CPC_ERR_ARG; }
+        const PencilLayout &L = pp[i]->layout(), &L0 = pp[0]->layout();
+        if (!pp[i]->in_process() || L.pr * L.pc != nplans || L.rank != i || L.nx != L0.nx || L.ny != L0.ny || L.nz != L0.nz ||
+            L.pr != L0.pr || L.pc != L0.pc || pp[i]->elem_bytes() != pp[0]->elem_bytes()) {
+            set_error("cpc_pencil_apply_lockstep: plans[i] must be rank i of one p_rows x p_cols grid of %d in-process plans", nplans);
+            return CPC_ERR_ARG;
+        }
+    }
+    auto sync_all = [&]() -> int {
+        for (int i = 0; i < nplans; ++i) {
+            CPC_CUDA(cudaSetDevice(plans[i]->impl->device));
+            CPC_CUDA(cudaStreamSynchronize(plans[i]->impl->stream));
+        }
+        return CPC_OK;
+    };
+    int rc;
+    for (int i = 0; i < nplans; ++i) {
+        if ((rc = check_alignment(b[i], x[i], mem_kind, "cpc_pencil_apply_lockstep"))) return rc;
+        if ((rc = pp[i]->begin(b[i], x[i], mem_kind))) return rc;
+    }
+    const std::vector<PencilStep> &steps = pp[0]->steps();
+    std::vector<const void *> send((size_t)nplans);
+    std::vector<void *> recv((size_t)nplans);
+    std::vector<int> peers((size_t)nplans);
+    for (size_t k = 0; k < steps.size(); ++k) {
+        const int kind = steps[k].kind;
+        if (kind != PSTEP_A2A_ROW && kind != PSTEP_A2A_COL) {
+            for (int i = 0; i < nplans; ++i)
+                if ((rc = pp[i]->local_step(k))) return rc;
+            continue;
+        }
+        for (int i = 0; i < nplans; ++i)
+            if ((rc = pp[i]->exchange_buffers(k, &send[i], &recv[i]))) return rc;
+        if ((rc = sync_all())) return rc;                    // every rank's send buffer is complete
+        for (int i = 0; i < nplans; ++i) {
+            const PencilLayout &L = pp[i]->layout();
+            const int np = pencil_group(L, kind, peers.data());
+            const size_t chunk = pp[i]->elem_bytes() * (size_t)(L.nloc / np);
+            const int me = kind == PSTEP_A2A_ROW ? L.r : L.c;            // this rank's place in its group
+            CPC_CUDA(cudaSetDevice(plans[i]->impl->device));
+            for (int q = 0; q < np; ++q)
+                CPC_CUDA(cudaMemcpyAsync((char *)recv[peers[q]] + (size_t)me * chunk, (const char *)send[i] + (size_t)q * chunk,
+                                         chunk, cudaMemcpyDefault, plans[i]->impl->stream));
+        }
+        if ((rc = sync_all())) return rc;                    // every chunk has landed
+    }
+    for (int i = 0; i < nplans; ++i)
+        if ((rc = pp[i]->finish())) return rc;
     return CPC_OK;
 }
 
@@ -309,6 +385,57 @@ int cpc_slab_recv_chunk(int nx, int ny, int nz, int ncomp, int nranks, int rank,
     *offset = (long long)zs.start * yr.count * W;
     *count = (long long)zs.count * yr.count * W;
     return CPC_OK;
+}
+
+int cpc_pencil_layout(int nx, int ny, int nz, int p_rows, int p_cols, int rank, cpc_pencil_layout_t *out)
+{
+    PencilLayout L;
+    if (!out || pencil_make_layout(nx, ny, nz, p_rows, p_cols, rank, &L)) {
+        set_error("cpc_pencil_layout: bad grid, rank or extents (nx, ny divisible by p_rows; ny, nz by p_cols)");
+        return CPC_ERR_ARG;
+    }
+    out->r = L.r; out->c = L.c;
+    out->nxl = L.nxl; out->x0 = L.x0; out->nyl = L.nyl; out->y0 = L.y0;
+    out->nyl2 = L.nyl2; out->y02 = L.y02; out->nzl = L.nzl; out->z0 = L.z0;
+    out->local_elems = L.nloc;
+    return CPC_OK;
+}
+
+int cpc_pencil_steps(int nx, int ny, int nz, int p_rows, int p_cols, int rank, cpc_pencil_step_t *steps, int max_steps, int *nsteps)
+{
+    PencilLayout L;
+    if (!nsteps || pencil_make_layout(nx, ny, nz, p_rows, p_cols, rank, &L)) {
+        set_error("cpc_pencil_steps: bad grid, rank or extents");
+        return CPC_ERR_ARG;
+    }
+    const std::vector<PencilStep> s = pencil_schedule(L);
+    *nsteps = (int)s.size();
+    if (!steps) return CPC_OK;
+    if (max_steps < (int)s.size()) { set_error("cpc_pencil_steps: %d steps, room for %d", (int)s.size(), max_steps); return CPC_ERR_ARG; }
+    for (size_t k = 0; k < s.size(); ++k) {
+        steps[k].kind = s[k].kind; steps[k].dir = s[k].dir;
+        steps[k].a = s[k].A; steps[k].b = s[k].B; steps[k].inner = s[k].inner;
+        steps[k].scale = s[k].scale;
+    }
+    return CPC_OK;
+}
+
+int cpc_pencil_group(int nx, int ny, int nz, int p_rows, int p_cols, int rank, int step_kind, int *peers, int *npeers)
+{
+    PencilLayout L;
+    if (!peers || !npeers || (step_kind != PSTEP_A2A_ROW && step_kind != PSTEP_A2A_COL) ||
+        pencil_make_layout(nx, ny, nz, p_rows, p_cols, rank, &L)) {
+        set_error("cpc_pencil_group: bad argument");
+        return CPC_ERR_ARG;
+    }
+    *npeers = pencil_group(L, step_kind, peers);
+    return CPC_OK;
+}
+
+int64_t cpc_pencil_swap_source(int64_t o, int64_t a, int64_t b, int64_t inner)
+{
+    if (a < 1 || b < 1 || inner < 1 || o < 0 || o >= a * b * inner) return -1;
+    return pencil_swap_source(o, a, b, inner);
 }
 
 int cpc_symbol_recurrence_lambda(int nx, int ny, int nz, const double *ax, const double *ay, const double *az, double *lambda_z)

@@ -207,6 +207,25 @@ int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes
     return CPC_OK;
 }
 
+int dist_alltoall_group(DistState &d, const void *send, void *recv, size_t chunk_bytes, const int *peers, int npeers,
+                        cudaStream_t stream)
+{
+    if (npeers == 1) {                     // a group of one: the "exchange" is a copy
+        CPC_CUDA(cudaMemcpyAsync(recv, send, chunk_bytes, cudaMemcpyDeviceToDevice, stream));
+        return CPC_OK;
+    }
+    if (!d.comm) { set_error("group all-to-all without an NCCL communicator"); return CPC_ERR_STATE; }
+    CPC_NCCL(g_api.GroupStart());
+    for (int q = 0; q < npeers; ++q) {
+        CPC_NCCL(g_api.Send((const char *)send + (size_t)q * chunk_bytes, chunk_bytes, NCCL_UINT8, peers[q],
+                            (ncclComm_tt)d.comm, stream));
+        CPC_NCCL(g_api.Recv((char *)recv + (size_t)q * chunk_bytes, chunk_bytes, NCCL_UINT8, peers[q], (ncclComm_tt)d.comm,
+                            stream));
+    }
+    CPC_NCCL(g_api.GroupEnd());
+    return CPC_OK;
+}
+
 struct FlagPeers {
     unsigned long long *p[CPC_DIST_MAX_PEERS];
 };

@@ -31,6 +31,11 @@ void dist_destroy(DistState &d);
 // Rank r sends bytes [q*chunk_bytes, (q+1)*chunk_bytes) of `send` to rank q and receives rank s's chunk into
 // recv + s*chunk_bytes (grouped ncclSend/ncclRecv: NCCL 2.27 has no all-to-all entry point).
 int dist_alltoall(DistState &d, const void *send, void *recv, size_t chunk_bytes, cudaStream_t stream);
+// The same among a subset of the ranks (the row or column group of a pencil grid, pencil.h), on the world communicator:
+// chunk q of `send` goes to rank peers[q], chunk q of `recv` comes from rank peers[q]; peers lists the group in the same
+// order on every member and contains this rank.  Groups are disjoint, so all groups exchange at once.
+int dist_alltoall_group(DistState &d, const void *send, void *recv, size_t chunk_bytes, const int *peers, int npeers,
+                        cudaStream_t stream);
 // ncclAllGather of `bytes` per rank (the z-slab carry exchange of the recurrence middle pass, zsolve.cuh).
 int dist_allgather(DistState &d, const void *send, void *recv, size_t bytes, cudaStream_t stream);
 // In-place sum over ranks of `count` floats (agreement flags of collective set-up steps).

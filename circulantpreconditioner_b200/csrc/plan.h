@@ -77,6 +77,9 @@ int build_diag_separable(int nx, int ny, int nz, const double *cx, const double 
                          double lz, int z0, int nzl, void *diag, int mem_kind);
 PlanBase *make_plan_f64();
 PlanBase *make_plan_f32();
+// pencil (p_rows x p_cols) plans, pencil_impl.cuh
+PlanBase *make_pencil_plan_f64(int p_rows, int p_cols);
+PlanBase *make_pencil_plan_f32(int p_rows, int p_cols);
 
 }  // namespace cpc
 

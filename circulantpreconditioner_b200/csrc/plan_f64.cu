@@ -1,5 +1,5 @@
 // plan_f64.cu -- complex128 instantiation of the plan and its kernels (PetscScalar of a complex PETSc build).
-#include "plan_impl.cuh"
+#include "pencil_impl.cuh"
 
 #include <vector>
 
@@ -116,5 +116,6 @@ int build_diag_separable(int nx, int ny, int nz, const double *cx, const double 
 }
 
 PlanBase *make_plan_f64() { return new PlanT<double>(); }
+PlanBase *make_pencil_plan_f64(int p_rows, int p_cols) { return new PencilPlanT<double>(p_rows, p_cols); }
 
 }  // namespace cpc

@@ -30,6 +30,51 @@ def slab_range(n, nranks, rank):
     return s.value, c.value
 
 
+def pencil_layout(nx, ny, nz, p_rows, p_cols, rank):
+    """What rank (r, c) = (rank % p_rows, rank / p_rows) of a pencil grid holds (include/circulantpc.h,
+    cpc_pencil_layout_t) as a dict."""
+    out = _lib.PencilLayout()
+    check(lib().cpc_pencil_layout(nx, ny, nz, p_rows, p_cols, rank, ctypes.byref(out)))
+    return {f[0]: getattr(out, f[0]) for f in out._fields_}
+
+
+def pencil_steps(nx, ny, nz, p_rows, p_cols, rank):
+    """The steps of one apply on a pencil grid, the list the GPU plan executes (cpc_pencil_steps) as dicts."""
+    n = ctypes.c_int()
+    check(lib().cpc_pencil_steps(nx, ny, nz, p_rows, p_cols, rank, None, 0, ctypes.byref(n)))
+    arr = (_lib.PencilStep * n.value)()
+    check(lib().cpc_pencil_steps(nx, ny, nz, p_rows, p_cols, rank, arr, n.value, ctypes.byref(n)))
+    return [{f[0]: getattr(st, f[0]) for f in st._fields_} for st in arr]
+
+
+def pencil_group(nx, ny, nz, p_rows, p_cols, rank, step_kind):
+    """Ranks of the row (step_kind 4) / column (5) group of `rank`, in chunk order."""
+    peers = (ctypes.c_int * (p_rows * p_cols))()
+    n = ctypes.c_int()
+    check(lib().cpc_pencil_group(nx, ny, nz, p_rows, p_cols, rank, step_kind, peers, ctypes.byref(n)))
+    return [peers[i] for i in range(n.value)]
+
+
+def pencil_apply_lockstep(plans, bs, xs):
+    """One apply on every rank of a pencil grid whose plans all live in this process (created with pencil=(pr, pc),
+    nranks = pr * pc and no nccl_id): plans[i] is rank i, bs[i] / xs[i] its local arrays (cpc_pencil_apply_lockstep)."""
+    n = len(plans)
+    if len(bs) != n or len(xs) != n:
+        raise ValueError("one input and one output per plan")
+    pb, px, keep, kinds = (ctypes.c_void_p * n)(), (ctypes.c_void_p * n)(), [], set()
+    for i, (p, b, x) in enumerate(zip(plans, bs, xs)):
+        a, ka, k1 = _ptr_and_kind(b, np_dtype=p.np_dtype, count=p.local_elems, device=p.device, what="input")
+        c, kc, k2 = _ptr_and_kind(x, writable=True, np_dtype=p.np_dtype, count=p.local_elems, device=p.device, what="output")
+        pb[i], px[i] = a, c
+        keep += [k1, k2]
+        kinds |= {ka, kc}
+    if len(kinds) != 1:
+        raise ValueError("all inputs and outputs must live in the same memory kind")
+    handles = (ctypes.c_void_p * n)(*[p._h for p in plans])
+    check(lib().cpc_pencil_apply_lockstep(handles, n, pb, px, kinds.pop()))
+    return xs
+
+
 def _ptr_and_kind(a, writable=False, np_dtype=None, count=None, device=None, what="array"):
     """(address, mem_kind, keepalive) of a torch tensor or numpy array.
 
@@ -64,7 +109,9 @@ _TORCH_DTYPES = ({"complex128": torch.complex128, "complex64": torch.complex64, 
 
 class CirculantPlan:
     def __init__(self, nx, ny=1, nz=1, ncomp=1, dtype="c128", stream=None, device=-1, nranks=1, rank=0,
-                 nccl_id: bytes | None = None):
+                 nccl_id: bytes | None = None, pencil=None):
+        """pencil=(p_rows, p_cols): a pencil grid instead of z-slabs (cpc_plan_create_pencil); nranks = p_rows * p_cols.
+        Without nccl_id such a plan is driven together with its peers by pencil_apply_lockstep."""
         self._h = ctypes.c_void_p()
         self.nx, self.ny, self.nz, self.ncomp = int(nx), int(ny), int(nz), int(ncomp)
         self.dtype = dtype
@@ -75,7 +122,11 @@ class CirculantPlan:
         d = _lib.PlanDesc(self.nx, self.ny, self.nz, self.ncomp, _lib.DTYPES[dtype], int(nranks), int(rank),
                           ctypes.cast(self._id_buf, ctypes.c_void_p) if self._id_buf else None,
                           ctypes.c_void_p(stream or 0), int(device))
-        check(lib().cpc_plan_create(ctypes.byref(self._h), ctypes.byref(d)))
+        self.pencil = tuple(int(v) for v in pencil) if pencil else None
+        if self.pencil:
+            check(lib().cpc_plan_create_pencil(ctypes.byref(self._h), ctypes.byref(d), *self.pencil))
+        else:
+            check(lib().cpc_plan_create(ctypes.byref(self._h), ctypes.byref(d)))
         inf = self.info()
         self.local_elems = int(inf["local_elems"])        # elements of b / x held by this rank
         self.local_cells = self.local_elems // self.ncomp
@@ -208,4 +259,5 @@ class CirculantPlan:
         return {f[0]: (list(getattr(inf, f[0])) if f[0] == "fast_path" else getattr(inf, f[0])) for f in inf._fields_}
 
 
-__all__ = ["CirculantPlan", "CpcError", "nccl_unique_id", "slab_range"]
+__all__ = ["CirculantPlan", "CpcError", "nccl_unique_id", "slab_range", "pencil_layout", "pencil_steps", "pencil_group",
+           "pencil_apply_lockstep"]

@@ -82,6 +82,19 @@ typedef struct {
  * cpc_destroy      <- destroyFFTPrec3D (PCSHELLFft_3D.cxx:86-99)
  * The plan owns twiddle tables, symbol tables, staging buffers and (multi-rank) the NCCL communicator. */
 int cpc_plan_create(cpc_plan *plan, const cpc_plan_desc *desc);
+/* The same on a p_rows x p_cols pencil grid (p_rows * p_cols == desc->nranks; rank = c * p_rows + r) instead of z-slabs
+ * <- MatCreateFFT(PETSC_COMM_WORLD, ...) (PCSHELLFft_3D.cxx:35), whose fftw-mpi distribution is slab-only: the pencil
+ * grid is what BASELINE config 4 names and what lifts the limit nranks <= nz.  b and x of rank (r, c) hold the planes
+ * z in slab c (of p_cols) and the rows y in slab r (of p_rows), all of x: index i + nx*(jl + nyl*kl)
+ * (cpc_pencil_layout below).  Needs nx, ny divisible by p_rows and ny, nz by p_cols.  Scalar complex plans with the
+ * transport / separable symbol; cpc_apply only (5 transform passes, 6 reordering passes, 4 all-to-alls within the row /
+ * column groups).  With desc->nccl_unique_id == NULL and nranks > 1 the plan has no communicator of its own: the plans
+ * of all ranks then live in one process and are driven together by cpc_pencil_apply_lockstep. */
+int cpc_plan_create_pencil(cpc_plan *plan, const cpc_plan_desc *desc, int p_rows, int p_cols);
+/* One cpc_apply on every rank of a pencil grid from a single process: plans[i] is rank i (i < p_rows * p_cols, created
+ * with nccl_unique_id == NULL, on any visible devices), b[i] / x[i] its local arrays.  The exchanges are peer copies
+ * between the plans' buffers; returns after they have all been queued and the streams have been synchronised. */
+int cpc_pencil_apply_lockstep(cpc_plan *plans, int nplans, const void *const *b, void *const *x, int mem_kind);
 int cpc_destroy(cpc_plan plan);
 int cpc_set_stream(cpc_plan plan, void *stream);
 int cpc_sync(cpc_plan plan);
@@ -175,7 +188,8 @@ typedef struct {
     int nx, ny, nz, ncomp, dtype, nranks, rank;
     int symbol_kind;
     int passes_per_apply;          /* HBM passes (kernel launches) of one cpc_apply */
-    int dist_mode;                 /* 0 single rank, 1 NCCL all-to-all transposes, 2 transposes fused into the passes
+    int dist_mode;                 /* 4: pencil grid (cpc_plan_create_pencil).  Otherwise:
+                                      0 single rank, 1 NCCL all-to-all transposes, 2 transposes fused into the passes
                                       (stores pushed to IPC-mapped peer buffers over NVLink), 3 no transposes: the
                                       current (transport) symbol's middle pass is a recurrence along z, the z-slabs
                                       only exchange one carry per (kx, ky) line */
@@ -204,6 +218,34 @@ int cpc_slab_send_chunk(int nx, int ny, int nz, int ncomp, int nranks, int rank,
 /* Same for the chunk received from rank `s` into the transposed buffer [z_glob][y_loc][x]. */
 int cpc_slab_recv_chunk(int nx, int ny, int nz, int ncomp, int nranks, int rank, int s,
                         int64_t *offset, int64_t *count);
+/* Pencil grid (cpc_plan_create_pencil): what rank (r, c) = (rank % p_rows, rank / p_rows) holds in the three
+ * distributions -- X pencils [z in slab c][y in slab r][x] (b and x), Y pencils [z in slab c][y][x in slab r],
+ * Z pencils [z][y in slab c (of p_cols)][x in slab r] (the middle pass). */
+typedef struct {
+    int r, c;
+    int nxl, x0;                   /* x slab of the Y and Z pencils (over p_rows) */
+    int nyl, y0;                   /* y slab of the X pencils (over p_rows) */
+    int nyl2, y02;                 /* y slab of the Z pencils (over p_cols) */
+    int nzl, z0;                   /* z slab of the X and Y pencils (over p_cols) */
+    int64_t local_elems;
+} cpc_pencil_layout_t;
+int cpc_pencil_layout(int nx, int ny, int nz, int p_rows, int p_cols, int rank, cpc_pencil_layout_t *out);
+/* The steps of one apply on that grid, in order (the very list the GPU plan executes).  kind: 0 x pass, 1 y pass,
+ * 2 middle pass (forward z, division, backward z, scaled by 1 / (nxl nyl2 nz)), 3 SWAP: in[a][b][inner] ->
+ * out[b][a][inner] times scale, 4 / 5 all-to-all of local_elems / group size elements per peer within the row /
+ * column group.  dir: -1 forward, +1 backward (passes).  steps == NULL: only *nsteps is written. */
+typedef struct {
+    int kind, dir;
+    int64_t a, b, inner;
+    double scale;
+} cpc_pencil_step_t;
+int cpc_pencil_steps(int nx, int ny, int nz, int p_rows, int p_cols, int rank, cpc_pencil_step_t *steps, int max_steps,
+                     int *nsteps);
+/* The ranks of the row (step_kind 4) or column (5) group of `rank`, in chunk order: chunk q of the send buffer goes to
+ * peers[q], chunk q of the receive buffer comes from peers[q]. */
+int cpc_pencil_group(int nx, int ny, int nz, int p_rows, int p_cols, int rank, int step_kind, int *peers, int *npeers);
+/* Source element of output element o of SWAP(a, b, inner) -- the index map of the reordering kernel; -1 on bad arguments. */
+int64_t cpc_pencil_swap_source(int64_t o, int64_t a, int64_t b, int64_t inner);
 /* The test the library applies to a separable symbol before it takes the recurrence form of the middle pass (see
  * cpc_apply): tables ax[nx], ay[ny], az[nz] as HOST complex128 arrays, already multiplied by their lambdas, the "+1"
  * of build_diag_mat_vec_3D (FftLinearSolver_3D.c:155) riding on ay.  Returns 1 and *lambda_z when az is
