@@ -20,7 +20,11 @@ Parity pinning: ``tests/golden/make_golden.py`` runs the reference's own
 Python tests (imported from ``/root/reference``) and stores their inputs and
 outputs; ``tests/test_oracle.py`` checks this module against those fixtures
 and against the integer known-answer vectors of the reference's C tests
-(SURVEY.md Appendix B).
+(SURVEY.md Appendix B).  Second pin: the reference's own
+``src/FftLinearSolver_3D.c``, compiled unmodified against a CPU stand-in for
+the PETSc calls it makes (``oracle/petsc_standin/``, ``oracle/_ref/``), must
+agree with this module on Diag, on every solver entry point and on the
+fixtures (``tests/test_reference_c.py``).
 """
 from __future__ import annotations
 
