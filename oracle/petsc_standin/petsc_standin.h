@@ -1,7 +1,8 @@
 /* petsc_standin.h -- TEST INFRASTRUCTURE ONLY.  A minimal CPU stand-in for the ~30 PETSc calls that the reference's
  * src/FftLinearSolver_3D.c makes, so that THAT FILE, unmodified and compiled from where it lies under /root/reference,
  * can run in this image (no PETSc, FFTW or MPI here) and pin the oracle: oracle/Makefile target
- * _ref/libreference_fftsolver.so, used by tests/test_reference_c.py only.
+ * _ref/libreference_fftsolver.so, used by tests/test_reference_c.py only.  The reference's own C test programs
+ * (tests/FFTDirectSolver/testFftSolver_{1D,2D,3D}.c) build against it too (_ref/testFftSolver_*).
  *
  * What is the reference's and what is ours: everything FftLinearSolver_3D.c does itself -- the transport column
  * (:80-90), the Kronecker layout of Diag (:92-164), the order forward transform / VecPointwiseDivide / backward
@@ -14,8 +15,11 @@
  */
 #ifndef PETSC_STANDIN_H
 #define PETSC_STANDIN_H
-#include <complex.h>
+#include <assert.h>      /* the reference's C tests call assert / strcmp / printf-style output without including these: */
+#include <complex.h>     /* with a real PETSc they arrive through petscsys.h */
 #include <stddef.h>
+#include <stdio.h>
+#include <string.h>
 
 #define PETSC_USE_COMPLEX 1
 typedef int PetscErrorCode;
@@ -31,12 +35,22 @@ typedef const char *MatType;
 #define PETSC_COMM_WORLD 1
 #define PETSC_COMM_SELF 2
 #define MATFFTW "fftw"
+#define MATAIJ "aij"
+#define PETSC_DECIDE (-1)
+#define PETSC_VIEWER_STDOUT_WORLD ((PetscViewer)0)
+typedef void *PetscViewer;
+typedef enum { NORM_1 = 0, NORM_2 = 1, NORM_INFINITY = 3 } NormType;
+typedef enum { MAT_FLUSH_ASSEMBLY = 1, MAT_FINAL_ASSEMBLY = 0 } MatAssemblyType;
+typedef enum { MAT_INITIAL_MATRIX = 0, MAT_REUSE_MATRIX = 1 } MatReuse;
+typedef enum { MAT_DO_NOT_COPY_VALUES = 0, MAT_COPY_VALUES = 1 } MatDuplicateOption;
+typedef enum { DIFFERENT_NONZERO_PATTERN = 0, SUBSET_NONZERO_PATTERN = 1, SAME_NONZERO_PATTERN = 2 } MatStructure;
 typedef enum { NOT_SET_VALUES = 0, INSERT_VALUES = 1, ADD_VALUES = 2 } InsertMode;
 
 #define PetscFunctionBeginUser do { } while (0)
 #define PetscFunctionReturn(v) return (v)
 #define PetscCall(call) do { PetscErrorCode ierr_standin_ = (call); if (ierr_standin_) return ierr_standin_; } while (0)
 #define PetscCheck(cond, comm, code, ...) do { if (!(cond)) return (code); } while (0)
+#define SETERRQ(comm, code, ...) return (code)
 
 typedef struct _p_Vec *Vec;
 typedef struct _p_Mat *Mat;
@@ -68,4 +82,24 @@ PetscErrorCode MatCreateVecsFFTW(Mat A, Vec *x, Vec *y, Vec *z);
 PetscErrorCode MatMult(Mat A, Vec x, Vec y);                   /* unnormalised forward DFT */
 PetscErrorCode MatMultTranspose(Mat A, Vec x, Vec y);          /* unnormalised backward DFT */
 PetscErrorCode MatDestroy(Mat *A);
+
+/* ---- what the reference's C test programs (tests/FFTDirectSolver/testFftSolver_{1D,2D,3D}.c) use on top: small AIJ
+ * matrices (held dense here: the tests build 4 x 4 .. 24 x 24 circulant matrices by Kronecker products), norms, output */
+PetscErrorCode PetscInitialize(int *argc, char ***argv, const char *file, const char *help);
+PetscErrorCode PetscFinalize(void);
+PetscErrorCode PetscPrintf(MPI_Comm comm, const char *fmt, ...);
+PetscErrorCode VecNorm(Vec v, NormType type, PetscReal *nrm);
+PetscErrorCode VecView(Vec v, PetscViewer viewer);
+PetscErrorCode MatCreateAIJ(MPI_Comm comm, PetscInt m, PetscInt n, PetscInt M, PetscInt N, PetscInt d_nz, const PetscInt *d_nnz,
+                            PetscInt o_nz, const PetscInt *o_nnz, Mat *A);
+PetscErrorCode MatSetValue(Mat A, PetscInt i, PetscInt j, PetscScalar v, InsertMode mode);
+PetscErrorCode MatAssemblyBegin(Mat A, MatAssemblyType t);
+PetscErrorCode MatAssemblyEnd(Mat A, MatAssemblyType t);
+PetscErrorCode MatShift(Mat A, PetscScalar a);
+PetscErrorCode MatSeqAIJKron(Mat A, Mat B, MatReuse reuse, Mat *C);      /* C = A (x) B */
+PetscErrorCode MatDuplicate(Mat A, MatDuplicateOption op, Mat *B);
+PetscErrorCode MatAXPY(Mat Y, PetscScalar a, Mat X, MatStructure str);   /* Y += a X */
+PetscErrorCode MatCreateVecs(Mat A, Vec *right, Vec *left);
+PetscErrorCode MatGetType(Mat A, MatType *type);
+PetscErrorCode MatView(Mat A, PetscViewer viewer);
 #endif

@@ -6,7 +6,8 @@ direct O(n^2) DFT with FFTW's conventions).  Everything that file does itself --
 Kronecker layout of Diag (:92-164), solve_3D's forward / divide / backward / VecScale(1/size) (:166-190), the wrappers
 with their lambdas and degenerate axes (:192-312) -- therefore runs exactly as the reference wrote it, and the oracle
 (oracle/circulant_oracle.py, circulant_oracle.c) must reproduce it, as must the fixtures generated from the reference's
-Python tests.  Needs the built library (made where /root/reference exists; it travels to the GPU box).
+Python tests.  The reference's own C test programs (tests/FFTDirectSolver/testFftSolver_{1D,2D,3D}.c) are built the same
+way and must run clean.  Needs the built files (made where /root/reference exists; they travel to the GPU box).
 """
 import os
 
@@ -118,6 +119,36 @@ def test_kat1_first_column_form_is_outside_this_file():
     Diag = np.fft.fft(f["col"])
     got = R.solve_3D(Diag, f["b"].astype(np.complex128), 4, 1, 1)
     assert np.allclose(got.real, f["x"], rtol=0, atol=1e-13) and np.allclose(got.real, [6.7, 2.9, 6.3, 20.1], atol=1e-13)
+
+
+def _run_reference_test_program(name):
+    import subprocess
+    exe = os.path.join(os.path.dirname(R.PATH), name)
+    if not os.path.exists(exe):
+        pytest.skip(f"{exe} is not built")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr          # their assert()s held and every PetscCall returned 0
+    return r.stdout
+
+
+def test_the_references_own_c_test_programs_run():
+    """tests/FFTDirectSolver/testFftSolver_{1D,2D,3D}.c of the reference, compiled unmodified against the stand-in
+    (oracle/Makefile): their own assertions hold, and what they print is the known-answer data of SURVEY.md appendix B."""
+    import re
+    out = _run_reference_test_program("testFftSolver_1D")
+    # KAT-1: column [1.5, -0.5, 0, 0], b = [0, 1, 8, 27] -> eigenvalues [1, 1.5+0.5i, 2, 1.5-0.5i], x = [6.7, 2.9, 6.3, 20.1]
+    sol = out.split("Vecteur solution x:")[1].split("Matrice circulante")[0]
+    vals = [float(t) for t in re.findall(r"^(-?\d+(?:\.\d+)?(?:e[-+]?\d+)?)\s*$", sol, flags=re.M)]
+    assert np.allclose(vals, [6.7, 2.9, 6.3, 20.1], rtol=0, atol=1e-13)
+    eig = out.split("Valeurs propres lambdas")[1].split("Vecteur second membre b:")[0]
+    assert "1.5 + 0.5 i" in eig and "1.5 - 0.5 i" in eig
+    res = float(re.search(r"norme du r.sidu = (\S+)", out).group(1))
+    assert res < 1e-13
+    for name in ("testFftSolver_2D", "testFftSolver_3D"):       # KAT-2 (3 x 2) and KAT-3 (4 x 3 x 2): X_ref[m] = m^3
+        out = _run_reference_test_program(name)
+        rr = float(re.search(r"Relative residual = (\S+)", out).group(1))
+        re_ = float(re.search(r"Relative error = (\S+)", out).group(1))
+        assert rr < 1e-14 and re_ < 1e-14, (name, rr, re_)
 
 
 @pytest.mark.gpu
