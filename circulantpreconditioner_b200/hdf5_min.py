@@ -16,7 +16,6 @@ Anything else raises NotImplementedError instead of guessing.
 """
 from __future__ import annotations
 
-import struct
 import zlib
 
 import numpy as np
