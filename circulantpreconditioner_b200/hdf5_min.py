@@ -4,12 +4,12 @@ Harness code for BASELINE config 5: no HDF5 library ex
 Kershaw meshes (meshes/3DKershaw/Kershaw{1,2}.med) ship as .med only.  Written from the published HDF5 file-format
 specification (version 3.0); covers exactly what those files use:
 
-  superblock        versions 0-3
+  superblock        versions 0-3, behind a user block too
   groups            new style: link messages in the object header (compact) or fractal heap (dense), and old style:
                     symbol table (B-tree v1 + local heap)
   object headers    version 1 and version 2 ("OHDR"), with continuation blocks
-  datasets          contiguous, compact, and chunked (B-tree v1 index; deflate / shuffle filters) layouts; fixed-point,
-                    floating-point and fixed-length string types
+  datasets          contiguous, compact, and chunked (B-tree v1 index; deflate / shuffle filters) layouts, layout
+                    message versions 1-3; fixed-point, floating-point and fixed-length string types
   attributes        versions 1-3, scalar or simple dataspaces of the same types
 
 Anything else raises NotImplementedError instead of guessing.
@@ -105,9 +105,14 @@ class File:
 
     # ------------------------------------------------------------------ superblock
     def _superblock(self):
-        base = self.b.find(_SIG)
-        if base != 0:
-            raise Hdf5Error("not an HDF5 file (or a user block precedes the superblock)")
+        # the superblock sits at 0 or, behind a user block, at 512, 1024, 2048, ...; file addresses count from there
+        base = 0
+        while self.b[base:base + 8] != _SIG:
+            base = 512 if base == 0 else 2 * base
+            if base + 8 > len(self.b):
+                raise Hdf5Error("not an HDF5 file")
+        if base:
+            self.b = self.b[base:]
         r = _Reader(self.b, 8)
         ver = r.u(1)
         if ver in (0, 1):
@@ -440,11 +445,27 @@ class File:
     def _read_layout(self, msgs, shape, dtype, strlen):
         r = _Reader(msgs[0x08][0])
         ver = r.u(1)
+        count = int(np.prod(shape)) if shape else 1
+        nbytes = count * dtype.itemsize
+        undef = _UNDEF & ((1 << (8 * self.O)) - 1)
+        if ver in (1, 2):                               # the layout message of HDF5 <= 1.6 writers
+            ndim, cls = r.u(1), r.u(1)
+            r.skip(5)
+            addr = r.u(self.O) if cls != 0 else undef
+            dims = [r.u(4) for _ in range(ndim)]
+            if cls == 0:
+                raw = r.raw(r.u(4))[:nbytes]
+            elif cls == 1:
+                raw = self.b[addr:addr + nbytes] if addr != undef else bytes(nbytes)
+            elif cls == 2:                              # dims = chunk extents, the element size last
+                raw = self._read_chunked(addr, dims[:-1], shape, dtype, msgs.get(0x0B))
+            else:
+                raise NotImplementedError("data layout class")
+            a = np.frombuffer(raw, dtype=dtype, count=count).reshape(shape if shape else ())
+            return a if strlen is not None else a.astype(dtype.newbyteorder("="))
         if ver != 3:
             raise NotImplementedError(f"data layout version {ver}")
         cls = r.u(1)
-        count = int(np.prod(shape)) if shape else 1
-        nbytes = count * dtype.itemsize
         if cls == 0:
             n = r.u(2)
             raw = r.raw(n)[:nbytes]

@@ -17,7 +17,7 @@ from circulantpreconditioner_b200 import med
 from circulantpreconditioner_b200 import meshes as MS
 
 REF = "/root/reference/meshes"
-pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference is not available here")
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference is not available here")
 
 # meshes/README.md: (file, nodes, cells)
 TABLE = [("3DHexaèdres/mesh_hexa_1.med", 27, 8), ("3DHexaèdres/mesh_hexa_2.med", 125, 64),
@@ -27,6 +27,7 @@ TABLE = [("3DHexaèdres/mesh_hexa_1.med", 27, 8), ("3DHexaèdres/mesh_hexa_2.med
          ("3DKershaw/Kershaw1.med", 729, 512), ("3DKershaw/Kershaw2.med", 4913, 4096)]
 
 
+@needs_ref
 def test_hdf5_tree_of_a_med_file():
     f = H.File(os.path.join(REF, "3DKershaw", "Kershaw1.med"))
     assert f.O == 8 and f.L == 8
@@ -54,6 +55,21 @@ def test_hdf5_tree_of_a_med_file():
     assert len(paths) == len(set(paths)) and any(p.startswith("/FAS/mesh/ELEME/") for p in paths)
 
 
+def test_old_style_hdf5_file_from_scipys_test_data():
+    """The other flavour of HDF5 -- superblock version 0 behind a 512-byte user block, a symbol-table group, version-1
+    object headers and attributes, layout message version 2 -- on the one such file this image holds: scipy's MATLAB 7.3
+    sample (testdouble = linspace(0, 2 pi, 9)).  The reference's .med files exercise the new-style structures."""
+    import scipy.io
+    p = os.path.join(os.path.dirname(scipy.io.__file__), "matlab", "tests", "data", "testhdf5_7.4_GLNX86.mat")
+    if not os.path.exists(p):
+        pytest.skip("scipy's test data is not installed")
+    f = H.File(p)
+    assert f.root.keys() == ["testdouble"]
+    d = f["testdouble"]
+    assert d.shape == (9, 1) and d.dtype == np.dtype("<f8") and d.attrs["MATLAB_class"] == "double"
+    assert np.allclose(d.read().ravel(), np.linspace(0.0, 2.0 * np.pi, 9), rtol=0, atol=1e-15)
+
+
 def test_not_hdf5(tmp_path):
     p = tmp_path / "x.med"
     p.write_bytes(b"$MeshFormat\n2.2 0 8\n")
@@ -61,6 +77,7 @@ def test_not_hdf5(tmp_path):
         H.File(str(p))
 
 
+@needs_ref
 @pytest.mark.parametrize("rel,nnodes,ncells", TABLE)
 def test_counts_of_the_reference_mesh_table(rel, nnodes, ncells):
     xyz, cells = med.read_med_mesh(os.path.join(REF, rel))
@@ -68,6 +85,7 @@ def test_counts_of_the_reference_mesh_table(rel, nnodes, ncells):
     assert np.allclose(xyz.min(axis=0), 0.0) and np.allclose(xyz.max(axis=0), 1.0)      # the unit cube
 
 
+@needs_ref
 @pytest.mark.parametrize("rel,fixture", [("3DHexaèdres/mesh_hexa_3.med", "hexa_3"),
                                          ("3DTetrahedra_Kershaw/3DKershawTetra1.med", "kershaw_tetra1")])
 def test_med_route_equals_gmsh_route(rel, fixture):
@@ -92,6 +110,7 @@ def test_med_route_equals_gmsh_route(rel, fixture):
     assert max(np.abs(got[k] - want[k]).max() for k in got) < 1e-14
 
 
+@needs_ref
 @pytest.mark.parametrize("name,rel,ncells,nfaces,nborder", [("kershaw1", "3DKershaw/Kershaw1.med", 512, 1344, 384),
                                                             ("kershaw2", "3DKershaw/Kershaw2.med", 4096, 11520, 1536)])
 def test_kershaw_fixtures_regenerate(name, rel, ncells, nfaces, nborder):
