@@ -205,12 +205,25 @@ def _child(_, fn_name, args, ret):
     ret["value"] = globals()[fn_name](*args)
 
 
+def _spawn(fn, args, nprocs, seconds=240):
+    """mp.spawn with a deadline: a hang (an exchange that never completes) ends as a failed test, not as a stuck suite."""
+    import time
+    ctx = mp.spawn(fn, args=args, nprocs=nprocs, join=False)
+    deadline = time.time() + seconds
+    while not ctx.join(timeout=5):
+        if time.time() > deadline:
+            for p in ctx.processes:
+                if p.is_alive():
+                    p.kill()
+            pytest.fail(f"timed out after {seconds} s")
+
+
 def _isolated(fn_name, *args):
     """Run a GPU test body in a fresh process: code that has never run on hardware must not be able to take the CUDA
     context of the pytest process (and with it every test that follows) down with it."""
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_child, args=(fn_name, args, ret), nprocs=1, join=True)
+    _spawn(_child, (fn_name, args, ret), 1)
     return ret["value"]
 
 
@@ -340,6 +353,6 @@ def test_pencil_grid_over_nccl(shape, pr, pc):
     mgr = mp.Manager()
     errs = mgr.dict()
     port = 29100 + (os.getpid() % 2000)
-    mp.spawn(_nccl_worker, args=(P, port, shape, pr, pc, b, want, errs), nprocs=P, join=True)
+    _spawn(_nccl_worker, (P, port, shape, pr, pc, b, want, errs), P)
     for r, (e1, e2) in dict(errs).items():
         assert e1 < 1e-12 and e2 < 1e-12, (r, e1, e2)
