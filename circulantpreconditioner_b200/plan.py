@@ -118,7 +118,8 @@ class CirculantPlan:
         self.np_dtype = {"c128": np.complex128, "c64": np.complex64, "f64": np.float64, "f32": np.float32}[dtype]
         self._id_buf = ctypes.create_string_buffer(nccl_id, len(nccl_id)) if nccl_id else None
         if stream is None and torch is not None and torch.cuda.is_available():
-            stream = torch.cuda.current_stream().cuda_stream
+            # torch's current stream of the device the plan will live on (a stream belongs to one device)
+            stream = (torch.cuda.current_stream(int(device)) if int(device) >= 0 else torch.cuda.current_stream()).cuda_stream
         d = _lib.PlanDesc(self.nx, self.ny, self.nz, self.ncomp, _lib.DTYPES[dtype], int(nranks), int(rank),
                           ctypes.cast(self._id_buf, ctypes.c_void_p) if self._id_buf else None,
                           ctypes.c_void_p(stream or 0), int(device))
