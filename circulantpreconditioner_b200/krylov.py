@@ -7,6 +7,8 @@ CUDA plan (`CirculantPlan.apply`) or, in tests, the CPU oracle.  Reference behav
                PETSc defaults otherwise: restart 30, left preconditioning, zero initial guess, classical Gram-Schmidt)
   operators    src/TransportEquation.cxx:75-133 (+ MatShift(A,1), tests/TransportEquation_...:117)
                src/WaveSystem.cxx:92-176        (+ MatShift(A,1), tests/WaveSystem_..._impl_mpi.cxx:127)
+               (pinned: tests/test_reference_assembly.py compiles those two files, unmodified, against a stand-in for the
+               SOLVERLAB mesh classes and compares the assembled matrices with these operators entry by entry)
 """
 from __future__ import annotations
 

@@ -1,0 +1,1 @@
+#include "solverlab_standin.hxx"
