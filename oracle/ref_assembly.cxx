@@ -15,6 +15,8 @@
 
 /* the reference's functions (declared in its headers TransportEquation2.hxx / WaveSystem.hxx) and the sound speed its
  * header defines as a global */
+void initial_conditions_shock(Mesh my_mesh, Field &Temperature_field);
+void initial_conditions_shock(Mesh my_mesh, Field &pressure_field, Field &velocity_field);
 void computeDivergenceMatrix(Mesh my_mesh, Mat *implMat, double dt, Vector vitesseTransport);
 void computeDivergenceMatrix(Mesh my_mesh, Mat *implMat, double dt);
 Matrix jacobianMatrices(Vector normal, double coeff);
@@ -32,7 +34,8 @@ static const char *group_name(int code)
 
 static Mesh make_mesh(int dim, int ncells, int nfaces, const int *cell_face_ptr, const int *cell_face_idx,
                       const double *cell_face_normal, const double *cell_measure, const double *cell_centre,
-                      const double *face_measure, const int *face_cells, const int *face_group, const int *face_twin)
+                      const double *face_measure, const int *face_cells, const int *face_group, const int *face_twin,
+                      const double *bbox = nullptr)
 {
     auto d = std::make_shared<StandinMeshData>();
     d->dim = dim;
@@ -50,7 +53,7 @@ static Mesh make_mesh(int dim, int ncells, int nfaces, const int *cell_face_ptr,
     d->face_cells.assign(face_cells, face_cells + 2 * (size_t)nfaces);
     d->face_twin.assign(face_twin, face_twin + nfaces);
     for (int f = 0; f < nfaces; ++f) d->face_group.push_back(group_name(face_group[f]));
-    for (int a = 0; a < 3; ++a) { d->lo[a] = 1e300; d->hi[a] = -1e300; }
+    for (int a = 0; a < 3; ++a) { d->lo[a] = bbox ? bbox[a] : 1e300; d->hi[a] = bbox ? bbox[3 + a] : -1e300; }
     return Mesh(d);
 }
 
@@ -104,4 +107,38 @@ REF_API int ref_jacobian_minus(int dim, const double *normal, double coeff, doub
     for (int i = 0; i <= dim; ++i)
         for (int j = 0; j <= dim; ++j) out[i * (dim + 1) + j] = M(i, j);
     return 0;
+}
+
+/* initial_conditions_shock of both files (src/TransportEquation.cxx:25-73, src/WaveSystem.cxx:25-82): the spherical step
+ * around the centre of the bounding box (bbox = xmin, ymin, zmin, xmax, ymax, zmax).  kind 0: out[ncells] = temperature;
+ * kind 1: out[ncells * (1 + dim)] = pressure, then the velocity components, per cell. */
+REF_API int ref_initial_conditions(int kind, int dim, int ncells, const double *cell_centre, const double *bbox, double *out)
+{
+    try {
+        auto d = std::make_shared<StandinMeshData>();
+        d->dim = dim;
+        d->cell_faces.resize((size_t)ncells);
+        d->cell_normals.resize((size_t)ncells);
+        d->cell_measure.assign((size_t)ncells, 1.0);
+        d->cell_centre.assign(cell_centre, cell_centre + 3 * (size_t)ncells);
+        for (int a = 0; a < 3; ++a) { d->lo[a] = bbox[a]; d->hi[a] = bbox[3 + a]; }
+        Mesh m(d);
+        if (kind == 0) {
+            Field T(ncells);
+            initial_conditions_shock(m, T);
+            for (int j = 0; j < ncells; ++j) out[j] = T(j);
+        } else {
+            /* (fields start from zero, as SOLVERLAB's do; the reference's `velocity_field[j,idim]=0` is a comma expression
+             * and only ever touches the first dim entries, src/WaveSystem.cxx:69) */
+            Field p(ncells), v(ncells, dim);
+            initial_conditions_shock(m, p, v);
+            for (int j = 0; j < ncells; ++j) {
+                out[(size_t)j * (dim + 1)] = p(j);
+                for (int c = 0; c < dim; ++c) out[(size_t)j * (dim + 1) + 1 + c] = v(j, c);
+            }
+        }
+        return 0;
+    } catch (const std::exception &) {
+        return 1;
+    }
 }

@@ -35,6 +35,7 @@ def lib():
         ip, dp, i, d = ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double), ctypes.c_int, ctypes.c_double
         L.ref_assemble.argtypes = [i, i, i, i, ip, ip, dp, dp, dp, dp, ip, ip, ip, d, dp, d, i, dp]
         L.ref_jacobian_minus.argtypes = [i, dp, d, d, dp]
+        L.ref_initial_conditions.argtypes = [i, i, i, dp, dp, dp]
         _LIB = L
     return _LIB
 
@@ -133,4 +134,20 @@ def jacobian_minus(normal, coeff, c0):
     out = np.zeros((dim + 1, dim + 1))
     lib().ref_jacobian_minus(dim, nrm.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), float(coeff), float(c0),
                              out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    return out
+
+
+def initial_conditions(kind, centres, lo, hi):
+    """initial_conditions_shock of src/TransportEquation.cxx ('transport': temperature per cell) or src/WaveSystem.cxx
+    ('wave': [pressure, velocity components] per cell) for cells with the given centres in the box lo .. hi."""
+    k = {"transport": 0, "wave": 1}[kind]
+    c = np.ascontiguousarray(centres, dtype=np.float64)
+    nc = len(c)
+    bbox = np.ascontiguousarray(list(lo) + list(hi), dtype=np.float64)
+    out = np.zeros(nc * (1 if k == 0 else 4), dtype=np.float64)
+    rc = lib().ref_initial_conditions(k, 3, nc, c.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                      bbox.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                      out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    if rc:
+        raise RuntimeError("reference initial condition failed")
     return out

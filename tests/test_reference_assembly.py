@@ -157,3 +157,21 @@ def test_transport_circulant_model_vs_the_references_matrix():
     assert np.allclose(np.diag(C)[idx], np.diag(A)[idx], atol=1e-14)
     mask = (A != 0) & ~np.eye(n, dtype=bool)
     assert np.allclose(C[mask], -A[mask], atol=1e-14)
+
+
+def test_spherical_explosion_initial_data():
+    """initial_conditions_shock of both reference files against the three restatements the tests and bench.py use for b
+    (oracle.spherical_step, krylov.spherical_step, meshes.spherical_step)."""
+    n = 16
+    k, j, i = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    cen = np.stack([(i.ravel() + 0.5) / n - 0.5, (j.ravel() + 0.5) / n - 0.5, (k.ravel() + 0.5) / n - 0.5], axis=1)
+    lo, hi = (-0.5,) * 3, (0.5,) * 3
+    T = RA.initial_conditions("transport", cen, lo, hi)
+    assert set(np.unique(T)) == {600.0, 650.0}
+    assert np.array_equal(T, O.spherical_step(n, n, n, 650.0, 600.0))
+    assert np.array_equal(T, K.spherical_step((n, n, n), 650.0, 600.0).numpy())
+    W = RA.initial_conditions("wave", cen, lo, hi).reshape(-1, 4)
+    assert np.array_equal(W[:, 0], O.spherical_step(n, n, n, 155e5, 70e5)) and np.all(W[:, 1:] == 0.0)
+    for name in ("kershaw1", "hexa_3"):
+        m = MS.load_fixture(name)
+        assert np.array_equal(RA.initial_conditions("transport", m["centre"], m["bbox"][0], m["bbox"][1]), MS.spherical_step(m))
