@@ -9,7 +9,7 @@ specification (version 3.0); covers exactly what those files use:
                     symbol table (B-tree v1 + local heap)
   object headers    version 1 and version 2 ("OHDR"), with continuation blocks
   datasets          contiguous, compact, and chunked (B-tree v1 index; deflate / shuffle filters) layouts, layout
-                    message versions 1-3; fixed-point, floating-point and fixed-length string types
+                    message versions 1-3; fixed-point, floating-point, fixed-length string and array types
   attributes        versions 1-3, scalar or simple dataspaces of the same types
 
 Anything else raises NotImplementedError instead of guessing.
@@ -409,6 +409,16 @@ class File:
             return np.dtype(f"{order}f{size}"), None
         if cls == 3:
             return np.dtype(f"S{size}"), size
+        if cls == 10:                                   # array of a base type (MED group names: 80 one-byte integers)
+            ver = cv >> 4
+            ndim = r.u(1)
+            if ver < 3:
+                r.skip(3)
+            dims = [r.u(4) for _ in range(ndim)]
+            if ver < 3:
+                r.skip(4 * ndim)                        # permutation indices
+            base, _ = self._datatype(body[r.p:])
+            return np.dtype((base, tuple(dims))), None
         raise NotImplementedError(f"datatype class {cls}")
 
     def _attribute(self, body):
@@ -461,8 +471,7 @@ class File:
                 raw = self._read_chunked(addr, dims[:-1], shape, dtype, msgs.get(0x0B))
             else:
                 raise NotImplementedError("data layout class")
-            a = np.frombuffer(raw, dtype=dtype, count=count).reshape(shape if shape else ())
-            return a if strlen is not None else a.astype(dtype.newbyteorder("="))
+            return self._as_array(raw, dtype, count, shape, strlen)
         if ver != 3:
             raise NotImplementedError(f"data layout version {ver}")
         cls = r.u(1)
@@ -480,7 +489,16 @@ class File:
             raw = self._read_chunked(btree, cdims[:-1], shape, dtype, msgs.get(0x0B))
         else:
             raise NotImplementedError("data layout class")
-        a = np.frombuffer(raw, dtype=dtype, count=count).reshape(shape if shape else ())
+        return self._as_array(raw, dtype, count, shape, strlen)
+
+    @staticmethod
+    def _as_array(raw, dtype, count, shape, strlen):
+        shape = tuple(shape) if shape else ()
+        if dtype.subdtype is not None:                  # array datatype: every element is a small array of the base type
+            base, sub = dtype.subdtype
+            a = np.frombuffer(raw, dtype=base, count=count * int(np.prod(sub))).reshape(shape + tuple(sub))
+            return a.astype(base.newbyteorder("="))
+        a = np.frombuffer(raw, dtype=dtype, count=count).reshape(shape)
         if strlen is not None:
             return a
         return a.astype(dtype.newbyteorder("="))

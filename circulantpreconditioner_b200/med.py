@@ -10,6 +10,8 @@ MED 3.x / 4.x layout (as found in the reference's files):
   /ENS_MAA/<mesh>/<step>/MAI/POE/IFN        polyhedra: cell -> first face, 1-based, n_cells + 1 entries
   /ENS_MAA/<mesh>/<step>/MAI/POE/INN        face -> first node in NOD, 1-based, n_faces + 1 entries
   /ENS_MAA/<mesh>/<step>/MAI/POE/NOD        node numbers of the faces, 1-based
+  /ENS_MAA/<mesh>/<step>/MAI/<geo>/FAM      family number of every entity (faces: TR3, QU4, POG; cells: TE4, HE8, POE)
+  /FAS/<mesh>/ELEME/<family>                attribute NUM = family number; GRO/NOM = its group names (80 chars each)
 """
 from __future__ import annotations
 
@@ -105,3 +107,25 @@ def fv_geometry(xyz, cells):
         if np.linalg.norm(net) > 1e-12 * surf[c]:
             raise ValueError(f"cell {c} is not closed (net area {net})")
     return centre, vol, surf, np.asarray(fc, dtype=np.int32), np.asarray(fa), len(seen)
+
+
+def read_med_families(path):
+    """({family number: [group names]}, {geometry: family number per entity}) of the first mesh of a MED file -- what
+    SOLVERLAB's `Face::getGroupName()` is made of (the reference's assemblies branch on it: src/WaveSystem.cxx:150-171
+    treats every border face outside the groups "Periodic" / "Neumann" as a wall)."""
+    f = hdf5_min.File(path)
+    name = f["ENS_MAA"].keys()[0]
+    steps = f["ENS_MAA"][name]
+    mai = steps[steps.keys()[0]]["MAI"]
+    families = {0: []}
+    fas = f["FAS"][name] if name in f["FAS"] else None
+    if fas is not None and "ELEME" in fas:
+        for fam in fas["ELEME"].keys():
+            g = fas["ELEME"][fam]
+            names = []
+            if "GRO" in g:
+                raw = g["GRO/NOM"].read().astype(np.uint8)
+                names = [bytes(row).split(b"\0")[0].decode("latin-1").strip() for row in raw.reshape(-1, raw.shape[-1])]
+            families[int(g.attrs["NUM"])] = names
+    per_geo = {geo: mai[geo]["FAM"].read().astype(np.int64) for geo in mai.keys() if "FAM" in mai[geo]}
+    return families, per_geo

@@ -128,3 +128,17 @@ def test_kershaw_fixtures_regenerate(name, rel, ncells, nfaces, nborder):
     # the one-call loader of the harness gives the same dictionary
     direct = MS.load_med(os.path.join(REF, rel))
     assert all(np.allclose(direct[k], fix[k], rtol=1e-14, atol=1e-16) for k in direct)
+
+
+@needs_ref
+def test_boundary_groups_of_the_reference_meshes():
+    """Family numbers and group names (what Face::getGroupName() returns in the reference's assemblies)."""
+    fam, per_geo = med.read_med_families(os.path.join(REF, "3DKershaw", "Kershaw1.med"))
+    assert fam[-2] == ["boundary"] and fam[0] == []
+    faces = per_geo["POG"]                               # 3 * 8 * 8 * 9 quadrilateral faces, the 6 * 8 * 8 border ones in "boundary"
+    assert len(faces) == 1728 and int((faces == -2).sum()) == 384 and int((faces == -1).sum()) == 1344
+    assert np.all(per_geo["POE"] == 0)
+    fam, per_geo = med.read_med_families(os.path.join(REF, "meshCube.med"))
+    sides = {names[0] for num, names in fam.items() if names}
+    assert sides == {"Bas", "Haut", "Gauche", "Droite", "Devant", "Derriere"}
+    assert len(per_geo["TR3"]) == 84 and set(np.unique(per_geo["TR3"])) <= set(fam)
