@@ -40,7 +40,8 @@ class PencilLayout(ctypes.Structure):
 
 class PencilStep(ctypes.Structure):
     _fields_ = [("kind", ctypes.c_int), ("dir", ctypes.c_int), ("a", ctypes.c_int64), ("b", ctypes.c_int64),
-                ("inner", ctypes.c_int64), ("scale", ctypes.c_double)]
+                ("inner", ctypes.c_int64), ("scale", ctypes.c_double), ("src_buf", ctypes.c_int), ("dst_buf", ctypes.c_int),
+                ("src_buf_staged", ctypes.c_int), ("dst_buf_staged", ctypes.c_int)]
 
 
 # every symbol include/circulantpc.h declares: name -> (restype, argtypes)

@@ -412,10 +412,13 @@ int cpc_pencil_steps(int nx, int ny, int nz, int p_rows, int p_cols, int rank, c
     *nsteps = (int)s.size();
     if (!steps) return CPC_OK;
     if (max_steps < (int)s.size()) { set_error("cpc_pencil_steps: %d steps, room for %d", (int)s.size(), max_steps); return CPC_ERR_ARG; }
+    const std::vector<PencilBuffers> dev = pencil_buffer_plan(s, false, nullptr), stg = pencil_buffer_plan(s, true, nullptr);
     for (size_t k = 0; k < s.size(); ++k) {
         steps[k].kind = s[k].kind; steps[k].dir = s[k].dir;
         steps[k].a = s[k].A; steps[k].b = s[k].B; steps[k].inner = s[k].inner;
         steps[k].scale = s[k].scale;
+        steps[k].src_buf = dev[k].src; steps[k].dst_buf = dev[k].dst;
+        steps[k].src_buf_staged = stg[k].src; steps[k].dst_buf_staged = stg[k].dst;
     }
     return CPC_OK;
 }

@@ -108,6 +108,29 @@ inline std::vector<PencilStep> pencil_schedule(const PencilLayout &L)
     return s;
 }
 
+// Which array every step reads and writes.  Device arrays: the first step reads the caller's b, the last one writes the
+// caller's x (b == x is fine: b is only read by the first step, x only written by the last).  Host arrays are staged:
+// b is copied into W0 first, the result is copied out of *final_buf afterwards.  A pass runs in place on a work buffer;
+// a SWAP or an all-to-all moves the data to the other work buffer.
+enum PencilBufferId { PBUF_B = 0, PBUF_W0 = 1, PBUF_W1 = 2, PBUF_X = 3 };
+struct PencilBuffers { int src, dst; };
+inline std::vector<PencilBuffers> pencil_buffer_plan(const std::vector<PencilStep> &s, bool staged, int *final_buf)
+{
+    std::vector<PencilBuffers> out;
+    int cur = staged ? PBUF_W0 : PBUF_B;
+    for (size_t k = 0; k < s.size(); ++k) {
+        const bool pass = s[k].kind == PSTEP_PASS_X || s[k].kind == PSTEP_PASS_Y || s[k].kind == PSTEP_MIDDLE;
+        int dst;
+        if (k + 1 == s.size() && !staged) dst = PBUF_X;
+        else if (pass && cur != PBUF_B) dst = cur;
+        else dst = cur == PBUF_W0 ? PBUF_W1 : PBUF_W0;
+        out.push_back(PencilBuffers{ cur, dst });
+        cur = dst;
+    }
+    if (final_buf) *final_buf = cur;
+    return out;
+}
+
 // source element of output element o of SWAP(A, B, inner): out[b][a][t] = in[a][b][t]
 #if defined(__CUDACC__)
 __host__ __device__

@@ -38,9 +38,12 @@ template <typename T> struct PencilPlanT : PlanBase, PencilIface {
     DistState dist;
     bool loopback = false;         // no NCCL id: the exchanges are done by cpc_pencil_apply_lockstep
     int pr = 1, pc = 1;
+    // which array every step reads / writes (pencil_buffer_plan), for device arrays and for staged host arrays
+    std::vector<PencilBuffers> bufplan[2];
+    int final_buf[2] = { PBUF_X, PBUF_W0 };
     // state of the apply in flight
-    const C *src = nullptr;
-    C *final_out = nullptr;
+    const void *arr[4] = { nullptr, nullptr, nullptr, nullptr };     // PBUF_B, PBUF_W0, PBUF_W1, PBUF_X
+    int staged = 0;
     void *host_out = nullptr;
 
     PencilPlanT(int pr_, int pc_) : pr(pr_), pc(pc_) {}
@@ -79,6 +82,7 @@ template <typename T> struct PencilPlanT : PlanBase, PencilIface {
         }
         if (rc0) { set_error("pencil plans: bad grid or rank"); return CPC_ERR_ARG; }
         sched = pencil_schedule(L);
+        for (int st = 0; st < 2; ++st) bufplan[st] = pencil_buffer_plan(sched, st != 0, &final_buf[st]);
         int rc;
         if ((rc = make_sub(0, L.nx, L.nyl, L.nzl))) return rc;
         if ((rc = make_sub(1, L.nxl, L.ny, L.nzl))) return rc;
@@ -144,8 +148,6 @@ template <typename T> struct PencilPlanT : PlanBase, PencilIface {
     size_t elem_bytes() const override { return sizeof(C); }
     bool in_process() const override { return loopback || desc.nranks == 1; }
 
-    C *other_of(const C *p) const { return p == buf[0] ? buf[1] : buf[0]; }
-
     int begin(const void *b, void *x, int mem_kind) override
     {
         if (symbol_kind != CPC_SYMBOL_SEPARABLE) { set_error("cpc_apply: no symbol set (call cpc_set_symbol_* first)"); return CPC_ERR_STATE; }
@@ -153,69 +155,60 @@ template <typename T> struct PencilPlanT : PlanBase, PencilIface {
         if (mem_kind != CPC_MEM_DEVICE && mem_kind != CPC_MEM_HOST) { set_error("bad mem_kind %d", mem_kind); return CPC_ERR_ARG; }
         CPC_CUDA(cudaSetDevice(device));
         for (auto *s : sub) s->stream = stream;
+        arr[PBUF_W0] = buf[0];
+        arr[PBUF_W1] = buf[1];
         if (mem_kind == CPC_MEM_HOST) {
             CPC_CUDA(cudaMemcpyAsync(buf[0], b, sizeof(C) * (size_t)L.nloc, cudaMemcpyHostToDevice, stream));
             h2d_bytes += sizeof(C) * (size_t)L.nloc;
-            src = buf[0];
-            final_out = nullptr;
+            staged = 1;
+            arr[PBUF_B] = arr[PBUF_X] = nullptr;        // never touched by the staged plan
             host_out = x;
         } else {
-            src = (const C *)b;
-            final_out = (C *)x;
+            staged = 0;
+            arr[PBUF_B] = b;
+            arr[PBUF_X] = x;
             host_out = nullptr;
         }
         return CPC_OK;
     }
 
-    // where the step after `src` writes: the caller's x for the last step, the array itself for a pass (unless the
-    // array is the caller's b), the other work buffer otherwise
-    C *target(size_t k, bool in_place_ok) const
-    {
-        if (k + 1 == sched.size() && final_out) return final_out;
-        const bool ours = (src == buf[0] || src == buf[1]);
-        if (in_place_ok && ours) return (C *)src;
-        return ours ? other_of(src) : buf[0];
-    }
+    const C *src_of(size_t k) const { return (const C *)arr[bufplan[staged][k].src]; }
+    C *dst_of(size_t k) const { return (C *)arr[bufplan[staged][k].dst]; }
 
     int local_step(size_t k) override
     {
         const PencilStep &s = sched[k];
         int rc = CPC_OK;
         CPC_CUDA(cudaSetDevice(device));        // (cpc_pencil_apply_lockstep may drive plans on several devices)
+        const C *src = src_of(k);
+        C *out = dst_of(k);
         if (s.kind == PSTEP_SWAP) {
-            C *out = target(k, false);
             const long long total = s.A * s.B * s.inner;
             const long long want = (total + 255) / 256;
             const int grid = (int)(want < 148ll * 16 ? (want > 0 ? want : 1) : 148ll * 16);
             pencil_swap_kernel<C><<<grid, 256, 0, stream>>>(src, out, s.A, s.B, s.inner, total, s.scale);
             ++launches;
             CPC_CUDA(cudaGetLastError());
-            src = out;
             return CPC_OK;
         }
-        C *out = target(k, true);
         if (s.kind == PSTEP_PASS_X) rc = sub[0]->run_pass(0, s.dir < 0 ? MODE_FWD : MODE_INV, src, out, 0, L.nzl, 0, stream);
         else if (s.kind == PSTEP_PASS_Y) rc = sub[1]->run_pass(1, s.dir < 0 ? MODE_FWD : MODE_INV, src, out, 0, L.nzl, 0, stream);
         else if (s.kind == PSTEP_MIDDLE) rc = sub[2]->run_pass(2, sub[2]->fused_mode(), src, out, 0, L.nz, 0, stream);
         else { set_error("pencil schedule: step %d is not a local step", (int)k); return CPC_ERR_STATE; }
-        if (rc) return rc;
-        src = out;
-        return CPC_OK;
+        return rc;
     }
 
     int exchange_buffers(size_t k, const void **send, void **recv) override
     {
-        C *out = target(k, false);
-        *send = src;
-        *recv = out;
-        src = out;
+        *send = src_of(k);
+        *recv = dst_of(k);
         return CPC_OK;
     }
 
     int finish() override
     {
         if (host_out) {
-            CPC_CUDA(cudaMemcpyAsync(host_out, src, sizeof(C) * (size_t)L.nloc, cudaMemcpyDeviceToHost, stream));
+            CPC_CUDA(cudaMemcpyAsync(host_out, arr[final_buf[1]], sizeof(C) * (size_t)L.nloc, cudaMemcpyDeviceToHost, stream));
             d2h_bytes += sizeof(C) * (size_t)L.nloc;
             CPC_CUDA(cudaStreamSynchronize(stream));
         }

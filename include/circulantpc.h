@@ -238,6 +238,11 @@ typedef struct {
     int kind, dir;
     int64_t a, b, inner;
     double scale;
+    int src_buf, dst_buf;          /* which array the step reads / writes when b and x are device arrays: 0 = the caller's b,
+                                      1 / 2 = the plan's two work buffers, 3 = the caller's x (passes run in place on a work
+                                      buffer; b is read by the first step only, x written by the last only, so b == x works) */
+    int src_buf_staged, dst_buf_staged;   /* the same for host arrays: b is copied into buffer 1 first, the result is copied
+                                      out of the last step's dst afterwards */
 } cpc_pencil_step_t;
 int cpc_pencil_steps(int nx, int ny, int nz, int p_rows, int p_cols, int rank, cpc_pencil_step_t *steps, int max_steps,
                      int *nsteps);

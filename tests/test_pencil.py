@@ -76,27 +76,48 @@ def test_schedule_on_virtual_ranks(shape, pr, pc):
     lays = [cpc.pencil_layout(nx, ny, nz, pr, pc, r) for r in range(P)]
     steps = [cpc.pencil_steps(nx, ny, nz, pr, pc, r) for r in range(P)]
     assert all(len(s) == len(steps[0]) and [t["kind"] for t in s] == [t["kind"] for t in steps[0]] for s in steps)
-    loc = [_x_pencil(b, shape, lays[r]).ravel() for r in range(P)]
-    assert all(a.size == lays[r]["local_elems"] == nx * ny * nz // P for r, a in enumerate(loc))
-    for k, st in enumerate(steps[0]):
-        if st["kind"] in (_lib.PSTEP_A2A_ROW, _lib.PSTEP_A2A_COL):
-            new = [np.empty_like(a) for a in loc]
-            for r in range(P):
-                peers = cpc.pencil_group(nx, ny, nz, pr, pc, r, st["kind"])
-                assert r in peers and len(peers) == (pr if st["kind"] == _lib.PSTEP_A2A_ROW else pc)
-                chunk = loc[r].size // len(peers)
-                me = peers.index(r)
-                for q, peer in enumerate(peers):
-                    assert cpc.pencil_group(nx, ny, nz, pr, pc, peer, st["kind"]) == peers     # same list on every member
-                    new[peer][me * chunk:(me + 1) * chunk] = loc[r][q * chunk:(q + 1) * chunk]
-            loc = new
-        else:
-            loc = [_local_step(loc[r], steps[r][k], shape, lays[r], tabs) for r in range(P)]
-    for r in range(P):
-        lay = lays[r]
-        got = loc[r].reshape(lay["nzl"], lay["nyl"], nx)
-        ref = want[lay["z0"]:lay["z0"] + lay["nzl"], lay["y0"]:lay["y0"] + lay["nyl"], :]
-        assert rel_l2(got, ref) < 1e-12, (r, rel_l2(got, ref))
+    nloc = nx * ny * nz // P
+    assert all(lays[r]["local_elems"] == nloc for r in range(P))
+    # The plan's arrays, as the library numbers them: 0 = the caller's b, 1 / 2 = the two work buffers, 3 = the caller's x.
+    # Three runs: device arrays, device arrays with b == x (in place), host arrays (staged through buffer 1).
+    for mode in ("device", "aliased", "staged"):
+        sk, dk = ("src_buf_staged", "dst_buf_staged") if mode == "staged" else ("src_buf", "dst_buf")
+        bufs = []
+        for r in range(P):
+            b_loc = _x_pencil(b, shape, lays[r]).ravel()
+            x_loc = b_loc if mode == "aliased" else np.full(nloc, np.nan + 0j)
+            w0 = b_loc.copy() if mode == "staged" else np.full(nloc, np.nan + 0j)
+            bufs.append({0: None if mode == "staged" else b_loc, 1: w0, 2: np.full(nloc, np.nan + 0j),
+                         3: None if mode == "staged" else x_loc})
+        b_before = [None if mode != "device" else bufs[r][0].copy() for r in range(P)]
+        for k, st in enumerate(steps[0]):
+            src, dst = st[sk], st[dk]
+            assert all(steps[r][k][sk] == src and steps[r][k][dk] == dst for r in range(P))
+            assert dst != 0                                            # the caller's b is never written
+            if st["kind"] in (_lib.PSTEP_A2A_ROW, _lib.PSTEP_A2A_COL):
+                assert src != dst
+                for r in range(P):
+                    peers = cpc.pencil_group(nx, ny, nz, pr, pc, r, st["kind"])
+                    assert r in peers and len(peers) == (pr if st["kind"] == _lib.PSTEP_A2A_ROW else pc)
+                    chunk = nloc // len(peers)
+                    me = peers.index(r)
+                    for q, peer in enumerate(peers):
+                        assert cpc.pencil_group(nx, ny, nz, pr, pc, peer, st["kind"]) == peers     # same list on every member
+                        bufs[peer][dst][me * chunk:(me + 1) * chunk] = bufs[r][src][q * chunk:(q + 1) * chunk]
+            else:
+                if st["kind"] == _lib.PSTEP_SWAP:
+                    assert src != dst                                  # the reordering kernel cannot run in place
+                for r in range(P):
+                    bufs[r][dst][:] = _local_step(bufs[r][src], steps[r][k], shape, lays[r], tabs)
+        final = steps[0][-1][dk]
+        assert mode == "staged" or final == 3                          # device arrays: the last step writes the caller's x
+        for r in range(P):
+            lay = lays[r]
+            got = bufs[r][final].reshape(lay["nzl"], lay["nyl"], nx)
+            ref = want[lay["z0"]:lay["z0"] + lay["nzl"], lay["y0"]:lay["y0"] + lay["nyl"], :]
+            assert rel_l2(got, ref) < 1e-12, (mode, r, rel_l2(got, ref))
+            if mode == "device":
+                assert np.array_equal(bufs[r][0], b_before[r])         # b untouched when x is another array
     # the plan's bookkeeping: 5 transform passes (fewer on degenerate axes) + 6 reorderings + 4 exchanges
     kinds = [t["kind"] for t in steps[0]]
     assert kinds.count(_lib.PSTEP_SWAP) == 6 and kinds.count(_lib.PSTEP_A2A_ROW) == 2 and kinds.count(_lib.PSTEP_A2A_COL) == 2
@@ -163,13 +184,17 @@ def _gloo_worker(rank, P, port, shape, pr, pc, b_full, ret):
     nx, ny, nz = shape
     lay = cpc.pencil_layout(nx, ny, nz, pr, pc, rank)
     tabs = _tables(shape, LAM)
-    a = _x_pencil(b_full, shape, lay).ravel()
+    nloc = lay["local_elems"]
+    bufs = {0: _x_pencil(b_full, shape, lay).ravel(), 1: np.zeros(nloc, complex), 2: np.zeros(nloc, complex),
+            3: np.zeros(nloc, complex)}
     for st in cpc.pencil_steps(nx, ny, nz, pr, pc, rank):
+        src, dst = st["src_buf"], st["dst_buf"]
         if st["kind"] in (_lib.PSTEP_A2A_ROW, _lib.PSTEP_A2A_COL):
             peers = cpc.pencil_group(nx, ny, nz, pr, pc, rank, st["kind"])
-            a = _group_alltoall(torch.from_numpy(np.ascontiguousarray(a)), peers, rank, P).numpy()
+            bufs[dst][:] = _group_alltoall(torch.from_numpy(np.ascontiguousarray(bufs[src])), peers, rank, P).numpy()
         else:
-            a = _local_step(a, st, shape, lay, tabs)
+            bufs[dst][:] = _local_step(bufs[src], st, shape, lay, tabs)
+    a = bufs[3]
     parts = [None] * P
     dist.all_gather_object(parts, (rank, a))
     if rank == 0:
