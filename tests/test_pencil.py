@@ -248,7 +248,7 @@ def _isolated(fn_name, *args):
     context of the pytest process (and with it every test that follows) down with it."""
     mgr = mp.Manager()
     ret = mgr.dict()
-    _spawn(_child, (fn_name, args, ret), 1)
+    _spawn(_child, (fn_name, args, ret), 1, seconds=120)
     return ret["value"]
 
 
