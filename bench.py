@@ -175,7 +175,11 @@ def cpu_baseline_block(b_host=None, x_gpu_host=None):
 
 
 def run_reference(args):
-    """The reference's CPU path (restated: oracle) on the box's host cores, same 512^3 config at every N; rank 0 only."""
+    """The reference's CPU path (restated: oracle) on the box's host cores, same 512^3 config at every N; rank 0 only.
+
+    kind stays "port": oracle/_ref does hold the reference's own src/FftLinearSolver_3D.c, but compiled against a stand-in
+    for PETSc whose MATFFTW is a direct O(n^2) DFT (oracle/petsc_standin/) -- a checker for parity, not a stand-in for
+    FFTW's speed; timing it would misstate the reference by orders of magnitude."""
     if int(os.environ.get("RANK", "0")) != 0:
         return 0
     from oracle import circulant_oracle as O
