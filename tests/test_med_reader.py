@@ -3,7 +3,7 @@
 BASELINE config 5 names the polyhedral Kershaw meshes, which the reference ships as MED (HDF5) only
 (meshes/3DKershaw/Kershaw{1,2}.med) and reads through SOLVERLAB / MEDCoupling / MEDfile / HDF5
 (tests/TransportEquation_SphericalExplosion_impl_mpi.cxx:221-255) -- none of them in this image.  The reader is pinned
-two ways: (1) against the reference's mesh table (meshes/README.md: node and cell counts of every family); (2) against the
+two ways: (1) against the reference's mesh table (meshes/README.md: node and cell counts of every .med file it ships); (2) against the
 independent Gmsh text siblings of the same meshes (tests/golden/make_mesh_fixtures.py): the MED route and the .msh route
 must give the same finite-volume geometry.  Needs /root/reference (this container; the GPU box only uses the fixtures).
 """
@@ -22,8 +22,12 @@ needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="/root/reference i
 # meshes/README.md: (file, nodes, cells)
 TABLE = [("3DHexaèdres/mesh_hexa_1.med", 27, 8), ("3DHexaèdres/mesh_hexa_2.med", 125, 64),
          ("3DHexaèdres/mesh_hexa_3.med", 729, 512), ("3DHexaèdres/mesh_hexa_4.med", 4913, 4096),
+         ("3DHexaèdres/mesh_hexa_5.med", 35937, 32768),
          ("3DTetrahedra/mesh_tetra_0.med", 80, 215), ("3DTetrahedra/mesh_tetra_1.med", 488, 2003),
-         ("3DTetrahedra_Kershaw/3DKershawTetra1.med", 3865, 11072),
+         ("3DTetrahedra/mesh_tetra_2.med", 857, 3898), ("3DTetrahedra/mesh_tetra_3.med", 1601, 7711),
+         ("3DTetrahedra/mesh_tetra_4.med", 2997, 15266), ("3DTetrahedra/mesh_tetra_5.med", 5692, 30480),
+         ("3DTetrahedra/mesh_tetra_6.med", 10994, 61052),
+         ("3DTetrahedra_Kershaw/3DKershawTetra1.med", 3865, 11072), ("3DTetrahedra_Kershaw/3DKershawTetra2.med", 31793, 93440),
          ("3DKershaw/Kershaw1.med", 729, 512), ("3DKershaw/Kershaw2.med", 4913, 4096)]
 
 
